@@ -1,0 +1,188 @@
+/*
+ * ldpc_b200.h -- C-ABI of the B200-native neural min-sum (NMS) LDPC decode / Monte-Carlo path.
+ *
+ * This is the drop-in boundary for the ONE hot path of ghy1228/LDPC_Error_Floor:
+ *   sess.run(net_dict["ya_output_all"], feed_dict={xa, ya, ...})     Print_Functions.py:148-151
+ *   Print_Functions.compute_results(...)                             Print_Functions.py:130-165
+ *   Print_Functions.create_mix_epoch(...)                            Print_Functions.py:29-72
+ *   Main_Functions.init_parameter / init_connecting_matrix           Main_Functions.py:8-150
+ * The reference has no FFI of its own (pure Python on TensorFlow); each entry point below
+ * cites the reference interface it replaces.  INTEGRATION.md shows the ctypes stub a
+ * reference maintainer would add.
+ *
+ * Conventions: plain pointers and sizes only; every function returns 0 or a negative
+ * LDPC_E_* code, never throws, never exits; `*_dev` pointers are caller-owned device
+ * allocations on the handle's device; `stream` is a cudaStream_t passed as void*
+ * (NULL = legacy default stream); launches are asynchronous w.r.t. the host unless noted;
+ * handles are immutable after creation and may be shared across streams.
+ * There is NO CPU fallback: without a CUDA device every compute entry point fails with
+ * LDPC_E_CUDA.
+ */
+#ifndef LDPC_B200_H
+#define LDPC_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define LDPC_OK 0
+#define LDPC_E_INVALID (-1)   /* bad argument (the reference prints and sys.exit()s, Main_Functions.py:503-521) */
+#define LDPC_E_UNSUPPORTED (-2)
+#define LDPC_E_CUDA (-3)      /* CUDA runtime error; text via ldpc_last_error() */
+#define LDPC_E_ALLOC (-4)
+#define LDPC_E_LIMIT (-5)     /* graph exceeds compiled table limits */
+
+typedef struct ldpc_graph ldpc_graph_t;       /* compiled base graph (host tables) */
+typedef struct ldpc_decoder ldpc_decoder_t;   /* graph + weights + arithmetic mode on one device */
+
+/* Result of the base-graph compiler.  Replaces the scalars returned by
+ * Main_Functions.init_parameter (Main_Functions.py:8-38). */
+typedef struct {
+    int32_t M, N, z, E;          /* proto rows / cols, lifting size, proto edges */
+    int32_t max_dc, max_dv;      /* largest proto row / column degree */
+    int32_t n_ref, k_ref;        /* n, k exactly as the reference computes them, incl. the "+1"
+                                    when no puncturing/shortening is configured (:24-28) */
+    int32_t n_true, k_true;      /* transmitted / information bits without that quirk */
+    double rate_ref, rate_true;  /* k/n both ways; the reference's sigma uses rate_ref (:29,:36) */
+} ldpc_graph_info_t;
+
+/* Per-SNR-point Monte-Carlo counters (uint64 each).  Replaces the float32 Results[4,nSNR]
+ * accumulators of Print_Functions.compute_results (:133, :158-161). */
+enum {
+    LDPC_CNT_FRAMES = 0,       /* frames decoded */
+    LDPC_CNT_FRAME_ERR_LAST,   /* FER_last numerator: last-iteration hard decision != codeword (:115-116) */
+    LDPC_CNT_FRAME_ERR_ANY,    /* FER numerator: never correct at ANY executed iteration (:105-111) */
+    LDPC_CNT_BIT_ERR_LAST,     /* BER_last numerator (:112-113) */
+    LDPC_CNT_ITERS,            /* sum of iterations executed (== frames*T without early termination) */
+    LDPC_CNT_SYND_FAIL,        /* final hard decision violates a parity check (detected failure) */
+    LDPC_CNT_UNDETECTED,       /* final hard decision is a codeword but not the transmitted one */
+    LDPC_CNT_HARVESTED,        /* words that met the harvest criterion (may exceed the buffer capacity) */
+    LDPC_NUM_COUNTERS
+};
+
+/* flags[] bits written by ldpc_decode */
+#define LDPC_FLAG_SYND_OK 1u      /* output hard decision satisfies every check */
+#define LDPC_FLAG_UNCOR_ANY 2u    /* never equal to the all-zero codeword at any executed iteration (D9 uncor_flag) */
+#define LDPC_FLAG_UNCOR_LAST 4u   /* output hard decision != all-zero codeword */
+#define LDPC_FLAG_SYND_OK_EVER 8u /* some iteration's hard decision satisfied every check */
+
+/* harvest criteria for ldpc_mc_run */
+#define LDPC_HARVEST_NONE 0
+#define LDPC_HARVEST_UNCOR_ANY 1   /* the reference's criterion (Print_Functions.py:155-156) */
+#define LDPC_HARVEST_UNCOR_LAST 2
+#define LDPC_HARVEST_SYND_FAIL 3
+
+const char *ldpc_last_error(void);   /* thread-local text of the last failure */
+int ldpc_version(void);
+
+/* ---- base-graph compiler -------------------------------------------------------------
+ * proto: M x N int32, row-major, -1 = no edge else circulant shift (used mod z); z = 1 for
+ * non-QC codes (MacKay / BCH / Polar: entries 0 / -1).  punct/short ranges are 1-based
+ * inclusive bit indices, 0,0 = none (main_Base.py:31-34).
+ * Replaces init_parameter + init_connecting_matrix (Main_Functions.py:8-150): instead of
+ * dense (E*z)^2 permutation matrices it emits circulant shift tables in E(C) (row-major)
+ * order and a column-sorted CSR edge list. */
+int ldpc_graph_create(const int32_t *proto, int32_t M, int32_t N, int32_t z, int32_t punct_start,
+                      int32_t punct_end, int32_t short_start, int32_t short_end, ldpc_graph_t **out);
+int ldpc_graph_destroy(ldpc_graph_t *g);
+int ldpc_graph_info(const ldpc_graph_t *g, ldpc_graph_info_t *info);
+/* edge tables, each E int32 in E(C) order (any may be NULL): proto row, proto column, shift */
+int ldpc_graph_edges(const ldpc_graph_t *g, int32_t *row, int32_t *col, int32_t *shift);
+/* sigma[i] = sqrt(1 / (2 * R * 10^(snr_db[i]/10))), R = rate_ref (use_ref_rate != 0, the
+ * reference's value, Main_Functions.py:35-36) or rate_true. */
+int ldpc_graph_sigma(const ldpc_graph_t *g, const double *snr_db, int32_t n, int32_t use_ref_rate,
+                     double *sigma);
+
+/* ---- decoder handle ------------------------------------------------------------------
+ * sharing[3] = {CN, UCN, VN} codes as in main_Base.py:24-25 (0 none, 1 per edge (E(C) order),
+ * 2 per proto node, 3 one scalar per iteration); rules of check_params apply
+ * (Main_Functions.py:515-521).  w_cn / w_ucn / w_vn: HOST float32 [T, width], width =
+ * 1 / M (CN,UCN) or N (VN) / E by code (Main_Functions.py:397-405); NULL when the code is 0.
+ * decoding_type 1 = min-sum (float32 messages, clip +-clip_llr), 2 = quantised min-sum
+ * (q_bit in {5,6,-5,4,3}, Main_Functions.py:483-492).  Replaces weight_init
+ * (Main_Functions.py:387-439) + the graph constants of build_neural_network. */
+int ldpc_decoder_create(const ldpc_graph_t *g, const int32_t sharing[3], int32_t T,
+                        const float *w_cn, const float *w_ucn, const float *w_vn,
+                        int32_t decoding_type, int32_t q_bit, float clip_llr, int32_t device,
+                        ldpc_decoder_t **out);
+int ldpc_decoder_destroy(ldpc_decoder_t *d);
+/* 1 if the packed-fp16x2 kernel serves this decoder, 0 if the float32 kernel does */
+int ldpc_decoder_uses_packed_kernel(const ldpc_decoder_t *d);
+/* frames decoded per CTA and CTAs per SM the launcher will use (for sizing batches) */
+int ldpc_decoder_geometry(const ldpc_decoder_t *d, int32_t *frames_per_cta, int32_t *ctas_per_sm,
+                          int32_t *threads_per_cta, int32_t *smem_bytes);
+
+/* ---- decode --------------------------------------------------------------------------
+ * Replaces sess.run(ya_output_all / ya_output{t}) (Print_Functions.py:148-151, main_Base.py:160).
+ *   llr_dev      f32 [B, N*z]  channel LLRs log(p1/p0), bit index j*z+c (== xa[B,N,z] flattened)
+ *   iters        iterations to run, 1..T (0 = T)
+ *   early_term   0: run all iterations (reference behaviour); 1: stop a frame at the first
+ *                iteration whose hard decision satisfies every check
+ *   app_dev      f32, NULL | [B, N*z] (app_all_iters == 0: APP of the output iteration) |
+ *                [iters, B, N*z] (app_all_iters != 0: ya_output_all, Main_Functions.py:380-383;
+ *                rows of iterations after a frame's early stop are left untouched)
+ *   hard_dev     u32 [B, ceil(N*z/32)]  bit k of a frame = (APP[k] >= 0) at word k/32, bit k%32
+ *   iters_dev    i32 [B]  iterations until the first zero syndrome (also reported when
+ *                early_term == 0), or `iters` if none
+ *   flags_dev    u8  [B]  LDPC_FLAG_*
+ *   biterr_dev   i32 [B]  ones in the output hard decision (bit errors vs the all-zero word)
+ * Any output pointer may be NULL. */
+int ldpc_decode(const ldpc_decoder_t *d, const float *llr_dev, int64_t B, int32_t iters,
+                int32_t early_term, float *app_dev, int32_t app_all_iters, uint32_t *hard_dev,
+                int32_t *iters_dev, uint8_t *flags_dev, int32_t *biterr_dev, void *stream);
+
+/* Same with HOST buffers: pinned or pageable host memory in and out, chunked over two
+ * streams so copies overlap compute; synchronous.  This is the end-to-end call. */
+int ldpc_decode_host(const ldpc_decoder_t *d, const float *llr_host, int64_t B, int32_t iters,
+                     int32_t early_term, float *app_host, int32_t app_all_iters,
+                     uint32_t *hard_host, int32_t *iters_host, uint8_t *flags_host,
+                     int32_t *biterr_host);
+
+/* ---- channel-sample generator ----------------------------------------------------------
+ * Replaces Print_Functions.create_mix_epoch (:29-72) for the all-zero codeword:
+ * llr = 2*(sigma*n - 1)/sigma^2, n ~ N(0,1) from Philox4x32-10 (key = seed, counter =
+ * (global frame index, bit-quad index)) + Box-Muller; quantised if the decoder is QMS;
+ * punctured bits -> 0, shortened bits -> -clip_llr.  Frame f of this call is global frame
+ * frame_offset + f, so shards on different ranks draw disjoint, world-size-independent
+ * streams.  ldpc_mc_run draws exactly the same samples. */
+int ldpc_llr_generate(const ldpc_decoder_t *d, double sigma, int64_t n_frames, uint64_t seed,
+                      uint64_t frame_offset, float *llr_dev, void *stream);
+
+/* ---- fused Monte-Carlo ---------------------------------------------------------------------
+ * Replaces Print_Functions.compute_results (:130-165) for one SNR point: generate, decode,
+ * count, harvest, all on the device.  counters_dev: u64[LDPC_NUM_COUNTERS], ACCUMULATED
+ * into (zero them first).  uncor_buf_dev: f32 [uncor_capacity, N*z] decoder-input LLRs of
+ * harvested words (NULL/0 = none), uncor_count_dev: u32 running count (accumulated; rows
+ * beyond the capacity are counted but dropped). */
+int ldpc_mc_run(const ldpc_decoder_t *d, double sigma, int64_t n_frames, uint64_t seed,
+                uint64_t frame_offset, int32_t iters, int32_t early_term, int32_t harvest_mode,
+                uint64_t *counters_dev, float *uncor_buf_dev, uint32_t *uncor_count_dev,
+                uint32_t uncor_capacity, void *stream);
+
+/* Host-buffer twin of ldpc_mc_run: counters_host u64[LDPC_NUM_COUNTERS] (overwritten),
+ * uncor_host f32 [uncor_capacity, N*z], *n_uncor_host = rows written.  Synchronous. */
+int ldpc_mc_run_host(const ldpc_decoder_t *d, double sigma, int64_t n_frames, uint64_t seed,
+                     uint64_t frame_offset, int32_t iters, int32_t early_term,
+                     int32_t harvest_mode, uint64_t *counters_host, float *uncor_host,
+                     uint32_t uncor_capacity, uint32_t *n_uncor_host);
+
+/* ---- post decoder ----------------------------------------------------------------------
+ * Replaces main_Post.py's use of the same graph on Inputs/[Uncor]_* words
+ * (main_Post.py:25-38; Print_Functions.read_uncor_llr :6-10): `post` is a decoder built
+ * from the boosted weight set (base rows followed by post rows); the words are re-decoded
+ * from their channel LLRs, which is the reference semantic.  uncor_dev holds
+ * n_words rows of N*z decoder-input LLRs, e.g. the buffer ldpc_mc_run filled.  counters_dev
+ * as in ldpc_mc_run (accumulated); other outputs as in ldpc_decode. */
+int ldpc_post_decode(const ldpc_decoder_t *post, const float *uncor_dev, int64_t n_words,
+                     int32_t iters, int32_t early_term, uint64_t *counters_dev, uint32_t *hard_dev,
+                     int32_t *iters_dev, uint8_t *flags_dev, void *stream);
+
+/* kernels launched by this library since load (for bench.py's gpu_launches) */
+uint64_t ldpc_launch_count(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* LDPC_B200_H */

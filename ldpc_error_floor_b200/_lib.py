@@ -1,0 +1,96 @@
+"""ctypes binding of libldpc_b200.so (include/ldpc_b200.h).  No fallback: if the shared
+library is missing, every entry point raises -- the product never decodes on the CPU."""
+from __future__ import annotations
+
+import ctypes
+import os
+import subprocess
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libldpc_b200.so")
+CSRC = os.path.join(_HERE, "csrc")
+
+NUM_COUNTERS = 8
+COUNTER_NAMES = ("frames", "frame_err_last", "frame_err_any", "bit_err_last", "iters",
+                 "synd_fail", "undetected", "harvested")
+
+FLAG_SYND_OK = 1
+FLAG_UNCOR_ANY = 2
+FLAG_UNCOR_LAST = 4
+FLAG_SYND_OK_EVER = 8
+
+HARVEST_NONE, HARVEST_UNCOR_ANY, HARVEST_UNCOR_LAST, HARVEST_SYND_FAIL = 0, 1, 2, 3
+
+
+class LdpcError(RuntimeError):
+    def __init__(self, code: int, msg: str):
+        super().__init__(f"ldpc_b200 error {code}: {msg}")
+        self.code = code
+
+
+class GraphInfo(ctypes.Structure):
+    _fields_ = [("M", ctypes.c_int32), ("N", ctypes.c_int32), ("z", ctypes.c_int32), ("E", ctypes.c_int32),
+                ("max_dc", ctypes.c_int32), ("max_dv", ctypes.c_int32),
+                ("n_ref", ctypes.c_int32), ("k_ref", ctypes.c_int32),
+                ("n_true", ctypes.c_int32), ("k_true", ctypes.c_int32),
+                ("rate_ref", ctypes.c_double), ("rate_true", ctypes.c_double)]
+
+
+# every symbol include/ldpc_b200.h declares: (name, restype, argtypes)
+_P = ctypes.c_void_p
+_I32, _I64, _U32, _U64 = ctypes.c_int32, ctypes.c_int64, ctypes.c_uint32, ctypes.c_uint64
+SYMBOLS = {
+    "ldpc_last_error": (ctypes.c_char_p, []),
+    "ldpc_version": (ctypes.c_int, []),
+    "ldpc_graph_create": (ctypes.c_int, [_P, _I32, _I32, _I32, _I32, _I32, _I32, _I32, ctypes.POINTER(_P)]),
+    "ldpc_graph_destroy": (ctypes.c_int, [_P]),
+    "ldpc_graph_info": (ctypes.c_int, [_P, ctypes.POINTER(GraphInfo)]),
+    "ldpc_graph_edges": (ctypes.c_int, [_P, _P, _P, _P]),
+    "ldpc_graph_sigma": (ctypes.c_int, [_P, _P, _I32, _I32, _P]),
+    "ldpc_decoder_create": (ctypes.c_int, [_P, _P, _I32, _P, _P, _P, _I32, _I32, ctypes.c_float, _I32,
+                                           ctypes.POINTER(_P)]),
+    "ldpc_decoder_destroy": (ctypes.c_int, [_P]),
+    "ldpc_decoder_uses_packed_kernel": (ctypes.c_int, [_P]),
+    "ldpc_decoder_geometry": (ctypes.c_int, [_P, ctypes.POINTER(_I32), ctypes.POINTER(_I32),
+                                             ctypes.POINTER(_I32), ctypes.POINTER(_I32)]),
+    "ldpc_decode": (ctypes.c_int, [_P, _P, _I64, _I32, _I32, _P, _I32, _P, _P, _P, _P, _P]),
+    "ldpc_decode_host": (ctypes.c_int, [_P, _P, _I64, _I32, _I32, _P, _I32, _P, _P, _P, _P]),
+    "ldpc_llr_generate": (ctypes.c_int, [_P, ctypes.c_double, _I64, _U64, _U64, _P, _P]),
+    "ldpc_mc_run": (ctypes.c_int, [_P, ctypes.c_double, _I64, _U64, _U64, _I32, _I32, _I32, _P, _P, _P, _U32, _P]),
+    "ldpc_mc_run_host": (ctypes.c_int, [_P, ctypes.c_double, _I64, _U64, _U64, _I32, _I32, _I32, _P, _P, _U32,
+                                        ctypes.POINTER(_U32)]),
+    "ldpc_post_decode": (ctypes.c_int, [_P, _P, _I64, _I32, _I32, _P, _P, _P, _P, _P]),
+    "ldpc_launch_count": (ctypes.c_uint64, []),
+}
+
+_lib = None
+
+
+def build(force: bool = False, jobs: int = 8) -> str:
+    """Compile the CUDA extension in-tree for sm_100a (`make -C csrc`)."""
+    if force:
+        subprocess.run(["make", "-C", CSRC, "clean"], check=True, stdout=subprocess.DEVNULL)
+    subprocess.run(["make", "-C", CSRC, f"-j{jobs}"], check=True, stdout=subprocess.DEVNULL)
+    return LIB_PATH
+
+
+def load():
+    """Load the shared library (once).  Raises if it has not been built."""
+    global _lib
+    if _lib is None:
+        if not os.path.exists(LIB_PATH):
+            raise LdpcError(-3, f"{LIB_PATH} is missing: build it with `python -c 'import __graft_entry__ as g; "
+                                f"g.build()'` (nvcc, sm_100a).  There is no CPU fallback.")
+        lib = ctypes.CDLL(LIB_PATH)
+        for name, (res, args) in SYMBOLS.items():
+            fn = getattr(lib, name)
+            fn.restype = res
+            fn.argtypes = args
+        _lib = lib
+    return _lib
+
+
+def check(rc: int) -> None:
+    if rc != 0:
+        msg = load().ldpc_last_error()
+        raise LdpcError(rc, msg.decode() if msg else "unknown")

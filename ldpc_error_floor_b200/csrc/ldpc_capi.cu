@@ -1,0 +1,622 @@
+// ldpc_capi.cu -- C-ABI (include/ldpc_b200.h): base-graph compiler, decoder handles, launchers.
+//
+// Host-side equivalents of Main_Functions.init_parameter / init_connecting_matrix
+// (Main_Functions.py:8-150) and weight_init (:387-439): instead of dense (E*z)^2 permutation
+// matrices the compiler emits E(C)-ordered circulant shift tables and a column-sorted CSR edge
+// list, pre-scaled for the lane-interleaved layout of the kernels (nms_common.cuh).
+#include "../../include/ldpc_b200.h"
+#include "nms_common.cuh"
+
+#include <algorithm>
+#include <cmath>
+#include <cstdarg>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <mutex>
+#include <new>
+#include <numeric>
+#include <string>
+#include <vector>
+
+// kernel address getters, one per compiled degree bucket (nms_h2.cu / nms_f32.cu)
+extern "C" {
+const void *nms_h2_func_16_8();
+const void *nms_h2_func_16_16();
+const void *nms_h2_func_32_8();
+const void *nms_h2_func_32_16();
+const void *nms_h2_func_0_0();
+const void *nms_f32_func_16_8();
+const void *nms_f32_func_16_16();
+const void *nms_f32_func_32_8();
+const void *nms_f32_func_32_16();
+const void *nms_f32_func_0_0();
+}
+
+namespace {
+
+thread_local std::string g_err;
+int fail(int code, const char *fmt, ...) {
+    char buf[512];
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(buf, sizeof buf, fmt, ap);
+    va_end(ap);
+    g_err = buf;
+    return code;
+}
+#define CUDA_TRY(expr)                                                                          \
+    do {                                                                                        \
+        cudaError_t _e = (expr);                                                                \
+        if (_e != cudaSuccess) return fail(LDPC_E_CUDA, "%s: %s", #expr, cudaGetErrorString(_e)); \
+    } while (0)
+
+struct DeviceGuard {
+    int prev = -1;
+    bool ok = false;
+    explicit DeviceGuard(int dev) {
+        if (cudaGetDevice(&prev) != cudaSuccess) { prev = -1; }
+        ok = cudaSetDevice(dev) == cudaSuccess;
+    }
+    ~DeviceGuard() { if (prev >= 0) cudaSetDevice(prev); }
+};
+
+}   // namespace
+
+struct ldpc_graph {
+    int M = 0, N = 0, z = 0, E = 0;
+    int punct_s = 0, punct_e = 0, short_s = 0, short_e = 0;
+    std::vector<int> proto, row, col, shift, row_ptr, col_ptr, col_edge;
+    ldpc_graph_info_t info{};
+};
+
+struct HostScratch {
+    size_t cap_frames = 0;
+    bool with_app = false;
+    int app_iters = 0;
+    float *llr[2] = {nullptr, nullptr};
+    float *app[2] = {nullptr, nullptr};
+    uint32_t *hard[2] = {nullptr, nullptr};
+    int *iters[2] = {nullptr, nullptr};
+    uint8_t *flags[2] = {nullptr, nullptr};
+    int *biterr[2] = {nullptr, nullptr};
+    cudaStream_t st[2] = {nullptr, nullptr};
+    unsigned long long *counters = nullptr;
+    unsigned int *ucount = nullptr;
+    float *ubuf = nullptr;
+    size_t ubuf_rows = 0;
+};
+
+struct ldpc_decoder {
+    ldpc_graph g;
+    int sharing[3] = {0, 0, 0};
+    int T = 0, decoding_type = 2, q_bit = 5, device = 0, sm_count = 148;
+    float clip = 20.0f;
+    bool packed = false;
+    const void *func = nullptr;
+    int dcb = 0, dvb = 0;
+    LaunchGeom geom{};
+    KParams base{};
+    float *d_w = nullptr;
+    std::mutex mu;
+    HostScratch hs;
+};
+
+// ------------------------------------------------------------------------------------ graph
+extern "C" const char *ldpc_last_error(void) { return g_err.c_str(); }
+extern "C" int ldpc_version(void) { return 100; }
+
+extern "C" int ldpc_graph_create(const int32_t *proto, int32_t M, int32_t N, int32_t z, int32_t ps, int32_t pe,
+                                 int32_t ss, int32_t se, ldpc_graph_t **out) {
+    if (!proto || !out || M <= 0 || N <= 0 || z <= 0) return fail(LDPC_E_INVALID, "graph_create: bad arguments");
+    if (ps < 0 || pe < ps || ss < 0 || se < ss || pe > N * z || se > N * z)
+        return fail(LDPC_E_INVALID, "graph_create: bad puncture/shorten range");
+    ldpc_graph *g = new (std::nothrow) ldpc_graph();
+    if (!g) return fail(LDPC_E_ALLOC, "graph_create: out of memory");
+    g->M = M; g->N = N; g->z = z;
+    g->punct_s = ps; g->punct_e = pe; g->short_s = ss; g->short_e = se;
+    g->proto.assign(proto, proto + (size_t)M * N);
+    g->row_ptr.assign(M + 1, 0);
+    for (int i = 0; i < M; ++i) {            // E(C) = row-major edge order (Main_Functions.py:69-75)
+        g->row_ptr[i] = (int)g->row.size();
+        for (int j = 0; j < N; ++j) {
+            const int p = proto[(size_t)i * N + j];
+            if (p == -1) continue;
+            g->row.push_back(i);
+            g->col.push_back(j);
+            g->shift.push_back(((p % z) + z) % z);   // :72
+        }
+    }
+    g->E = (int)g->row.size();
+    g->row_ptr[M] = g->E;
+    g->col_ptr.assign(N + 1, 0);
+    for (int e = 0; e < g->E; ++e) g->col_ptr[g->col[e] + 1]++;
+    for (int j = 0; j < N; ++j) g->col_ptr[j + 1] += g->col_ptr[j];
+    g->col_edge.assign(g->E, 0);
+    {
+        std::vector<int> fill(N, 0);
+        for (int e = 0; e < g->E; ++e) g->col_edge[g->col_ptr[g->col[e]] + fill[g->col[e]]++] = e;   // ascending E(C)
+    }
+    ldpc_graph_info_t &I = g->info;
+    I.M = M; I.N = N; I.z = z; I.E = g->E;
+    I.max_dc = 0; I.max_dv = 0;
+    for (int i = 0; i < M; ++i) I.max_dc = std::max(I.max_dc, g->row_ptr[i + 1] - g->row_ptr[i]);
+    for (int j = 0; j < N; ++j) I.max_dv = std::max(I.max_dv, g->col_ptr[j + 1] - g->col_ptr[j]);
+    const int punct_ref = pe - ps + 1, short_ref = se - ss + 1;   // "+1" even when 0,0 (:24-25)
+    I.n_ref = N * z - punct_ref - short_ref;
+    I.k_ref = (N - M) * z - short_ref;
+    I.rate_ref = 1.0 * I.k_ref / I.n_ref;                          // :27-29
+    const int punct_true = ps > 0 ? punct_ref : 0, short_true = ss > 0 ? short_ref : 0;
+    I.n_true = N * z - punct_true - short_true;
+    I.k_true = (N - M) * z - short_true;
+    I.rate_true = 1.0 * I.k_true / I.n_true;
+    *out = g;
+    return LDPC_OK;
+}
+
+extern "C" int ldpc_graph_destroy(ldpc_graph_t *g) { delete g; return LDPC_OK; }
+
+extern "C" int ldpc_graph_info(const ldpc_graph_t *g, ldpc_graph_info_t *info) {
+    if (!g || !info) return fail(LDPC_E_INVALID, "graph_info: null argument");
+    *info = g->info;
+    return LDPC_OK;
+}
+
+extern "C" int ldpc_graph_edges(const ldpc_graph_t *g, int32_t *row, int32_t *col, int32_t *shift) {
+    if (!g) return fail(LDPC_E_INVALID, "graph_edges: null graph");
+    for (int e = 0; e < g->E; ++e) {
+        if (row) row[e] = g->row[e];
+        if (col) col[e] = g->col[e];
+        if (shift) shift[e] = g->shift[e];
+    }
+    return LDPC_OK;
+}
+
+extern "C" int ldpc_graph_sigma(const ldpc_graph_t *g, const double *snr_db, int32_t n, int32_t use_ref_rate,
+                                double *sigma) {
+    if (!g || !snr_db || !sigma || n < 0) return fail(LDPC_E_INVALID, "graph_sigma: bad arguments");
+    const double R = use_ref_rate ? g->info.rate_ref : g->info.rate_true;
+    for (int i = 0; i < n; ++i) sigma[i] = std::sqrt(1.0 / (2.0 * std::pow(10.0, snr_db[i] / 10.0) * R));   // :35-36
+    return LDPC_OK;
+}
+
+// ---------------------------------------------------------------------------------- decoder
+namespace {
+
+int weight_width(int code, int kind, int M, int N, int E) {   // Main_Functions.py:397-405
+    if (code == 1) return E;
+    if (code == 2) return kind == 2 ? N : M;
+    if (code == 3) return 1;
+    return 0;
+}
+
+// degree-balanced visiting order: sort by degree (descending), deal to R slots boustrophedon
+void snake_order(const std::vector<int> &deg, int R, unsigned short *out) {
+    const int n = (int)deg.size();
+    std::vector<int> idx(n);
+    std::iota(idx.begin(), idx.end(), 0);
+    std::stable_sort(idx.begin(), idx.end(), [&](int a, int b) { return deg[a] > deg[b]; });
+    for (int k = 0; k * R < n; ++k)
+        for (int s = 0; s < R && k * R + s < n; ++s) {
+            const int lim = std::min(R, n - k * R);
+            const int src = (k & 1) ? k * R + (lim - 1 - s) : k * R + s;
+            out[k * R + s] = (unsigned short)idx[src];
+        }
+}
+
+const void *pick_kernel(bool packed, int max_dc, int max_dv, int *dcb, int *dvb) {
+    int dc = max_dc <= 16 ? 16 : (max_dc <= 32 ? 32 : 0);
+    int dv = max_dv <= 8 ? 8 : (max_dv <= 16 ? 16 : 0);
+    if (dc == 0 || dv == 0) dc = dv = 0;
+    if (getenv("LDPC_B200_FORCE_GENERIC")) dc = dv = 0;
+    *dcb = dc; *dvb = dv;
+    if (packed) {
+        if (dc == 16 && dv == 8) return nms_h2_func_16_8();
+        if (dc == 16 && dv == 16) return nms_h2_func_16_16();
+        if (dc == 32 && dv == 8) return nms_h2_func_32_8();
+        if (dc == 32 && dv == 16) return nms_h2_func_32_16();
+        return nms_h2_func_0_0();
+    }
+    if (dc == 16 && dv == 8) return nms_f32_func_16_8();
+    if (dc == 16 && dv == 16) return nms_f32_func_16_16();
+    if (dc == 32 && dv == 8) return nms_f32_func_32_8();
+    if (dc == 32 && dv == 16) return nms_f32_func_32_16();
+    return nms_f32_func_0_0();
+}
+
+constexpr int MISC_WORDS_HOST = NMS_MISC_WORDS;
+
+void fill_smem_layout(KParams *P, bool packed) {
+    int off = 0;
+    P->off_msg = off; off += P->E * P->LP;
+    off = (off + 3) & ~3;
+    P->off_xa = off; off += P->N * P->LP * (packed ? 2 : 1);
+    P->off_xq = off; off += (packed || P->qms) ? P->N * P->LP : 0;
+    P->off_hb = off; off += 2 * (packed ? 2 : 1) * P->N * P->C;
+    P->off_misc = off; off += MISC_WORDS_HOST;
+    P->smem_words = off;
+}
+
+// pick (Fp, R): lane efficiency x task balance x achievable warps/SM (from the real occupancy calculator)
+int choose_geometry(const ldpc_graph &g, bool packed, bool qms, const void *func, LaunchGeom *out) {
+    const int max_smem = 227 * 1024;
+    double best = -1.0;
+    int forced_fp = 0, forced_r = 0;
+    if (const char *s = getenv("LDPC_B200_FP")) forced_fp = atoi(s);
+    if (const char *s = getenv("LDPC_B200_R")) forced_r = atoi(s);
+    const int fp_max = packed ? LDPC_MAX_FB / 2 : LDPC_MAX_FB;
+    CUDA_TRY(cudaFuncSetAttribute(func, cudaFuncAttributeMaxDynamicSharedMemorySize, max_smem));
+    for (int Fp = 1; Fp <= fp_max; ++Fp) {
+        if (forced_fp && Fp != forced_fp) continue;
+        const int L = g.z * Fp, LP = (L + 31) & ~31, C = LP / 32;
+        if (C > 16) break;
+        KParams tmp{};
+        tmp.E = g.E; tmp.N = g.N; tmp.LP = LP; tmp.C = C; tmp.qms = qms;
+        fill_smem_layout(&tmp, packed);
+        const int smem = tmp.smem_words * 4;
+        if (smem > max_smem) break;
+        for (int R = 1; R * C <= 16; ++R) {
+            if (forced_r && R != forced_r) continue;
+            const int W = C * R;
+            if (W < 2) continue;   // the per-frame bookkeeping uses two warps
+            if (R > std::max(g.M, g.N)) break;
+            int cps = 0;
+            if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&cps, func, W * 32, smem) != cudaSuccess || cps < 1) {
+                cudaGetLastError();
+                continue;
+            }
+            const double lane_eff = (double)L / LP;
+            const double bal_m = (double)g.M / (((g.M + R - 1) / R) * R), bal_n = (double)g.N / (((g.N + R - 1) / R) * R);
+            const double warps = (double)cps * W;
+            const double occ = std::min(1.0, warps / 28.0);
+            const double score = lane_eff * (0.45 * bal_m + 0.55 * bal_n) * occ + 1e-4 * warps - 1e-5 * smem / 1024.0;
+            if (score > best) {
+                best = score;
+                out->Fp = Fp; out->FB = packed ? 2 * Fp : Fp; out->L = L; out->LP = LP; out->C = C; out->R = R;
+                out->threads = W * 32; out->smem_bytes = smem; out->ctas_per_sm = cps;
+            }
+        }
+    }
+    if (best < 0) return fail(LDPC_E_LIMIT, "no launch geometry fits this graph in shared memory");
+    return LDPC_OK;
+}
+
+int launch(const ldpc_decoder *d, const KParams &P, cudaStream_t st) {
+    const long long nb = (P.n_frames + P.FB - 1) / P.FB;
+    if (nb <= 0) return LDPC_OK;
+    const int grid = (int)std::min<long long>(nb, (long long)d->sm_count * d->geom.ctas_per_sm);
+    void *args[] = {(void *)&P};
+    CUDA_TRY(cudaLaunchKernel(d->func, dim3(grid), dim3(d->geom.threads), args, (size_t)d->geom.smem_bytes, st));
+    nms_note_launch();
+    return LDPC_OK;
+}
+
+}   // namespace
+
+extern "C" int ldpc_decoder_create(const ldpc_graph_t *g, const int32_t sharing[3], int32_t T, const float *w_cn,
+                                   const float *w_ucn, const float *w_vn, int32_t decoding_type, int32_t q_bit,
+                                   float clip_llr, int32_t device, ldpc_decoder_t **out) {
+    if (!g || !sharing || !out || T <= 0 || T > LDPC_MAX_T) return fail(LDPC_E_INVALID, "decoder_create: bad arguments");
+    // check_params (Main_Functions.py:507-521)
+    for (int i = 0; i < 3; ++i)
+        if (sharing[i] < 0 || sharing[i] > 3)
+            return fail(LDPC_E_UNSUPPORTED, "sharing code %d (temporal sharing 4/5 is not on the decode path)", sharing[i]);
+    if (sharing[2] == 1) return fail(LDPC_E_INVALID, "sharing[2] in [1,4] (Main_Functions.py:515-517)");
+    if (sharing[1] != 0 && sharing[1] != sharing[0])
+        return fail(LDPC_E_INVALID, "sharing[1] != 0 and sharing[0] != sharing[1] (Main_Functions.py:519-521)");
+    if (decoding_type != 1 && decoding_type != 2)
+        return fail(LDPC_E_UNSUPPORTED, "decoding_type %d (1 = min-sum, 2 = quantised min-sum)", decoding_type);
+    float qk = 1.f, qinv = 1.f, qmax = 0.f;
+    if (decoding_type == 2) {
+        switch (q_bit) {   // Main_Functions.py:483-492
+        case 5: qk = 2.f; qinv = 0.5f; qmax = 7.5f; break;
+        case 6: qk = 1.f; qinv = 1.f; qmax = 15.5f; break;
+        case -5: qk = 1.f; qinv = 1.f; qmax = 15.f; break;
+        case 4: qk = 1.f; qinv = 1.f; qmax = 7.f; break;
+        case 3: qk = 0.5f; qinv = 2.f; qmax = 6.f; break;
+        default: return fail(LDPC_E_INVALID, "q_bit %d has no quantiser branch", q_bit);
+        }
+    }
+    if ((sharing[0] && !w_cn) || (sharing[1] && !w_ucn) || (sharing[2] && !w_vn))
+        return fail(LDPC_E_INVALID, "decoder_create: missing weight block");
+    if (!(clip_llr > 0.f)) return fail(LDPC_E_INVALID, "clip_llr must be positive");
+    if (g->M > LDPC_MAX_M || g->N > LDPC_MAX_N || g->E > LDPC_MAX_E)
+        return fail(LDPC_E_LIMIT, "graph %dx%d with %d edges exceeds the table limits (%d, %d, %d)", g->M, g->N, g->E,
+                    LDPC_MAX_M, LDPC_MAX_N, LDPC_MAX_E);
+    int ndev = 0;
+    if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev <= 0) {
+        cudaGetLastError();
+        return fail(LDPC_E_CUDA, "no CUDA device: this library has no CPU fallback");
+    }
+    if (device < 0 || device >= ndev) return fail(LDPC_E_INVALID, "device %d out of range", device);
+    DeviceGuard guard(device);
+    if (!guard.ok) return fail(LDPC_E_CUDA, "cudaSetDevice(%d) failed", device);
+
+    ldpc_decoder *d = new (std::nothrow) ldpc_decoder();
+    if (!d) return fail(LDPC_E_ALLOC, "decoder_create: out of memory");
+    d->g = *g;
+    std::copy(sharing, sharing + 3, d->sharing);
+    d->T = T; d->decoding_type = decoding_type; d->q_bit = q_bit; d->clip = clip_llr; d->device = device;
+    const bool qms = decoding_type == 2;
+    // packed fp16x2 kernel: uniform quantiser grids closed under addition, no per-edge weights
+    d->packed = qms && q_bit != 6 && sharing[0] != 1 && g->info.max_dv <= 30 && !getenv("LDPC_B200_FORCE_F32");
+    if (!d->packed && g->info.max_dv > 64) { delete d; return fail(LDPC_E_LIMIT, "column degree > 64 in float mode"); }
+    d->func = pick_kernel(d->packed, g->info.max_dc, g->info.max_dv, &d->dcb, &d->dvb);
+    cudaDeviceProp prop;
+    if (cudaGetDeviceProperties(&prop, device) != cudaSuccess) { delete d; return fail(LDPC_E_CUDA, "cudaGetDeviceProperties"); }
+    d->sm_count = prop.multiProcessorCount;
+    int rc = choose_geometry(d->g, d->packed, qms, d->func, &d->geom);
+    if (rc != LDPC_OK) { delete d; return rc; }
+
+    KParams &P = d->base;
+    std::memset(&P, 0, sizeof P);
+    P.M = g->M; P.N = g->N; P.E = g->E; P.z = g->z; P.NZ = g->N * g->z;
+    P.Fp = d->geom.Fp; P.FB = d->geom.FB; P.L = d->geom.L; P.LP = d->geom.LP; P.C = d->geom.C; P.R = d->geom.R;
+    P.qms = qms; P.qk = qk; P.qinv = qinv; P.qmax = qmax; P.qmaxk = qmax * qk; P.clip = clip_llr;
+    P.sharing0 = sharing[0]; P.sharing1 = sharing[1]; P.sharing2 = sharing[2];
+    P.wc = weight_width(sharing[0], 0, g->M, g->N, g->E);
+    P.wu = weight_width(sharing[1], 1, g->M, g->N, g->E);
+    P.wv = weight_width(sharing[2], 2, g->M, g->N, g->E);
+    P.T_run = T;
+    P.punct_s = g->punct_s; P.punct_e = g->punct_e; P.short_s = g->short_s; P.short_e = g->short_e;
+    P.HW = (P.NZ + 31) / 32;
+    fill_smem_layout(&P, d->packed);
+    for (int i = 0; i <= g->M; ++i) P.row_ptr[i] = (unsigned short)g->row_ptr[i];
+    for (int j = 0; j <= g->N; ++j) P.col_ptr[j] = (unsigned short)g->col_ptr[j];
+    {
+        std::vector<int> dc(g->M), dv(g->N);
+        for (int i = 0; i < g->M; ++i) dc[i] = g->row_ptr[i + 1] - g->row_ptr[i];
+        for (int j = 0; j < g->N; ++j) dv[j] = g->col_ptr[j + 1] - g->col_ptr[j];
+        snake_order(dc, P.R, P.cn_order);
+        snake_order(dv, P.R, P.vn_order);
+    }
+    for (int e = 0; e < g->E; ++e) {
+        P.e_col[e] = (unsigned short)g->col[e];
+        P.e_sF[e] = (unsigned short)(g->shift[e] * P.Fp);
+    }
+    for (int k = 0; k < g->E; ++k) {
+        const int e = g->col_edge[k];
+        P.vn_edge[k].x = e * P.LP;
+        P.vn_edge[k].y = (P.L - g->shift[e] * P.Fp) % P.L;   // variable lane q -> check lane (q - s*Fp) mod L
+    }
+    // weights -> one device block [cn | ucn | vn]
+    const size_t n_c = (size_t)T * P.wc, n_u = (size_t)T * P.wu, n_v = (size_t)T * P.wv;
+    if (n_c + n_u + n_v > 0) {
+        std::vector<float> host(n_c + n_u + n_v);
+        if (n_c) std::memcpy(host.data(), w_cn, n_c * sizeof(float));
+        if (n_u) std::memcpy(host.data() + n_c, w_ucn, n_u * sizeof(float));
+        if (n_v) std::memcpy(host.data() + n_c + n_u, w_vn, n_v * sizeof(float));
+        if (cudaMalloc(&d->d_w, host.size() * sizeof(float)) != cudaSuccess ||
+            cudaMemcpy(d->d_w, host.data(), host.size() * sizeof(float), cudaMemcpyHostToDevice) != cudaSuccess) {
+            const char *msg = cudaGetErrorString(cudaGetLastError());
+            delete d;
+            return fail(LDPC_E_CUDA, "uploading weights: %s", msg);
+        }
+        P.w_cn = n_c ? d->d_w : nullptr;
+        P.w_ucn = n_u ? d->d_w + n_c : nullptr;
+        P.w_vn = n_v ? d->d_w + n_c + n_u : nullptr;
+    }
+    *out = d;
+    return LDPC_OK;
+}
+
+namespace {
+void free_scratch(HostScratch &h) {
+    for (int i = 0; i < 2; ++i) {
+        cudaFree(h.llr[i]); cudaFree(h.app[i]); cudaFree(h.hard[i]); cudaFree(h.iters[i]);
+        cudaFree(h.flags[i]); cudaFree(h.biterr[i]);
+        if (h.st[i]) cudaStreamDestroy(h.st[i]);
+    }
+    cudaFree(h.counters); cudaFree(h.ucount); cudaFree(h.ubuf);
+    h = HostScratch();
+}
+}   // namespace
+
+extern "C" int ldpc_decoder_destroy(ldpc_decoder_t *d) {
+    if (!d) return LDPC_OK;
+    {
+        DeviceGuard guard(d->device);
+        free_scratch(d->hs);
+        cudaFree(d->d_w);
+    }
+    delete d;
+    return LDPC_OK;
+}
+
+extern "C" int ldpc_decoder_uses_packed_kernel(const ldpc_decoder_t *d) { return d && d->packed ? 1 : 0; }
+
+extern "C" int ldpc_decoder_geometry(const ldpc_decoder_t *d, int32_t *frames_per_cta, int32_t *ctas_per_sm,
+                                     int32_t *threads_per_cta, int32_t *smem_bytes) {
+    if (!d) return fail(LDPC_E_INVALID, "decoder_geometry: null decoder");
+    if (frames_per_cta) *frames_per_cta = d->geom.FB;
+    if (ctas_per_sm) *ctas_per_sm = d->geom.ctas_per_sm;
+    if (threads_per_cta) *threads_per_cta = d->geom.threads;
+    if (smem_bytes) *smem_bytes = d->geom.smem_bytes;
+    return LDPC_OK;
+}
+
+// ----------------------------------------------------------------------------------- decode
+extern "C" int ldpc_decode(const ldpc_decoder_t *d, const float *llr_dev, int64_t B, int32_t iters, int32_t early_term,
+                           float *app_dev, int32_t app_all_iters, uint32_t *hard_dev, int32_t *iters_dev,
+                           uint8_t *flags_dev, int32_t *biterr_dev, void *stream) {
+    if (!d || (!llr_dev && B > 0) || B < 0) return fail(LDPC_E_INVALID, "decode: bad arguments");
+    if (iters < 0 || iters > d->T) return fail(LDPC_E_INVALID, "decode: iters %d outside 0..%d", iters, d->T);
+    if (B == 0) return LDPC_OK;
+    DeviceGuard guard(d->device);
+    if (!guard.ok) return fail(LDPC_E_CUDA, "cudaSetDevice(%d) failed", d->device);
+    KParams P = d->base;
+    P.T_run = iters == 0 ? d->T : iters;
+    P.early_term = early_term ? 1 : 0;
+    P.llr = llr_dev; P.n_frames = B;
+    P.app = app_dev; P.app_all = app_all_iters ? 1 : 0; P.app_stride_t = (long long)B * P.NZ;
+    P.hard = hard_dev; P.iters = iters_dev; P.flags = flags_dev; P.biterr = biterr_dev;
+    return launch(d, P, (cudaStream_t)stream);
+}
+
+namespace {
+int ensure_host_scratch(ldpc_decoder *d, size_t chunk, bool with_app, int app_iters) {
+    HostScratch &h = d->hs;
+    if (h.cap_frames >= chunk && (!with_app || (h.with_app && h.app_iters >= app_iters))) return LDPC_OK;
+    unsigned long long *cnt = h.counters; unsigned int *uc = h.ucount; float *ub = h.ubuf; size_t ur = h.ubuf_rows;
+    h.counters = nullptr; h.ucount = nullptr; h.ubuf = nullptr;
+    free_scratch(h);
+    h.counters = cnt; h.ucount = uc; h.ubuf = ub; h.ubuf_rows = ur;
+    const KParams &P = d->base;
+    for (int i = 0; i < 2; ++i) {
+        CUDA_TRY(cudaStreamCreateWithFlags(&h.st[i], cudaStreamNonBlocking));
+        CUDA_TRY(cudaMalloc(&h.llr[i], chunk * P.NZ * sizeof(float)));
+        CUDA_TRY(cudaMalloc(&h.hard[i], chunk * P.HW * sizeof(uint32_t)));
+        CUDA_TRY(cudaMalloc(&h.iters[i], chunk * sizeof(int)));
+        CUDA_TRY(cudaMalloc(&h.flags[i], chunk));
+        CUDA_TRY(cudaMalloc(&h.biterr[i], chunk * sizeof(int)));
+        if (with_app) CUDA_TRY(cudaMalloc(&h.app[i], (size_t)app_iters * chunk * P.NZ * sizeof(float)));
+    }
+    h.cap_frames = chunk; h.with_app = with_app; h.app_iters = app_iters;
+    return LDPC_OK;
+}
+}   // namespace
+
+extern "C" int ldpc_decode_host(const ldpc_decoder_t *dc, const float *llr_host, int64_t B, int32_t iters,
+                                int32_t early_term, float *app_host, int32_t app_all_iters, uint32_t *hard_host,
+                                int32_t *iters_host, uint8_t *flags_host, int32_t *biterr_host) {
+    ldpc_decoder *d = const_cast<ldpc_decoder *>(dc);
+    if (!d || (!llr_host && B > 0) || B < 0) return fail(LDPC_E_INVALID, "decode_host: bad arguments");
+    if (iters < 0 || iters > d->T) return fail(LDPC_E_INVALID, "decode_host: iters %d outside 0..%d", iters, d->T);
+    if (B == 0) return LDPC_OK;
+    DeviceGuard guard(d->device);
+    if (!guard.ok) return fail(LDPC_E_CUDA, "cudaSetDevice(%d) failed", d->device);
+    std::lock_guard<std::mutex> lock(d->mu);
+    const KParams &P0 = d->base;
+    const int T_run = iters == 0 ? d->T : iters;
+    const int app_iters = app_host ? (app_all_iters ? T_run : 1) : 0;
+    // chunk: a multiple of the frames one full wave of CTAs decodes, ~32 MiB of LLRs
+    const size_t wave = (size_t)d->sm_count * d->geom.ctas_per_sm * P0.FB;
+    size_t chunk = std::max<size_t>(wave, ((32u << 20) / (P0.NZ * sizeof(float)) / wave) * wave);
+    if (app_iters) chunk = wave;
+    chunk = std::min<size_t>(chunk, ((size_t)B + P0.FB - 1) / P0.FB * P0.FB);
+    int rc = ensure_host_scratch(d, chunk, app_iters > 0, app_iters);
+    if (rc != LDPC_OK) return rc;
+    HostScratch &h = d->hs;
+    int k = 0;
+    for (int64_t off = 0; off < B; off += (int64_t)chunk, k ^= 1) {
+        const int64_t nb = std::min<int64_t>((int64_t)chunk, B - off);
+        cudaStream_t st = h.st[k];
+        CUDA_TRY(cudaMemcpyAsync(h.llr[k], llr_host + off * P0.NZ, (size_t)nb * P0.NZ * sizeof(float),
+                                 cudaMemcpyHostToDevice, st));
+        KParams P = P0;
+        P.T_run = T_run; P.early_term = early_term ? 1 : 0;
+        P.llr = h.llr[k]; P.n_frames = nb;
+        P.app = app_iters ? h.app[k] : nullptr; P.app_all = app_all_iters ? 1 : 0; P.app_stride_t = (long long)nb * P.NZ;
+        P.hard = hard_host ? h.hard[k] : nullptr; P.iters = iters_host ? h.iters[k] : nullptr;
+        P.flags = flags_host ? h.flags[k] : nullptr; P.biterr = biterr_host ? h.biterr[k] : nullptr;
+        rc = launch(d, P, st);
+        if (rc != LDPC_OK) return rc;
+        if (hard_host)
+            CUDA_TRY(cudaMemcpyAsync(hard_host + off * P.HW, h.hard[k], (size_t)nb * P.HW * 4, cudaMemcpyDeviceToHost, st));
+        if (iters_host) CUDA_TRY(cudaMemcpyAsync(iters_host + off, h.iters[k], (size_t)nb * 4, cudaMemcpyDeviceToHost, st));
+        if (flags_host) CUDA_TRY(cudaMemcpyAsync(flags_host + off, h.flags[k], (size_t)nb, cudaMemcpyDeviceToHost, st));
+        if (biterr_host) CUDA_TRY(cudaMemcpyAsync(biterr_host + off, h.biterr[k], (size_t)nb * 4, cudaMemcpyDeviceToHost, st));
+        if (app_iters) {
+            const size_t row = (size_t)nb * P.NZ * sizeof(float);
+            CUDA_TRY(cudaMemcpy2DAsync(app_host + off * P.NZ, (size_t)B * P.NZ * sizeof(float), h.app[k], row, row,
+                                       (size_t)app_iters, cudaMemcpyDeviceToHost, st));
+        }
+        // buffer pair k is tied to stream k, so its reuse two chunks later is ordered by the stream itself
+    }
+    CUDA_TRY(cudaStreamSynchronize(h.st[0]));
+    CUDA_TRY(cudaStreamSynchronize(h.st[1]));
+    return LDPC_OK;
+}
+
+// ------------------------------------------------------------------- generator / Monte-Carlo
+namespace {
+void fill_channel(KParams &P, double sigma, uint64_t seed, uint64_t frame_offset) {
+    P.sigma = (float)sigma;
+    P.two_over_s2 = (float)(2.0 / (sigma * sigma));
+    P.seed = seed; P.frame_offset = frame_offset;
+}
+}   // namespace
+
+extern "C" int ldpc_llr_generate(const ldpc_decoder_t *d, double sigma, int64_t n_frames, uint64_t seed,
+                                 uint64_t frame_offset, float *llr_dev, void *stream) {
+    if (!d || !llr_dev || n_frames < 0 || !(sigma > 0.0)) return fail(LDPC_E_INVALID, "llr_generate: bad arguments");
+    if (n_frames == 0) return LDPC_OK;
+    DeviceGuard guard(d->device);
+    if (!guard.ok) return fail(LDPC_E_CUDA, "cudaSetDevice(%d) failed", d->device);
+    KParams P = d->base;
+    fill_channel(P, sigma, seed, frame_offset);
+    CUDA_TRY(nms_launch_generate(P, llr_dev, n_frames, (cudaStream_t)stream));
+    return LDPC_OK;
+}
+
+extern "C" int ldpc_mc_run(const ldpc_decoder_t *d, double sigma, int64_t n_frames, uint64_t seed, uint64_t frame_offset,
+                           int32_t iters, int32_t early_term, int32_t harvest_mode, uint64_t *counters_dev,
+                           float *uncor_buf_dev, uint32_t *uncor_count_dev, uint32_t uncor_capacity, void *stream) {
+    if (!d || n_frames < 0 || !(sigma > 0.0) || !counters_dev) return fail(LDPC_E_INVALID, "mc_run: bad arguments");
+    if (iters < 0 || iters > d->T) return fail(LDPC_E_INVALID, "mc_run: iters %d outside 0..%d", iters, d->T);
+    if (harvest_mode < 0 || harvest_mode > 3) return fail(LDPC_E_INVALID, "mc_run: harvest_mode %d", harvest_mode);
+    if (n_frames == 0) return LDPC_OK;
+    DeviceGuard guard(d->device);
+    if (!guard.ok) return fail(LDPC_E_CUDA, "cudaSetDevice(%d) failed", d->device);
+    KParams P = d->base;
+    fill_channel(P, sigma, seed, frame_offset);
+    P.T_run = iters == 0 ? d->T : iters;
+    P.early_term = early_term ? 1 : 0;
+    P.llr = nullptr; P.n_frames = n_frames;
+    P.counters = (unsigned long long *)counters_dev;
+    P.harvest_mode = harvest_mode;
+    P.uncor_buf = uncor_buf_dev; P.uncor_count = uncor_count_dev; P.uncor_cap = uncor_capacity;
+    return launch(d, P, (cudaStream_t)stream);
+}
+
+extern "C" int ldpc_mc_run_host(const ldpc_decoder_t *dc, double sigma, int64_t n_frames, uint64_t seed,
+                                uint64_t frame_offset, int32_t iters, int32_t early_term, int32_t harvest_mode,
+                                uint64_t *counters_host, float *uncor_host, uint32_t uncor_capacity,
+                                uint32_t *n_uncor_host) {
+    ldpc_decoder *d = const_cast<ldpc_decoder *>(dc);
+    if (!d || !counters_host) return fail(LDPC_E_INVALID, "mc_run_host: bad arguments");
+    DeviceGuard guard(d->device);
+    if (!guard.ok) return fail(LDPC_E_CUDA, "cudaSetDevice(%d) failed", d->device);
+    std::lock_guard<std::mutex> lock(d->mu);
+    HostScratch &h = d->hs;
+    if (!h.counters) CUDA_TRY(cudaMalloc(&h.counters, LDPC_NUM_COUNTERS * sizeof(unsigned long long)));
+    if (!h.ucount) CUDA_TRY(cudaMalloc(&h.ucount, sizeof(unsigned int)));
+    const bool want_rows = uncor_host && uncor_capacity > 0 && harvest_mode != 0;
+    if (want_rows && h.ubuf_rows < uncor_capacity) {
+        cudaFree(h.ubuf); h.ubuf = nullptr; h.ubuf_rows = 0;
+        CUDA_TRY(cudaMalloc(&h.ubuf, (size_t)uncor_capacity * d->base.NZ * sizeof(float)));
+        h.ubuf_rows = uncor_capacity;
+    }
+    CUDA_TRY(cudaMemsetAsync(h.counters, 0, LDPC_NUM_COUNTERS * sizeof(unsigned long long), 0));
+    CUDA_TRY(cudaMemsetAsync(h.ucount, 0, sizeof(unsigned int), 0));
+    int rc = ldpc_mc_run(d, sigma, n_frames, seed, frame_offset, iters, early_term, harvest_mode,
+                         (uint64_t *)h.counters, want_rows ? h.ubuf : nullptr, h.ucount, want_rows ? uncor_capacity : 0,
+                         nullptr);
+    if (rc != LDPC_OK) return rc;
+    CUDA_TRY(cudaMemcpy(counters_host, h.counters, LDPC_NUM_COUNTERS * sizeof(unsigned long long), cudaMemcpyDeviceToHost));
+    unsigned int n = 0;
+    CUDA_TRY(cudaMemcpy(&n, h.ucount, sizeof n, cudaMemcpyDeviceToHost));
+    n = std::min(n, want_rows ? uncor_capacity : 0u);
+    if (n_uncor_host) *n_uncor_host = n;
+    if (n > 0) CUDA_TRY(cudaMemcpy(uncor_host, h.ubuf, (size_t)n * d->base.NZ * sizeof(float), cudaMemcpyDeviceToHost));
+    return LDPC_OK;
+}
+
+extern "C" int ldpc_post_decode(const ldpc_decoder_t *post, const float *uncor_dev, int64_t n_words, int32_t iters,
+                                int32_t early_term, uint64_t *counters_dev, uint32_t *hard_dev, int32_t *iters_dev,
+                                uint8_t *flags_dev, void *stream) {
+    if (!post || (!uncor_dev && n_words > 0) || n_words < 0) return fail(LDPC_E_INVALID, "post_decode: bad arguments");
+    if (iters < 0 || iters > post->T) return fail(LDPC_E_INVALID, "post_decode: iters %d outside 0..%d", iters, post->T);
+    if (n_words == 0) return LDPC_OK;
+    DeviceGuard guard(post->device);
+    if (!guard.ok) return fail(LDPC_E_CUDA, "cudaSetDevice(%d) failed", post->device);
+    KParams P = post->base;
+    P.T_run = iters == 0 ? post->T : iters;
+    P.early_term = early_term ? 1 : 0;
+    P.llr = uncor_dev; P.n_frames = n_words;
+    P.counters = (unsigned long long *)counters_dev;
+    P.hard = hard_dev; P.iters = iters_dev; P.flags = flags_dev;
+    return launch(post, P, (cudaStream_t)stream);
+}
+
+extern "C" uint64_t ldpc_launch_count(void) { return nms_launch_count(); }

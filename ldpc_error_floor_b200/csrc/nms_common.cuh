@@ -1,0 +1,87 @@
+// nms_common.cuh -- shared declarations of the sm_100a NMS decode kernels and their launcher.
+//
+// Layout idea (DESIGN.md "Data layout"): one CTA decodes FB frames at once.  A "slot" packs
+// either two frames as fp16x2 (packed kernel, exact for the quantised min-sum grids) or one
+// frame as fp32 (float kernel).  Fp slots are interleaved lane-wise, q = a*Fp + fp with a the
+// circulant lane, so that the block sees ONE quasi-cyclic code of lifting size L = z*Fp whose
+// shift for proto edge e is s_e*Fp: a rotation by s is q -> (q + s*Fp) mod L for every
+// interleaved frame at once, and consecutive threads touch consecutive shared-memory words on
+// both sides of every rotation (conflict-free up to the single wrap point).
+#pragma once
+#include <cuda_fp16.h>
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#define LDPC_MAX_M 256
+#define LDPC_MAX_N 256
+#define LDPC_MAX_E 1024
+#define LDPC_MAX_FB 64   // frames per CTA
+#define LDPC_MAX_T 256
+
+// tables + scalars, passed as ONE __grid_constant__ kernel parameter (constant bank, LDC/ULDC)
+struct KParams {
+    // geometry
+    int M, N, E, z, NZ;
+    int Fp;   // slots interleaved per CTA
+    int FB;   // frames per CTA (2*Fp packed, Fp float)
+    int L;    // z*Fp  (active lanes)
+    int LP;   // L rounded up to 32
+    int C;    // LP/32 lane chunks
+    int R;    // task slots (warps per chunk); CTA = C*R warps
+    // arithmetic
+    int qms;           // 1: quantised min-sum
+    float qk, qinv;    // Q(x) = clamp(rint(x*qk), +-qmaxk) * qinv      (Main_Functions.py:483-492)
+    float qmaxk, qmax; // qmax*qk, qmax
+    float clip;        // clip_LLR (main_Base.py:69)
+    int sharing0, sharing1, sharing2;
+    int wc, wu, wv;    // weight row widths
+    const float *w_cn, *w_ucn, *w_vn;   // device [T, width]
+    int T_run, early_term;
+    // source: llr != nullptr -> global LLRs; else Philox generator
+    const float *llr;
+    long long n_frames;
+    float sigma, two_over_s2;
+    unsigned long long seed, frame_offset;
+    int punct_s, punct_e, short_s, short_e;
+    // outputs (nullable)
+    float *app; int app_all; long long app_stride_t;   // elements between iterations (B*NZ)
+    uint32_t *hard; int HW;
+    int *iters; uint8_t *flags; int *biterr;
+    unsigned long long *counters;
+    float *uncor_buf; unsigned int *uncor_count; unsigned int uncor_cap; int harvest_mode;
+    // shared-memory carve-up (word offsets)
+    int off_msg, off_xa, off_xq, off_hb, off_misc, smem_words;
+    // tables
+    unsigned short row_ptr[LDPC_MAX_M + 1];   // E(C) edges of proto row i: [row_ptr[i], row_ptr[i+1])
+    unsigned short col_ptr[LDPC_MAX_N + 1];   // CSR by proto column into vn_edge
+    unsigned short cn_order[LDPC_MAX_M];      // row visiting order (degree-balanced)
+    unsigned short vn_order[LDPC_MAX_N];
+    unsigned short e_col[LDPC_MAX_E];         // proto column of E(C) edge e
+    unsigned short e_sF[LDPC_MAX_E];          // s_e*Fp: check lane q -> variable lane (q + sF) mod L
+    int2 vn_edge[LDPC_MAX_E];                 // column-sorted: {e*LP (words), (L - s_e*Fp) mod L}
+};
+
+struct LaunchGeom {
+    int Fp, FB, L, LP, C, R, threads, smem_bytes, ctas_per_sm;
+};
+
+// ---- Philox4x32-10 (Salmon et al., SC'11), written out so the host tests can restate it
+__host__ __device__ __forceinline__ void philox4x32_10(uint32_t c0, uint32_t c1, uint32_t c2, uint32_t c3,
+                                                       uint32_t k0, uint32_t k1, uint32_t out[4]) {
+#pragma unroll
+    for (int r = 0; r < 10; ++r) {
+        const uint64_t p0 = (uint64_t)0xD2511F53u * c0;
+        const uint64_t p1 = (uint64_t)0xCD9E8D57u * c2;
+        const uint32_t n0 = (uint32_t)(p1 >> 32) ^ c1 ^ k0;
+        const uint32_t n2 = (uint32_t)(p0 >> 32) ^ c3 ^ k1;
+        c1 = (uint32_t)p1; c3 = (uint32_t)p0; c0 = n0; c2 = n2;
+        k0 += 0x9E3779B9u; k1 += 0xBB67AE85u;
+    }
+    out[0] = c0; out[1] = c1; out[2] = c2; out[3] = c3;
+}
+
+#define NMS_MISC_WORDS 400   // per-CTA bookkeeping words at the end of shared memory (nms_device.cuh)
+
+cudaError_t nms_launch_generate(const KParams &P, float *out, long long n_frames, cudaStream_t st);
+void nms_note_launch();
+unsigned long long nms_launch_count();

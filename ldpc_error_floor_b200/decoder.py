@@ -1,0 +1,299 @@
+"""Host side of the NMS decode op: decoder handle + PyTorch custom op over the C-ABI.
+
+`NMSDecoder.decode` is what a shimmed `sess.run(net_dict["ya_output_all"], feed_dict={xa: ...})`
+(Print_Functions.py:148-151) maps onto; `NMSDecoder.ya_output_all` returns exactly that
+tensor ([T*B, N*z] float32, iterations concatenated along axis 0, Main_Functions.py:380-383).
+PyTorch is only plumbing here (device memory, streams); all arithmetic is in csrc/.
+"""
+
+import ctypes
+from dataclasses import dataclass
+from typing import Dict, List, Optional
+
+import numpy as np
+import torch
+
+from . import _lib
+from .formats import WeightSet, weight_width
+from .graph import BaseGraph
+
+
+def check_params(sampling_type, SNR_Matrix, sharing, iters_max, fixed_iter, iter_step):
+    """Main_Functions.check_params (:498-523) with the same rules; raises ValueError where the
+    reference prints and sys.exit()s."""
+    SNR_Matrix = np.asarray(SNR_Matrix, dtype=np.float64)
+    if sampling_type == 1:
+        if len(SNR_Matrix) > 1:
+            SNR_Matrix = np.array([0.0])
+    elif sampling_type == 2:
+        if len(SNR_Matrix) > 1:
+            raise ValueError("sampling_type == 2 and len(SNR_Matrix) > 1")
+    if np.sum(sharing) == 0:
+        raise ValueError("np.sum(sharing) == 0")
+    if any(v in [4, 5] for v in sharing) and (iters_max - fixed_iter) % iter_step > 0:
+        raise ValueError("any(value in [4,5] for value in sharing) and (iters_max - fixed_iter) % iter_step > 0")
+    if sharing[2] in [1, 4]:
+        raise ValueError("sharing[2] in [1,4]")
+    if sharing[1] != 0 and sharing[0] != sharing[1]:
+        raise ValueError("sharing[1] != 0 and sharing[0]!=sharing[1])")
+    return SNR_Matrix
+
+
+@dataclass
+class DecodeResult:
+    hard: Optional[torch.Tensor]      # uint8 [B, N*z] hard decision (bit = APP >= 0) -- unpacked view
+    hard_packed: Optional[torch.Tensor]   # int32 [B, ceil(N*z/32)] as the kernel wrote it
+    iters: torch.Tensor               # int32 [B] iterations until the first zero syndrome (else T)
+    flags: torch.Tensor               # uint8 [B] LDPC_FLAG_* bits
+    biterr: torch.Tensor              # int32 [B] ones in the output decision
+    app: Optional[torch.Tensor]       # f32 [B, N*z] or [T, B, N*z]
+
+    @property
+    def synd_ok(self):
+        return (self.flags & _lib.FLAG_SYND_OK) != 0
+
+    @property
+    def uncor_any(self):
+        return (self.flags & _lib.FLAG_UNCOR_ANY) != 0
+
+    @property
+    def uncor_last(self):
+        return (self.flags & _lib.FLAG_UNCOR_LAST) != 0
+
+
+def _ptr(t: Optional[torch.Tensor]):
+    return ctypes.c_void_p(t.data_ptr()) if t is not None else None
+
+
+def unpack_bits(packed: torch.Tensor, nbits: int) -> torch.Tensor:
+    """int32 [B, W] -> uint8 [B, nbits]; bit k lives at word k//32, bit k%32."""
+    shifts = torch.arange(32, device=packed.device, dtype=torch.int32)
+    bits = (packed.unsqueeze(-1) >> shifts) & 1
+    return bits.reshape(packed.shape[0], -1)[:, :nbits].to(torch.uint8)
+
+
+class NMSDecoder:
+    """Flooding neural min-sum decoder for one (graph, weight set, arithmetic mode) on one GPU.
+
+    weights: WeightSet (sharing codes + [T, width] blocks, format F2); `iters` defaults to the
+    number of weight rows.  decoding_type 1 = min-sum, 2 = quantised min-sum (q_bit as in
+    Main_Functions.py:483-492).  A "post decoder" is simply an NMSDecoder built from the boosted
+    weight file (base rows followed by post rows)."""
+
+    def __init__(self, graph: BaseGraph, weights: WeightSet, iters: Optional[int] = None, decoding_type: int = 2,
+                 q_bit: int = 5, clip_llr: float = 20.0, device: Optional[int] = None):
+        self.graph = graph
+        self.sharing = [int(s) for s in weights.sharing]
+        T = weights.iterations if iters is None else int(iters)
+        if T <= 0:
+            raise ValueError("a decoder needs at least one iteration (all-zero sharing carries no rows: pass iters)")
+        self.T = T
+        self.decoding_type, self.q_bit, self.clip_llr = int(decoding_type), int(q_bit), float(clip_llr)
+        if device is None:
+            device = torch.cuda.current_device() if torch.cuda.is_available() else 0
+        self.device_index = int(device)
+        self.device = torch.device("cuda", self.device_index)
+        blocks = [None, None, None]
+        for i, code in enumerate(self.sharing):
+            if code > 0:
+                w = np.ascontiguousarray(np.asarray(weights.blocks[i], dtype=np.float32))
+                width = weight_width(code, i, graph.M, graph.N, graph.E)
+                if w.ndim == 1:
+                    w = w.reshape(-1, 1)
+                if w.shape[0] < T or w.shape[1] != width:
+                    raise ValueError(f"weight block {i}: shape {w.shape}, need [>={T}, {width}]")
+                blocks[i] = np.ascontiguousarray(w[:T])
+        self._blocks = blocks
+        lib = _lib.load()
+        sh = (ctypes.c_int32 * 3)(*self.sharing)
+        self._h = ctypes.c_void_p()
+        _lib.check(lib.ldpc_decoder_create(
+            graph._h, sh, T, *[b.ctypes.data if b is not None else None for b in blocks],
+            self.decoding_type, self.q_bit, self.clip_llr, self.device_index, ctypes.byref(self._h)))
+        self.packed = bool(lib.ldpc_decoder_uses_packed_kernel(self._h))
+        fb, cps, thr, smem = (ctypes.c_int32() for _ in range(4))
+        _lib.check(lib.ldpc_decoder_geometry(self._h, ctypes.byref(fb), ctypes.byref(cps), ctypes.byref(thr),
+                                             ctypes.byref(smem)))
+        self.frames_per_cta, self.ctas_per_sm = fb.value, cps.value
+        self.threads_per_cta, self.smem_bytes = thr.value, smem.value
+        self.hard_words = (graph.NZ + 31) // 32
+
+    def __del__(self):
+        h = getattr(self, "_h", None)
+        if h:
+            try:
+                _lib.load().ldpc_decoder_destroy(h)
+            except Exception:
+                pass
+            self._h = None
+
+    # ------------------------------------------------------------------ decode (device buffers)
+    def decode(self, llr: torch.Tensor, iters: int = 0, early_term: bool = False, app: Optional[str] = None,
+               want_hard: bool = True, unpack: bool = False) -> DecodeResult:
+        """llr: CUDA float32 [B, N, z] or [B, N*z] (log p1/p0).  app: None | 'last' | 'all'."""
+        if app not in (None, "last", "all"):
+            raise ValueError("app must be None, 'last' or 'all'")
+        return _decode_via_op(self, llr, iters, early_term, app, want_hard, unpack)
+
+    def _decode_impl(self, llr, iters, early_term, app, want_hard, unpack) -> DecodeResult:
+        g = self.graph
+        if not llr.is_cuda or llr.dtype != torch.float32:
+            raise ValueError("decode: llr must be a CUDA float32 tensor (use decode_host for host buffers)")
+        if llr.device.index != self.device_index:
+            raise ValueError(f"decode: llr lives on {llr.device}, decoder on {self.device}")
+        B = llr.shape[0]
+        if llr.numel() != B * g.NZ:
+            raise ValueError(f"decode: llr has {llr.numel()} elements, expected {B}x{g.NZ}")
+        llr = llr.contiguous()
+        T_run = self.T if iters == 0 else iters
+        dev = self.device
+        hard = torch.empty((B, self.hard_words), dtype=torch.int32, device=dev) if want_hard else None
+        it = torch.empty((B,), dtype=torch.int32, device=dev)
+        fl = torch.empty((B,), dtype=torch.uint8, device=dev)
+        be = torch.empty((B,), dtype=torch.int32, device=dev)
+        app_t = None
+        if app == "last":
+            app_t = torch.empty((B, g.NZ), dtype=torch.float32, device=dev)
+        elif app == "all":
+            app_t = torch.zeros((T_run, B, g.NZ), dtype=torch.float32, device=dev)
+        elif app is not None:
+            raise ValueError("app must be None, 'last' or 'all'")
+        stream = torch.cuda.current_stream(dev).cuda_stream
+        _lib.check(_lib.load().ldpc_decode(self._h, _ptr(llr), B, int(iters), 1 if early_term else 0, _ptr(app_t),
+                                           1 if app == "all" else 0, _ptr(hard), _ptr(it), _ptr(fl), _ptr(be),
+                                           ctypes.c_void_p(stream)))
+        return DecodeResult(unpack_bits(hard, g.NZ) if (unpack and hard is not None) else None, hard, it, fl, be, app_t)
+
+    def ya_output_all(self, xa: torch.Tensor, iters: int = 0) -> torch.Tensor:
+        """net_dict["ya_output_all"] of the reference: [T*B, N*z] float32 (Main_Functions.py:380-383)."""
+        r = self.decode(xa, iters=iters, early_term=False, app="all", want_hard=False)
+        return r.app.reshape(-1, self.graph.NZ)
+
+    # -------------------------------------------------------------------- decode (host buffers)
+    def decode_host(self, llr, iters: int = 0, early_term: bool = False, app: Optional[str] = None) -> Dict:
+        """End-to-end call: llr is a host array (numpy or CPU torch tensor, pinned or not); results
+        come back in host numpy arrays.  Copies and kernels are pipelined inside the library."""
+        g = self.graph
+        if isinstance(llr, torch.Tensor):
+            if llr.is_cuda:
+                raise ValueError("decode_host takes host memory")
+            arr = llr.contiguous().numpy()
+        else:
+            arr = np.ascontiguousarray(llr, dtype=np.float32)
+        if arr.dtype != np.float32:
+            arr = arr.astype(np.float32)
+        B = arr.shape[0]
+        if arr.size != B * g.NZ:
+            raise ValueError(f"decode_host: llr has {arr.size} elements, expected {B}x{g.NZ}")
+        T_run = self.T if iters == 0 else iters
+        hard = np.empty((B, self.hard_words), dtype=np.uint32)
+        it = np.empty((B,), dtype=np.int32)
+        fl = np.empty((B,), dtype=np.uint8)
+        be = np.empty((B,), dtype=np.int32)
+        app_a = None
+        if app == "last":
+            app_a = np.empty((B, g.NZ), dtype=np.float32)
+        elif app == "all":
+            app_a = np.zeros((T_run, B, g.NZ), dtype=np.float32)
+        _lib.check(_lib.load().ldpc_decode_host(
+            self._h, arr.ctypes.data, B, int(iters), 1 if early_term else 0,
+            app_a.ctypes.data if app_a is not None else None, 1 if app == "all" else 0, hard.ctypes.data,
+            it.ctypes.data, fl.ctypes.data, be.ctypes.data))
+        return {"hard_packed": hard, "iters": it, "flags": fl, "biterr": be, "app": app_a}
+
+    # --------------------------------------------------------------------- generator / MC / post
+    def generate(self, sigma: float, n_frames: int, seed: int, frame_offset: int = 0) -> torch.Tensor:
+        """BPSK/AWGN LLRs of the all-zero codeword, CUDA float32 [n_frames, N, z]
+        (replaces Print_Functions.create_mix_epoch, :29-72; Philox instead of MT19937)."""
+        out = torch.empty((n_frames, self.graph.N, self.graph.z), dtype=torch.float32, device=self.device)
+        stream = torch.cuda.current_stream(self.device).cuda_stream
+        _lib.check(_lib.load().ldpc_llr_generate(self._h, float(sigma), int(n_frames), int(seed) & (2**64 - 1),
+                                                 int(frame_offset), _ptr(out), ctypes.c_void_p(stream)))
+        return out
+
+    def mc_run(self, sigma: float, n_frames: int, seed: int, frame_offset: int = 0, iters: int = 0,
+               early_term: bool = False, harvest: int = _lib.HARVEST_NONE, capacity: int = 0,
+               counters: Optional[torch.Tensor] = None, uncor_buf: Optional[torch.Tensor] = None,
+               uncor_count: Optional[torch.Tensor] = None):
+        """Fused generate + decode + count (+ harvest) for one SNR point, asynchronous on the current
+        stream.  Returns (counters int64[8] CUDA, uncor_buf f32 [capacity, N*z] CUDA or None,
+        uncor_count int32[1] CUDA); pass the tensors back in to keep accumulating."""
+        dev = self.device
+        if counters is None:
+            counters = torch.zeros((_lib.NUM_COUNTERS,), dtype=torch.int64, device=dev)
+        if uncor_count is None:
+            uncor_count = torch.zeros((1,), dtype=torch.int32, device=dev)
+        if harvest != _lib.HARVEST_NONE and capacity > 0 and uncor_buf is None:
+            uncor_buf = torch.empty((capacity, self.graph.NZ), dtype=torch.float32, device=dev)
+        cap = 0 if uncor_buf is None else uncor_buf.shape[0]
+        stream = torch.cuda.current_stream(dev).cuda_stream
+        _lib.check(_lib.load().ldpc_mc_run(self._h, float(sigma), int(n_frames), int(seed) & (2**64 - 1),
+                                           int(frame_offset), int(iters), 1 if early_term else 0, int(harvest),
+                                           _ptr(counters), _ptr(uncor_buf), _ptr(uncor_count), cap,
+                                           ctypes.c_void_p(stream)))
+        return counters, uncor_buf, uncor_count
+
+    def mc_run_host(self, sigma: float, n_frames: int, seed: int, frame_offset: int = 0, iters: int = 0,
+                    early_term: bool = False, harvest: int = _lib.HARVEST_NONE, capacity: int = 0):
+        """Synchronous host-buffer twin: returns (dict of counters, numpy [n_uncor, N*z])."""
+        cnt = np.zeros(_lib.NUM_COUNTERS, dtype=np.uint64)
+        rows = np.empty((max(capacity, 1), self.graph.NZ), dtype=np.float32)
+        n = ctypes.c_uint32(0)
+        _lib.check(_lib.load().ldpc_mc_run_host(self._h, float(sigma), int(n_frames), int(seed) & (2**64 - 1),
+                                                int(frame_offset), int(iters), 1 if early_term else 0, int(harvest),
+                                                cnt.ctypes.data, rows.ctypes.data if capacity > 0 else None,
+                                                int(capacity), ctypes.byref(n)))
+        return dict(zip(_lib.COUNTER_NAMES, (int(v) for v in cnt))), rows[:n.value]
+
+    def post_decode(self, words: torch.Tensor, iters: int = 0, early_term: bool = False,
+                    counters: Optional[torch.Tensor] = None):
+        """Run this (boosted) decoder on compacted uncorrected words: CUDA float32 [n, N*z] decoder-input
+        LLRs, e.g. the buffer mc_run filled (main_Post.py on Inputs/[Uncor]_*)."""
+        dev = self.device
+        n = words.shape[0]
+        if counters is None:
+            counters = torch.zeros((_lib.NUM_COUNTERS,), dtype=torch.int64, device=dev)
+        hard = torch.empty((n, self.hard_words), dtype=torch.int32, device=dev)
+        it = torch.empty((n,), dtype=torch.int32, device=dev)
+        fl = torch.empty((n,), dtype=torch.uint8, device=dev)
+        stream = torch.cuda.current_stream(dev).cuda_stream
+        _lib.check(_lib.load().ldpc_post_decode(self._h, _ptr(words.contiguous()), n, int(iters),
+                                                1 if early_term else 0, _ptr(counters), _ptr(hard), _ptr(it),
+                                                _ptr(fl), ctypes.c_void_p(stream)))
+        return counters, DecodeResult(None, hard, it, fl, torch.empty(0), None)
+
+
+# ---- PyTorch custom op: torch.ops.ldpc_b200.nms_decode(llr, handle, ...) -> (hard, iters, flags, biterr, app)
+_REGISTRY: Dict[int, "NMSDecoder"] = {}
+
+
+@torch.library.custom_op("ldpc_b200::nms_decode", mutates_args=(), device_types="cuda")
+def _nms_decode_op(llr: torch.Tensor, handle: int, iters: int, early_term: bool, app_mode: int) -> List[torch.Tensor]:
+    dec = _REGISTRY[handle]
+    app = {0: None, 1: "last", 2: "all"}[app_mode]
+    r = dec._decode_impl(llr, iters, early_term, app, True, False)
+    app_t = r.app if r.app is not None else torch.empty(0, device=llr.device)
+    return [r.hard_packed, r.iters, r.flags, r.biterr, app_t]
+
+
+@_nms_decode_op.register_fake
+def _(llr, handle, iters, early_term, app_mode):
+    dec = _REGISTRY[handle]
+    B = llr.shape[0]
+    T_run = dec.T if iters == 0 else iters
+    app = (torch.empty(0, device=llr.device) if app_mode == 0 else
+           llr.new_empty((B, dec.graph.NZ)) if app_mode == 1 else llr.new_empty((T_run, B, dec.graph.NZ)))
+    return [llr.new_empty((B, dec.hard_words), dtype=torch.int32), llr.new_empty((B,), dtype=torch.int32),
+            llr.new_empty((B,), dtype=torch.uint8), llr.new_empty((B,), dtype=torch.int32), app]
+
+
+def _decode_via_op(dec: NMSDecoder, llr, iters, early_term, app, want_hard, unpack) -> DecodeResult:
+    """Routes NMSDecoder.decode through torch.ops.ldpc_b200.nms_decode and re-wraps the outputs."""
+    _REGISTRY[id(dec)] = dec
+    try:
+        hard, it, fl, be, app_t = torch.ops.ldpc_b200.nms_decode(
+            llr, id(dec), int(iters), bool(early_term), {None: 0, "last": 1, "all": 2}[app])
+    finally:
+        _REGISTRY.pop(id(dec), None)
+    return DecodeResult(unpack_bits(hard, dec.graph.NZ) if unpack else None, hard if want_hard else None, it, fl,
+                        be, app_t if app is not None else None)

@@ -1,0 +1,231 @@
+"""Mints the committed golden fixtures from the reference's own code (Oracle A).
+
+Run ONLY in the development container (needs /root/reference, read-only):
+    python tests/golden/make_golden.py
+It imports /root/reference/Main_Functions.py and Print_Functions.py UNMODIFIED on top of the
+numpy stand-in for tensorflow.compat.v1 (oracle/tf_shim) -- see oracle/ref_runner.py -- and writes
+
+  codes.npz          every shipped BaseGraph/*.txt proto matrix, every shipped weight table
+                     (Weights/*.txt, Results/**.txt) and the init_parameter scalars per graph
+  decode_<case>.npz  channel LLRs from Print_Functions.create_mix_epoch + the per-iteration APP
+                     tensors build_neural_network produces for them (ya_output{t})
+  mc_wimax.npz       a small Print_Functions.compute_results run (Results[4,nSNR]) and the
+                     Uncor.txt it appended (format F3)
+
+The GPU box has no /root/reference; tests and bench.py read only these fixtures.
+"""
+import glob
+import os
+import sys
+import tempfile
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+sys.path.insert(0, ROOT)
+from ldpc_error_floor_b200 import formats  # noqa: E402
+from oracle import ref_runner  # noqa: E402
+
+REF = ref_runner.REFERENCE_ROOT
+OUT = os.path.dirname(os.path.abspath(__file__))
+
+GRAPHS = {
+    # key: (file stem, z, punct, short)
+    "wimax": ("wman_N0576_R34_z24", 24, (0, 0), (0, 0)),
+    "wifi": ("802_11n_N648_R56_z27", 27, (0, 0), (0, 0)),
+    "mackay": ("MACKAY_N96_K48", 1, (0, 0), (0, 0)),
+    "bch": ("BCH_63_51", 1, (0, 0), (0, 0)),
+    "polar": ("Polar_64_48", 1, (0, 0), (0, 0)),
+    "5g_r033_z32": ("5G_LDPC_R0.33_n_dec896_n768_k256_z32_s257_320", None, None, None),
+    "5g_r050_z32": ("5G_LDPC_R0.50_n_dec640_n512_k256_z32_s257_320", None, None, None),
+    "5g_r050_z64": ("5G_LDPC_R0.50_n_dec1280_n1024_k512_z64_s513_640", None, None, None),
+    "5g_r073_z32": ("5G_LDPC_R0.73_n_dec480_n352_k256_z32_s257_320", None, None, None),
+    "5g_r073_z72": ("5G_LDPC_R0.73_n_dec2304_n2112_k1536_z72_s1537_1584", None, None, None),
+}
+WEIGHTS = {
+    "wimax_base20": "Weights/C0_wman_N0576_R34_z24_Opt_Weight_End20.txt",
+    "wimax_boost50": "Results/WiMAX/Weights_Iter50.txt",
+    "wifi_boost50": "Results/WIFI/Weights_Iter50.txt",
+    "5g_r033_z32_boost50": "Results/5G/5G_LDPC_R0.33_n_dec896_n768_k256_z32_s257_320_Weight_End50.txt",
+    "5g_r050_z32_boost50": "Results/5G/5G_LDPC_R0.50_n_dec640_n512_k256_z32_s257_320_Weight_End50.txt",
+    "5g_r050_z64_boost50": "Results/5G/5G_LDPC_R0.50_n_dec1280_n1024_k512_z64_s513_640_Weight_End50.txt",
+    "5g_r073_z32_boost50": "Results/5G/5G_LDPC_R0.73_n_dec480_n352_k256_z32_s257_320_Weight_End50.txt",
+}
+
+
+def graph_meta(key):
+    stem, z, punct, short = GRAPHS[key]
+    path = os.path.join(REF, "BaseGraph", stem + ".txt")
+    proto = formats.read_base_graph(path)
+    if z is None:
+        m = formats.parse_5g_name(stem)
+        z, punct, short = m["z"], m["punct"], m["short"]
+    return stem, proto, z, punct, short
+
+
+def make_codes():
+    mf, _ = ref_runner.load_reference()
+    out = {}
+    snr = np.array([1.0, 2.0, 2.5, 3.0, 3.5, 4.0, 5.0])
+    for key in GRAPHS:
+        stem, proto, z, punct, short = graph_meta(key)
+        raw = open(os.path.join(REF, "BaseGraph", stem + ".txt"), "rb").read()
+        M, N, base, cn, vn, E, rate, sigma = mf.init_parameter(proto.astype(int), snr, z, punct[0], punct[1],
+                                                               short[0], short[1])
+        out[f"graph/{key}/proto"] = proto.astype(np.int16)
+        out[f"graph/{key}/meta"] = np.array([z, punct[0], punct[1], short[0], short[1], int(E)], dtype=np.int64)
+        out[f"graph/{key}/stem"] = np.array(stem)
+        out[f"graph/{key}/crlf"] = np.array(b"\r\n" in raw)
+        out[f"graph/{key}/rate_ref"] = np.array(rate, dtype=np.float64)
+        out[f"graph/{key}/sigma_ref"] = np.asarray(sigma, dtype=np.float64)
+        out[f"graph/{key}/cn_deg"] = np.asarray(cn, dtype=np.int64)
+        out[f"graph/{key}/vn_deg"] = np.asarray(vn, dtype=np.int64)
+    out["snr_grid"] = snr
+    for key, rel in WEIGHTS.items():
+        ws = formats.read_weights(os.path.join(REF, rel))
+        out[f"weights/{key}/sharing"] = np.array(ws.sharing, dtype=np.int64)
+        for i, b in ws.blocks.items():
+            out[f"weights/{key}/block{i}"] = b
+        out[f"weights/{key}/text"] = np.array(open(os.path.join(REF, rel), "r").read())
+    np.savez_compressed(os.path.join(OUT, "codes.npz"), **out)
+    print("codes.npz", len(out), "arrays")
+
+
+def ref_llrs(pf, sigmas, B, N, z, decoding_type, punct, short, q_bit, clip, seed):
+    word = np.random.RandomState(2042 + seed)      # main_Base.py:71-74
+    noise = np.random.RandomState(1074 + seed)
+    X, _ = pf.create_mix_epoch(np.asarray(sigmas), word, noise, B, N, N, z, [], True, decoding_type,
+                               punct[0], punct[1], short[0], short[1], q_bit, clip)
+    return np.asarray(X, dtype=np.float32)
+
+
+def make_decode_case(name, gkey, sharing, weights, T, decoding_type, q_bit, B, snr_db, seed=2, clip=20.0,
+                     raw_llr=False):
+    stem, proto, z, punct, short = graph_meta(gkey)
+    rd = ref_runner.ReferenceDecoder(proto.astype(int), z, sharing, weights, T, decoding_type, q_bit, clip,
+                                     punct, short, snr_db)
+    # raw_llr: feed UNQUANTISED channel LLRs to the quantised decoder (legal in the reference: the
+    # graph quantises its input itself, Main_Functions.py:176-177, 321-322)
+    X = ref_llrs(rd.pf, rd.snr_sigma, B, rd.N, z, 1 if raw_llr else decoding_type, punct, short, q_bit, clip, seed)
+    res = rd.decode(X)
+    out = {"proto": proto.astype(np.int16), "meta": np.array([z, punct[0], punct[1], short[0], short[1]]),
+           "sharing": np.array(sharing), "T": np.array(T), "decoding_type": np.array(decoding_type),
+           "q_bit": np.array(q_bit), "clip": np.array(clip, dtype=np.float32), "xa": X,
+           "app": res["app"].astype(np.float32), "sigma": np.asarray(rd.snr_sigma)}
+    for i in range(3):
+        if sharing[i] > 0:
+            out[f"w{i}"] = np.asarray(weights[i], dtype=np.float32)[:T]
+    np.savez_compressed(os.path.join(OUT, f"decode_{name}.npz"), **out)
+    hard_fail = ((res["app"][-1] >= 0).sum(axis=1) > 0).sum()
+    print(f"decode_{name}.npz  B={B} T={T}  frames still wrong at the end: {hard_fail}")
+
+
+def shipped(key):
+    ws = formats.read_weights(os.path.join(REF, WEIGHTS[key]))
+    return ws.sharing, ws.blocks
+
+
+def const_weights(sharing, T, M, N, E, cn=0.8, ucn=0.6, vn=1.0, rng=None):
+    width = lambda code, kind: {0: 0, 1: E, 2: (N if kind == 2 else M), 3: 1}[code]
+    vals = (cn, ucn, vn)
+    blocks = {}
+    for i in range(3):
+        if sharing[i] > 0:
+            w = np.full((T, width(sharing[i], i)), vals[i], dtype=np.float32)
+            if rng is not None:
+                w = (w + rng.uniform(-0.25, 0.25, size=w.shape)).astype(np.float32)
+            blocks[i] = w
+    return blocks
+
+
+def make_decode_cases():
+    sh, w = shipped("wimax_base20")
+    make_decode_case("wimax_qms_333_t20", "wimax", sh, w, 20, 2, 5, 8, [2.5, 3.0, 3.5, 4.0])
+    make_decode_case("wimax_float_333_t20", "wimax", sh, w, 20, 1, 5, 8, [2.5, 3.0, 3.5, 4.0])
+    make_decode_case("wimax_qms_303_t20", "wimax", [3, 0, 3], {0: w[0], 2: w[2]}, 20, 2, 5, 6, [3.0, 3.5])
+    make_decode_case("wimax_qmsraw_333_t20", "wimax", sh, w, 20, 2, 5, 6, [3.0, 3.5], raw_llr=True)
+    sh, w = shipped("wimax_boost50")
+    make_decode_case("wimax_qms_333_t50", "wimax", sh, w, 50, 2, 5, 6, [2.5, 3.0])
+    sh, w = shipped("wifi_boost50")
+    make_decode_case("wifi_qms_333_t50", "wifi", sh, w, 50, 2, 5, 6, [3.0, 3.5, 4.0])
+    sh, w = shipped("5g_r050_z64_boost50")
+    make_decode_case("5g_r050_z64_qms_222_t50", "5g_r050_z64", sh, w, 50, 2, 5, 4, [1.0, 2.0])
+    sh, w = shipped("5g_r073_z32_boost50")
+    make_decode_case("5g_r073_z32_qms_222_t50", "5g_r073_z32", sh, w, 50, 2, 5, 4, [3.0, 4.0])
+    make_decode_case("5g_r073_z32_float_222_t50", "5g_r073_z32", sh, w, 50, 1, 5, 4, [3.0, 4.0])
+    sh, w = shipped("5g_r033_z32_boost50")
+    make_decode_case("5g_r033_z32_qms_222_t20", "5g_r033_z32", sh, w, 20, 2, 5, 4, [0.0, 1.0])
+    rng = np.random.RandomState(7)
+    # no weights are shipped for these graphs: synthetic ones
+    _, p, z, _, _ = graph_meta("5g_r073_z72")
+    M, N = p.shape
+    E = int((p != -1).sum())
+    make_decode_case("5g_r073_z72_qms_222_t8", "5g_r073_z72", [2, 2, 2],
+                     const_weights([2, 2, 2], 8, M, N, E, rng=rng), 8, 2, 5, 2, [3.0, 4.0])
+    _, p, z, _, _ = graph_meta("mackay")
+    M, N = p.shape
+    E = int((p != -1).sum())
+    make_decode_case("mackay_float_300_t20", "mackay", [3, 0, 0], const_weights([3, 0, 0], 20, M, N, E), 20, 1, 5,
+                     16, [2.0, 3.0, 4.0, 5.0])
+    make_decode_case("mackay_qms_300_t20", "mackay", [3, 0, 0], const_weights([3, 0, 0], 20, M, N, E), 20, 2, 5,
+                     16, [2.0, 3.0, 4.0, 5.0])
+    _, p, z, _, _ = graph_meta("bch")
+    M, N = p.shape
+    E = int((p != -1).sum())
+    make_decode_case("bch_qms_333_t10", "bch", [3, 3, 3], const_weights([3, 3, 3], 10, M, N, E, rng=rng), 10, 2, 5,
+                     8, [3.0, 5.0])
+    _, p, z, _, _ = graph_meta("polar")
+    M, N = p.shape
+    E = int((p != -1).sum())
+    make_decode_case("polar_qms_223_t6", "polar", [2, 2, 3], const_weights([2, 2, 3], 6, M, N, E, rng=rng), 6, 2, 5,
+                     8, [3.0, 5.0])
+    make_decode_case("polar_float_300_t6", "polar", [3, 0, 0], const_weights([3, 0, 0], 6, M, N, E), 6, 1, 5,
+                     8, [3.0, 5.0])
+    # per-edge weights (sharing code 1) and the other quantisers, on WiMAX
+    _, p, z, _, _ = graph_meta("wimax")
+    M, N = p.shape
+    E = int((p != -1).sum())
+    make_decode_case("wimax_qms_112_t6", "wimax", [1, 1, 2], const_weights([1, 1, 2], 6, M, N, E, rng=rng), 6, 2, 5,
+                     4, [3.0, 3.5])
+    make_decode_case("wimax_float_102_t6", "wimax", [1, 0, 2], const_weights([1, 0, 2], 6, M, N, E, rng=rng), 6, 1,
+                     5, 4, [3.0, 3.5])
+    for qb in (6, -5, 4, 3):
+        make_decode_case(f"wimax_qms_q{qb}_323_t6".replace("-", "m"), "wimax", [3, 3, 3],
+                         const_weights([3, 3, 3], 6, M, N, E, rng=rng), 6, 2, qb, 4, [3.0, 3.5])
+    make_decode_case("wimax_qms_000_t5", "wimax", [0, 0, 0], {}, 5, 2, 5, 4, [3.0, 3.5])
+
+
+def make_mc():
+    """compute_results exactly as main_Base.py:177 calls it at epoch 0 with sampling_type=2."""
+    sh, w = shipped("wimax_base20")
+    stem, proto, z, punct, short = graph_meta("wimax")
+    snr = [2.5, 3.0]
+    rd = ref_runner.ReferenceDecoder(proto.astype(int), z, sh, w, 20, 2, 5, 20.0, punct, short, snr)
+    with tempfile.TemporaryDirectory() as tmp:
+        # sampling_type 2 insists on one SNR point (Main_Functions.py:502-505): run the points one by one
+        results, texts = [], []
+        for k, s in enumerate(snr):
+            rd1 = ref_runner.ReferenceDecoder(proto.astype(int), z, sh, w, 20, 2, 5, 20.0, punct, short, [s])
+            res, _ = rd1.compute_results(200, 2044, 1076, 20, sampling_type=2, cwd=tmp)
+            results.append(res[:, 0])
+            path = os.path.join(tmp, "Uncor.txt")
+            texts.append(open(path).read() if os.path.exists(path) else "")
+            if os.path.exists(path):
+                os.remove(path)
+    np.savez_compressed(os.path.join(OUT, "mc_wimax.npz"), snr=np.array(snr), results=np.stack(results, axis=1),
+                        sigma=np.asarray(rd.snr_sigma), uncor_text_0=np.array(texts[0]),
+                        uncor_text_1=np.array(texts[1]), sample_num=np.array(200), batch=np.array(20),
+                        seeds=np.array([2044, 1076]))
+    print("mc_wimax.npz", np.stack(results, axis=1))
+
+
+if __name__ == "__main__":
+    if not ref_runner.reference_available():
+        raise SystemExit("needs /root/reference (development container only)")
+    what = sys.argv[1:] or ["codes", "decode", "mc"]
+    if "codes" in what:
+        make_codes()
+    if "decode" in what:
+        make_decode_cases()
+    if "mc" in what:
+        make_mc()

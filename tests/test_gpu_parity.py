@@ -1,0 +1,132 @@
+"""GPU parity: the CUDA path (through the C-ABI) against the golden vectors minted from the
+reference's own code, and against the C oracle on larger seeded batches.
+
+Pass criteria (BASELINE.json north_star): quantised path bit-exact (APP, hard decisions, syndrome
+flags); float path: hard decisions identical, APP within 1e-5 relative."""
+import numpy as np
+import pytest
+
+from conftest import all_cases, load_case
+
+pytestmark = pytest.mark.gpu
+
+REL_TOL = 1e-5   # float min-sum: |a-b| <= REL_TOL * max(1, |b|)
+
+
+def build_decoder(case, iters=None):
+    import ldpc_error_floor_b200 as L
+    g = L.BaseGraph(case["proto"], case["z"], case["punct"], case["short"])
+    ws = L.WeightSet(case["sharing"], {i: w for i, w in case["weights"].items()})
+    dec = L.NMSDecoder(g, ws, iters=case["T"] if iters is None else iters, decoding_type=case["decoding_type"],
+                       q_bit=case["q_bit"], clip_llr=case["clip"])
+    return g, dec
+
+
+def oracle_flags(g, app):
+    """app [T,B,NZ] -> per-frame reference observables (Print_Functions.py:100-118 + syndrome)."""
+    hard = app >= 0
+    T, B, _ = app.shape
+    synd_ok = np.stack([g.syndrome_ok(hard[t]) for t in range(T)])          # [T,B]
+    any_one = hard.any(axis=2)                                              # [T,B]
+    uncor_any = any_one.all(axis=0)
+    iters = np.where(synd_ok.any(axis=0), synd_ok.argmax(axis=0) + 1, T)
+    return hard, synd_ok, any_one, uncor_any, iters
+
+
+@pytest.mark.parametrize("name", all_cases())
+def test_golden_decode(name):
+    import torch
+    case = load_case(name)
+    g, dec = build_decoder(case)
+    xa = torch.from_numpy(case["xa"]).cuda()
+    r = dec.decode(xa, app="all", unpack=True)
+    app = r.app.cpu().numpy()
+    ref = case["app"]
+    assert app.shape == ref.shape
+    hard_ref, synd_ok, any_one, uncor_any, iters = oracle_flags(g, ref)
+    if case["decoding_type"] == 2:
+        assert np.array_equal(app, ref), f"max |diff| {np.abs(app - ref).max()}"
+    else:
+        err = np.abs(app - ref) / np.maximum(1.0, np.abs(ref))
+        assert err.max() <= REL_TOL, f"max rel diff {err.max()}"
+        assert np.array_equal(app >= 0, hard_ref)
+    T = case["T"]
+    assert np.array_equal(r.hard.cpu().numpy().astype(bool), hard_ref[T - 1])
+    flags = r.flags.cpu().numpy()
+    assert np.array_equal((flags & 1) != 0, synd_ok[T - 1])
+    assert np.array_equal((flags & 2) != 0, uncor_any)
+    assert np.array_equal((flags & 4) != 0, any_one[T - 1])
+    assert np.array_equal((flags & 8) != 0, synd_ok.any(axis=0))
+    assert np.array_equal(r.iters.cpu().numpy(), iters)
+    assert np.array_equal(r.biterr.cpu().numpy(), hard_ref[T - 1].sum(axis=1))
+    # ya_output_all layout == concat over iterations (Main_Functions.py:380-383)
+    assert np.array_equal(dec.ya_output_all(xa).cpu().numpy(), app.reshape(-1, app.shape[-1]))
+
+
+@pytest.mark.parametrize("name", ["wimax_qms_333_t20", "5g_r073_z32_qms_222_t50", "wimax_float_333_t20",
+                                  "mackay_qms_300_t20"])
+def test_golden_early_termination(name):
+    """With early termination a frame stops at the first zero syndrome: its outputs must equal the
+    reference's at that iteration; frames that never converge match the last iteration."""
+    import torch
+    case = load_case(name)
+    g, dec = build_decoder(case)
+    xa = torch.from_numpy(case["xa"]).cuda()
+    ref = case["app"]
+    hard_ref, synd_ok, any_one, uncor_any, iters = oracle_flags(g, ref)
+    r = dec.decode(xa, early_term=True, app="last", unpack=True)
+    T = case["T"]
+    stop = iters - 1   # iteration index whose decision is output
+    B = ref.shape[1]
+    want_hard = np.stack([hard_ref[stop[b], b] for b in range(B)])
+    assert np.array_equal(r.iters.cpu().numpy(), iters)
+    assert np.array_equal(r.hard.cpu().numpy().astype(bool), want_hard)
+    app = r.app.cpu().numpy()
+    want_app = np.stack([ref[stop[b], b] for b in range(B)])
+    if case["decoding_type"] == 2:
+        assert np.array_equal(app, want_app)
+    else:
+        assert (np.abs(app - want_app) / np.maximum(1, np.abs(want_app))).max() <= REL_TOL
+    flags = r.flags.cpu().numpy()
+    assert np.array_equal((flags & 1) != 0, np.array([synd_ok[stop[b], b] for b in range(B)]))
+    assert np.array_equal((flags & 4) != 0, np.array([any_one[stop[b], b] for b in range(B)]))
+
+
+@pytest.mark.parametrize("name,B", [("wimax_qms_333_t20", 3000), ("wifi_qms_333_t50", 700),
+                                    ("5g_r050_z64_qms_222_t50", 500), ("wimax_float_333_t20", 1500),
+                                    ("bch_qms_333_t10", 900), ("mackay_float_300_t20", 2500)])
+def test_against_c_oracle_large(name, B):
+    """Seeded batches big enough to exercise many CTAs, ragged tails and the persistent loop,
+    checked against oracle/nms_oracle.c (itself pinned to the goldens)."""
+    import torch
+    from oracle import c_oracle
+    case = load_case(name)
+    g, dec = build_decoder(case)
+    rng = np.random.RandomState(1234)
+    sig = float(np.mean(g.sigma([3.0])))
+    xa = (2.0 * (rng.normal(size=(B, g.N, g.z)) * sig - 1.0) / sig ** 2).astype(np.float32)
+    if case["decoding_type"] == 2:
+        xa = np.clip(np.rint(xa * 2) / 2, -7.5, 7.5).astype(np.float32)
+    if case["punct"][0] > 0:
+        xa.reshape(B, -1)[:, case["punct"][0] - 1:case["punct"][1]] = 0
+    if case["short"][0] > 0:
+        xa.reshape(B, -1)[:, case["short"][0] - 1:case["short"][1]] = -case["clip"]
+    T = case["T"]
+    ref = c_oracle.decode(case["proto"], case["z"], xa, case["sharing"], case["weights"], T, case["decoding_type"],
+                          case["q_bit"], case["clip"], want_all=False)
+    r = dec.decode(torch.from_numpy(xa).cuda(), app="last", unpack=True)
+    app = r.app.cpu().numpy()
+    if case["decoding_type"] == 2:
+        assert np.array_equal(app, ref["app_last"])
+    else:
+        err = np.abs(app - ref["app_last"]) / np.maximum(1, np.abs(ref["app_last"]))
+        assert err.max() <= REL_TOL
+        assert np.array_equal(app >= 0, ref["app_last"] >= 0)
+    assert np.array_equal((r.flags.cpu().numpy() & 1) != 0, ~ref["synd"][T - 1])
+    synd_ok = ~ref["synd"]
+    iters = np.where(synd_ok.any(axis=0), synd_ok.argmax(axis=0) + 1, T)
+    assert np.array_equal(r.iters.cpu().numpy(), iters)
+    # host-buffer entry point gives the same answer
+    h = dec.decode_host(xa, app=None)
+    assert np.array_equal(h["hard_packed"].view(np.int32), r.hard_packed.cpu().numpy())
+    assert np.array_equal(h["flags"], r.flags.cpu().numpy())

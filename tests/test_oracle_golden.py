@@ -1,0 +1,51 @@
+"""CPU: pins the oracle restatements (oracle/nms_oracle.py, oracle/nms_oracle.c) to the golden
+vectors minted from the reference's own build_neural_network (tests/golden/make_golden.py)."""
+import numpy as np
+import pytest
+
+from conftest import all_cases, load_case
+
+REL_TOL = 1e-5
+
+
+def _check(case, app):
+    ref = case["app"]
+    if case["decoding_type"] == 2:
+        assert np.array_equal(app, ref), f"max |diff| {np.abs(app - ref).max()}"
+    else:
+        err = np.abs(app - ref) / np.maximum(1.0, np.abs(ref))
+        assert err.max() <= REL_TOL
+        assert np.array_equal(app >= 0, ref >= 0)
+
+
+@pytest.mark.parametrize("name", all_cases())
+def test_c_oracle_matches_golden(name):
+    from oracle import c_oracle
+    case = load_case(name)
+    out = c_oracle.decode(case["proto"], case["z"], case["xa"], case["sharing"], case["weights"], case["T"],
+                          case["decoding_type"], case["q_bit"], case["clip"])
+    _check(case, out["app"])
+
+
+@pytest.mark.parametrize("name", ["wimax_qms_333_t20", "wimax_float_333_t20", "5g_r073_z32_qms_222_t50",
+                                  "wimax_qms_112_t6", "polar_qms_223_t6", "wimax_qms_q3_323_t6", "wimax_qms_q6_323_t6"])
+def test_numpy_oracle_matches_golden(name):
+    from oracle import nms_oracle as ob
+    case = load_case(name)
+    g = ob.OracleGraph(case["proto"], case["z"], case["punct"], case["short"])
+    out = ob.decode(g, case["xa"][:3], case["sharing"], case["weights"], case["T"], case["decoding_type"],
+                    case["q_bit"], case["clip"])
+    sub = dict(case)
+    sub["app"] = case["app"][:, :3]
+    _check(sub, out["app"])
+
+
+@pytest.mark.parametrize("name", ["wimax_qms_333_t20", "wimax_float_333_t20", "bch_qms_333_t10"])
+def test_c_oracle_naive_equals_fast(name):
+    from oracle import c_oracle
+    case = load_case(name)
+    a = c_oracle.decode(case["proto"], case["z"], case["xa"], case["sharing"], case["weights"], case["T"],
+                        case["decoding_type"], case["q_bit"], case["clip"], naive=False)
+    b = c_oracle.decode(case["proto"], case["z"], case["xa"], case["sharing"], case["weights"], case["T"],
+                        case["decoding_type"], case["q_bit"], case["clip"], naive=True)
+    assert np.array_equal(a["app"], b["app"]) and np.array_equal(a["synd"], b["synd"])
