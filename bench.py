@@ -314,7 +314,7 @@ def main():
     sm_now = clocks.get("sm_mhz") or sm_max
     hbm_bytes = B * (NZ * 4 + dec.hard_words * 4 + 4 + 1)
     roofline = {
-        "bound": "alu", "kernel": "nms_h2_kernel_16_8" if dec.packed else "nms_f32_kernel_16_8",
+        "bound": "alu", "kernel": dec.kernel_name,
         "achieved": ach, "peak": alu_peak, "unit": "Tlaneop/s", "frac": ach / alu_peak,
         "peak_source": f"148 SMs x 128 lanes x clocks.max.sm {sm_max:.0f} MHz (issue-slot roof; MEASURED_PEAKS.json "
                        f"carries no ALU figure)",

@@ -110,6 +110,8 @@ int ldpc_decoder_create(const ldpc_graph_t *g, const int32_t sharing[3], int32_t
 int ldpc_decoder_destroy(ldpc_decoder_t *d);
 /* 1 if the packed-fp16x2 kernel serves this decoder, 0 if the float32 kernel does */
 int ldpc_decoder_uses_packed_kernel(const ldpc_decoder_t *d);
+/* name of the __global__ function that serves this decoder (graph-specialised or generic bucket) */
+const char *ldpc_decoder_kernel_name(const ldpc_decoder_t *d);
 /* frames decoded per CTA and CTAs per SM the launcher will use (for sizing batches) */
 int ldpc_decoder_geometry(const ldpc_decoder_t *d, int32_t *frames_per_cta, int32_t *ctas_per_sm,
                           int32_t *threads_per_cta, int32_t *smem_bytes);

@@ -51,6 +51,7 @@ SYMBOLS = {
                                            ctypes.POINTER(_P)]),
     "ldpc_decoder_destroy": (ctypes.c_int, [_P]),
     "ldpc_decoder_uses_packed_kernel": (ctypes.c_int, [_P]),
+    "ldpc_decoder_kernel_name": (ctypes.c_char_p, [_P]),
     "ldpc_decoder_geometry": (ctypes.c_int, [_P, ctypes.POINTER(_I32), ctypes.POINTER(_I32),
                                              ctypes.POINTER(_I32), ctypes.POINTER(_I32)]),
     "ldpc_decode": (ctypes.c_int, [_P, _P, _I64, _I32, _I32, _P, _I32, _P, _P, _P, _P, _P]),

@@ -95,6 +95,7 @@ struct ldpc_decoder {
     bool packed = false;
     const void *func = nullptr;
     int dcb = 0, dvb = 0;
+    const char *spec_name = nullptr;
     LaunchGeom geom{};
     KParams base{};
     float *d_w = nullptr;
@@ -224,26 +225,38 @@ const void *pick_kernel(bool packed, int max_dc, int max_dv, int *dcb, int *dvb)
     return nms_f32_func_0_0();
 }
 
-constexpr int MISC_WORDS_HOST = NMS_MISC_WORDS;
-
 void fill_smem_layout(KParams *P, bool packed) {
-    int off = 0;
-    P->off_msg = off; off += P->E * P->LP;
+    int off = P->E * P->LP;                 // message array at word 0
     off = (off + 3) & ~3;
     P->off_xa = off; off += P->N * P->LP * (packed ? 2 : 1);
     P->off_xq = off; off += (packed || P->qms) ? P->N * P->LP : 0;
     P->off_hb = off; off += 2 * (packed ? 2 : 1) * P->N * P->C;
-    P->off_misc = off; off += MISC_WORDS_HOST;
+    P->off_w = off; off += P->w_staged ? P->w_words : 0;
+    P->off_misc = off; off += NMS_MISC_WORDS;
     P->smem_words = off;
 }
 
+unsigned long long graph_hash(const ldpc_graph &g) {   // FNV-1a over (M, N, z, proto[]) -- same as gen_spec.py
+    unsigned long long h = 0xcbf29ce484222325ull;
+    auto mix = [&](int v) {
+        unsigned u = (unsigned)v;
+        for (int k = 0; k < 4; ++k) { h ^= (u >> (8 * k)) & 0xffu; h *= 0x100000001b3ull; }
+    };
+    mix(g.M); mix(g.N); mix(g.z);
+    for (int v : g.proto) mix(v);
+    return h;
+}
+
 // pick (Fp, R): lane efficiency x task balance x achievable warps/SM (from the real occupancy calculator)
-int choose_geometry(const ldpc_graph &g, bool packed, bool qms, const void *func, LaunchGeom *out) {
+int choose_geometry(const ldpc_graph &g, bool packed, bool qms, int w_words, const void *func, int force_fp,
+                    int force_r, LaunchGeom *out) {
     const int max_smem = 227 * 1024;
     double best = -1.0;
-    int forced_fp = 0, forced_r = 0;
-    if (const char *s = getenv("LDPC_B200_FP")) forced_fp = atoi(s);
-    if (const char *s = getenv("LDPC_B200_R")) forced_r = atoi(s);
+    int forced_fp = force_fp, forced_r = force_r;
+    if (!force_fp) {
+        if (const char *s = getenv("LDPC_B200_FP")) forced_fp = atoi(s);
+        if (const char *s = getenv("LDPC_B200_R")) forced_r = atoi(s);
+    }
     const int fp_max = packed ? LDPC_MAX_FB / 2 : LDPC_MAX_FB;
     CUDA_TRY(cudaFuncSetAttribute(func, cudaFuncAttributeMaxDynamicSharedMemorySize, max_smem));
     for (int Fp = 1; Fp <= fp_max; ++Fp) {
@@ -252,6 +265,7 @@ int choose_geometry(const ldpc_graph &g, bool packed, bool qms, const void *func
         if (C > 16) break;
         KParams tmp{};
         tmp.E = g.E; tmp.N = g.N; tmp.LP = LP; tmp.C = C; tmp.qms = qms;
+        tmp.w_words = w_words; tmp.w_staged = w_words > 0 && w_words <= NMS_WSTAGE_MAX_WORDS;
         fill_smem_layout(&tmp, packed);
         const int smem = tmp.smem_words * 4;
         if (smem > max_smem) break;
@@ -306,14 +320,14 @@ extern "C" int ldpc_decoder_create(const ldpc_graph_t *g, const int32_t sharing[
         return fail(LDPC_E_INVALID, "sharing[1] != 0 and sharing[0] != sharing[1] (Main_Functions.py:519-521)");
     if (decoding_type != 1 && decoding_type != 2)
         return fail(LDPC_E_UNSUPPORTED, "decoding_type %d (1 = min-sum, 2 = quantised min-sum)", decoding_type);
-    float qk = 1.f, qinv = 1.f, qmax = 0.f;
+    float qk = 1.f, qmax = 0.f;
     if (decoding_type == 2) {
         switch (q_bit) {   // Main_Functions.py:483-492
-        case 5: qk = 2.f; qinv = 0.5f; qmax = 7.5f; break;
-        case 6: qk = 1.f; qinv = 1.f; qmax = 15.5f; break;
-        case -5: qk = 1.f; qinv = 1.f; qmax = 15.f; break;
-        case 4: qk = 1.f; qinv = 1.f; qmax = 7.f; break;
-        case 3: qk = 0.5f; qinv = 2.f; qmax = 6.f; break;
+        case 5: qk = 2.f; qmax = 7.5f; break;
+        case 6: qk = 1.f; qmax = 15.5f; break;
+        case -5: qk = 1.f; qmax = 15.f; break;
+        case 4: qk = 1.f; qmax = 7.f; break;
+        case 3: qk = 0.5f; qmax = 6.f; break;
         default: return fail(LDPC_E_INVALID, "q_bit %d has no quantiser branch", q_bit);
         }
     }
@@ -341,26 +355,65 @@ extern "C" int ldpc_decoder_create(const ldpc_graph_t *g, const int32_t sharing[
     // packed fp16x2 kernel: uniform quantiser grids closed under addition, no per-edge weights
     d->packed = qms && q_bit != 6 && sharing[0] != 1 && g->info.max_dv <= 30 && !getenv("LDPC_B200_FORCE_F32");
     if (!d->packed && g->info.max_dv > 64) { delete d; return fail(LDPC_E_LIMIT, "column degree > 64 in float mode"); }
-    d->func = pick_kernel(d->packed, g->info.max_dc, g->info.max_dv, &d->dcb, &d->dvb);
     cudaDeviceProp prop;
     if (cudaGetDeviceProperties(&prop, device) != cudaSuccess) { delete d; return fail(LDPC_E_CUDA, "cudaGetDeviceProperties"); }
     d->sm_count = prop.multiProcessorCount;
-    int rc = choose_geometry(d->g, d->packed, qms, d->func, &d->geom);
+    int wc = weight_width(sharing[0], 0, g->M, g->N, g->E), wu = weight_width(sharing[1], 1, g->M, g->N, g->E),
+        wv = weight_width(sharing[2], 2, g->M, g->N, g->E);
+    // host copy of the device weight block [cn | ucn | vn]; the packed kernels get an "effective" block:
+    // a row of ones where the reference applies no CN weight (Main_Functions.py:267-268)
+    std::vector<float> wh;
+    const bool ones_cn = d->packed && sharing[0] == 0;
+    if (ones_cn) { wc = 1; wh.assign((size_t)T, 1.0f); }
+    else if (wc) wh.assign(w_cn, w_cn + (size_t)T * wc);
+    if (wu) wh.insert(wh.end(), w_ucn, w_ucn + (size_t)T * wu);
+    if (wv) wh.insert(wh.end(), w_vn, w_vn + (size_t)T * wv);
+    if (d->packed && (int)wh.size() > NMS_WSTAGE_MAX_WORDS) d->packed = false;   // weights must fit in shared memory
+    if (!d->packed && ones_cn) { wc = 0; wh.erase(wh.begin(), wh.begin() + T); }
+    const int w_words = (int)wh.size();
+    // a graph known at build time gets its specialised kernel (gen_spec.py); anything else the generic buckets
+    int rc = LDPC_E_LIMIT;
+    d->func = nullptr;
+    if (d->packed && !getenv("LDPC_B200_NO_SPEC")) {
+        int n = 0;
+        const NmsSpecEntry *tab = nms_spec_table(&n);
+        const unsigned long long h = graph_hash(d->g);
+        for (int k = 0; k < n; ++k) {
+            if (tab[k].graph_hash != h || tab[k].M != g->M || tab[k].N != g->N || tab[k].z != g->z) continue;
+            const void *f = tab[k].func();
+            LaunchGeom geo{};
+            if (choose_geometry(d->g, true, qms, w_words, f, tab[k].Fp, tab[k].R, &geo) == LDPC_OK) {
+                d->func = f; d->geom = geo; d->spec_name = tab[k].name; rc = LDPC_OK;
+                break;
+            }
+        }
+    }
+    if (d->func == nullptr) {
+        d->func = pick_kernel(d->packed, g->info.max_dc, g->info.max_dv, &d->dcb, &d->dvb);
+        rc = choose_geometry(d->g, d->packed, qms, w_words, d->func, 0, 0, &d->geom);
+    }
     if (rc != LDPC_OK) { delete d; return rc; }
 
     KParams &P = d->base;
     std::memset(&P, 0, sizeof P);
     P.M = g->M; P.N = g->N; P.E = g->E; P.z = g->z; P.NZ = g->N * g->z;
     P.Fp = d->geom.Fp; P.FB = d->geom.FB; P.L = d->geom.L; P.LP = d->geom.LP; P.C = d->geom.C; P.R = d->geom.R;
-    P.qms = qms; P.qk = qk; P.qinv = qinv; P.qmax = qmax; P.qmaxk = qmax * qk; P.clip = clip_llr;
+    P.qms = qms; P.qmagic = 12582912.0f / qk; P.qmax = qmax; P.clip = clip_llr;
     P.sharing0 = sharing[0]; P.sharing1 = sharing[1]; P.sharing2 = sharing[2];
-    P.wc = weight_width(sharing[0], 0, g->M, g->N, g->E);
-    P.wu = weight_width(sharing[1], 1, g->M, g->N, g->E);
-    P.wv = weight_width(sharing[2], 2, g->M, g->N, g->E);
+    P.wc = wc; P.wu = wu; P.wv = wv;
+    P.w_words = (int)wh.size(); P.w_staged = P.w_words > 0 && P.w_words <= NMS_WSTAGE_MAX_WORDS;
+    P.w_off_cn = 0; P.w_off_ucn = T * wc; P.w_off_vn = T * (wc + wu);
     P.T_run = T;
     P.punct_s = g->punct_s; P.punct_e = g->punct_e; P.short_s = g->short_s; P.short_e = g->short_e;
     P.HW = (P.NZ + 31) / 32;
     fill_smem_layout(&P, d->packed);
+    if (d->packed) {
+        P.h2w_c = P.off_w + P.w_off_cn; P.h2_wc = wc; P.h2_mc = wc > 1 ? -1 : 0;
+        if (wu) { P.h2w_u = P.off_w + P.w_off_ucn; P.h2_wu = wu; P.h2_mu = wu > 1 ? -1 : 0; }
+        else { P.h2w_u = P.h2w_c; P.h2_wu = P.h2_wc; P.h2_mu = P.h2_mc; }
+        P.h2w_v = P.off_w + P.w_off_vn; P.h2_wv = wv; P.h2_mv = wv > 1 ? -1 : 0;
+    }
+    if (P.smem_words * 4 != d->geom.smem_bytes) { delete d; return fail(LDPC_E_INVALID, "internal: smem layout mismatch"); }
     for (int i = 0; i <= g->M; ++i) P.row_ptr[i] = (unsigned short)g->row_ptr[i];
     for (int j = 0; j <= g->N; ++j) P.col_ptr[j] = (unsigned short)g->col_ptr[j];
     {
@@ -379,22 +432,14 @@ extern "C" int ldpc_decoder_create(const ldpc_graph_t *g, const int32_t sharing[
         P.vn_edge[k].x = e * P.LP;
         P.vn_edge[k].y = (P.L - g->shift[e] * P.Fp) % P.L;   // variable lane q -> check lane (q - s*Fp) mod L
     }
-    // weights -> one device block [cn | ucn | vn]
-    const size_t n_c = (size_t)T * P.wc, n_u = (size_t)T * P.wu, n_v = (size_t)T * P.wv;
-    if (n_c + n_u + n_v > 0) {
-        std::vector<float> host(n_c + n_u + n_v);
-        if (n_c) std::memcpy(host.data(), w_cn, n_c * sizeof(float));
-        if (n_u) std::memcpy(host.data() + n_c, w_ucn, n_u * sizeof(float));
-        if (n_v) std::memcpy(host.data() + n_c + n_u, w_vn, n_v * sizeof(float));
-        if (cudaMalloc(&d->d_w, host.size() * sizeof(float)) != cudaSuccess ||
-            cudaMemcpy(d->d_w, host.data(), host.size() * sizeof(float), cudaMemcpyHostToDevice) != cudaSuccess) {
+    if (!wh.empty()) {
+        if (cudaMalloc(&d->d_w, wh.size() * sizeof(float)) != cudaSuccess ||
+            cudaMemcpy(d->d_w, wh.data(), wh.size() * sizeof(float), cudaMemcpyHostToDevice) != cudaSuccess) {
             const char *msg = cudaGetErrorString(cudaGetLastError());
             delete d;
             return fail(LDPC_E_CUDA, "uploading weights: %s", msg);
         }
-        P.w_cn = n_c ? d->d_w : nullptr;
-        P.w_ucn = n_u ? d->d_w + n_c : nullptr;
-        P.w_vn = n_v ? d->d_w + n_c + n_u : nullptr;
+        P.w_all = d->d_w;
     }
     *out = d;
     return LDPC_OK;
@@ -424,6 +469,14 @@ extern "C" int ldpc_decoder_destroy(ldpc_decoder_t *d) {
 }
 
 extern "C" int ldpc_decoder_uses_packed_kernel(const ldpc_decoder_t *d) { return d && d->packed ? 1 : 0; }
+
+extern "C" const char *ldpc_decoder_kernel_name(const ldpc_decoder_t *d) {
+    static thread_local char buf[96];
+    if (!d) return "";
+    if (d->spec_name) snprintf(buf, sizeof buf, "nms_h2_spec_%s", d->spec_name);
+    else snprintf(buf, sizeof buf, "nms_%s_kernel_%d_%d", d->packed ? "h2" : "f32", d->dcb, d->dvb);
+    return buf;
+}
 
 extern "C" int ldpc_decoder_geometry(const ldpc_decoder_t *d, int32_t *frames_per_cta, int32_t *ctas_per_sm,
                                      int32_t *threads_per_cta, int32_t *smem_bytes) {

@@ -17,6 +17,8 @@
 #define LDPC_MAX_E 1024
 #define LDPC_MAX_FB 64   // frames per CTA
 #define LDPC_MAX_T 256
+#define NMS_MISC_WORDS 400        // per-CTA bookkeeping words (nms_device.cuh)
+#define NMS_WSTAGE_MAX_WORDS 8192 // weights are staged in shared memory when they fit in this many floats
 
 // tables + scalars, passed as ONE __grid_constant__ kernel parameter (constant bank, LDC/ULDC)
 struct KParams {
@@ -30,12 +32,18 @@ struct KParams {
     int R;    // task slots (warps per chunk); CTA = C*R warps
     // arithmetic
     int qms;           // 1: quantised min-sum
-    float qk, qinv;    // Q(x) = clamp(rint(x*qk), +-qmaxk) * qinv      (Main_Functions.py:483-492)
-    float qmaxk, qmax; // qmax*qk, qmax
+    float qmagic;      // 1.5*2^23/qk: (x + qmagic) - qmagic rounds x half-to-even to the quantiser step 1/qk
+    float qmax;        // Q(x) = clamp(round_to_step(x), +-qmax)            (Main_Functions.py:483-492)
     float clip;        // clip_LLR (main_Base.py:69)
     int sharing0, sharing1, sharing2;
     int wc, wu, wv;    // weight row widths
-    const float *w_cn, *w_ucn, *w_vn;   // device [T, width]
+    const float *w_all;   // device [T*wc | T*wu | T*wv]
+    int w_staged;      // 1: the three blocks are copied to shared memory at off_w (same layout)
+    int w_off_cn, w_off_ucn, w_off_vn, w_words;   // float offsets inside w_all / the staged copy
+    // packed kernels: weights are ALWAYS staged and indexed branch-free:
+    //   w = smem_f(h2w_X + t*h2_wX + (node & h2_mX)), X in {c (CN), u (UCN), v (VN)};
+    // "no weight" is a staged row of 1.0f, "no UCN weight" aliases the CN block.
+    int h2w_c, h2w_u, h2w_v, h2_wc, h2_wu, h2_wv, h2_mc, h2_mu, h2_mv;
     int T_run, early_term;
     // source: llr != nullptr -> global LLRs; else Philox generator
     const float *llr;
@@ -49,8 +57,8 @@ struct KParams {
     int *iters; uint8_t *flags; int *biterr;
     unsigned long long *counters;
     float *uncor_buf; unsigned int *uncor_count; unsigned int uncor_cap; int harvest_mode;
-    // shared-memory carve-up (word offsets)
-    int off_msg, off_xa, off_xq, off_hb, off_misc, smem_words;
+    // shared-memory carve-up (word offsets; the message array always starts at word 0)
+    int off_xa, off_xq, off_hb, off_w, off_misc, smem_words;
     // tables
     unsigned short row_ptr[LDPC_MAX_M + 1];   // E(C) edges of proto row i: [row_ptr[i], row_ptr[i+1])
     unsigned short col_ptr[LDPC_MAX_N + 1];   // CSR by proto column into vn_edge
@@ -64,6 +72,15 @@ struct KParams {
 struct LaunchGeom {
     int Fp, FB, L, LP, C, R, threads, smem_bytes, ctas_per_sm;
 };
+
+// one graph-specialised kernel (generated at build time by csrc/gen_spec.py)
+struct NmsSpecEntry {
+    const char *name;
+    unsigned long long graph_hash;   // FNV-1a over (M, N, z, proto[])
+    int M, N, z, E, Fp, R;
+    const void *(*func)();
+};
+extern "C" const NmsSpecEntry *nms_spec_table(int *count);
 
 // ---- Philox4x32-10 (Salmon et al., SC'11), written out so the host tests can restate it
 __host__ __device__ __forceinline__ void philox4x32_10(uint32_t c0, uint32_t c1, uint32_t c2, uint32_t c3,
@@ -79,8 +96,6 @@ __host__ __device__ __forceinline__ void philox4x32_10(uint32_t c0, uint32_t c1,
     }
     out[0] = c0; out[1] = c1; out[2] = c2; out[3] = c3;
 }
-
-#define NMS_MISC_WORDS 400   // per-CTA bookkeeping words at the end of shared memory (nms_device.cuh)
 
 cudaError_t nms_launch_generate(const KParams &P, float *out, long long n_frames, cudaStream_t st);
 void nms_note_launch();

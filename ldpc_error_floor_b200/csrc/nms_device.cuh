@@ -4,18 +4,24 @@
 //   load (global LLRs | fused Philox BPSK/AWGN generator)  ->  T x { CN phase ; VN phase }
 //   -> final syndrome pass -> outputs (packed hard bits, flags, counters, harvested words).
 // HBM sees LLRs in and bits/flags out; every edge message lives in shared memory / registers.
-// The arithmetic back-end is a Policy (nms_h2.cu / nms_f32.cu) providing
-//   cn_task(P,c,i,t,bad)  vn_task<INIT>(P,c,j,t,ones)  synd_row(P,c,i,tl)
+// The arithmetic back-end is a Policy (nms_h2.cuh / nms_f32.cu / generated graph-specialised
+// policies) providing
+//   cn_phase(P,c,t,bad)   vn_phase<INIT>(P,c,t,need_hb,ones)   synd_phase(P,c,tl) -> bad
+//
+// Shared memory is ONE array `nms_smem` addressed by word offsets (message array at word 0), so
+// every access compiles to LDS/STS [reg + immediate]; inactive padding lanes (q >= L) work on
+// their own padding words instead of being branched around.
 //
 // Reference semantics restated: Main_Functions.py:161-335 (steps D2..D8 of SURVEY.md 8a),
 // quantiser :475-494, sample generation Print_Functions.py:29-72, metrics :100-118.
 #pragma once
 #include "nms_common.cuh"
 
+extern __shared__ __align__(16) uint32_t nms_smem[];
+
 namespace nms {
 
-constexpr float RINT_MAGIC = 12582912.0f;   // 1.5 * 2^23: (t + M) - M == rintf(t) (half-to-even) for |t| < 2^22
-constexpr float XA_BOUND = 1.0e5f;          // QMS inputs are clamped here so the magic rint stays exact
+constexpr float XA_BOUND = 1.0e5f;          // QMS inputs are clamped here so the magic rounding stays exact
 constexpr uint32_t SIGN2 = 0x80008000u;
 constexpr uint32_t LSB2 = 0x00010001u;
 
@@ -25,55 +31,64 @@ constexpr int MISC_ONES = 128;    // [2][64] "hard decision has a one" flag, by 
 constexpr int MISC_BITERR = 256;  // [64]
 constexpr int MISC_HIDX = 320;    // [64] harvest row index (or 0xffffffff)
 constexpr int MISC_CTRL = 384;    // [16]
-constexpr int MISC_WORDS = NMS_MISC_WORDS;
-static_assert(MISC_WORDS >= 400, "misc layout");
+static_assert(NMS_MISC_WORDS >= 400, "misc layout");
 // ctrl words
 constexpr int CTRL_NEWLY = 0;     // [2] frames to copy out now
 constexpr int CTRL_FROZEN = 2;    // [2][2] frozen mask by iteration parity
 constexpr int CTRL_NEWONES = 6;   // [2] of those, frames whose decision has a one
 constexpr int CTRL_HARVEST = 8;   // [2]
 
-__device__ __forceinline__ float rint_magic(float t) { return __fsub_rn(__fadd_rn(t, RINT_MAGIC), RINT_MAGIC); }
+__device__ __forceinline__ float &smem_f(int w) { return reinterpret_cast<float *>(nms_smem)[w]; }
 
-// Q(x) with x already multiplied by qk: clamp(rint(t), +-maxk) (caller multiplies by qinv)
-__device__ __forceinline__ float qcore(float t, float maxk) {
-    return fminf(fmaxf(rint_magic(t), -maxk), maxk);
-}
+// round x half-to-even to the quantiser step (== rint(x*qk)/qk of Main_Functions.py:483-492; exact for
+// |x| < 2^21/qk): floats in [2^23/qk, 2^24/qk) are spaced exactly one step apart
+__device__ __forceinline__ float qround(float x, float magic) { return __fsub_rn(__fadd_rn(x, magic), magic); }
 __device__ __forceinline__ float qf(const KParams &P, float x) {   // full float quantiser
-    return __fmul_rn(qcore(__fmul_rn(x, P.qk), P.qmaxk), P.qinv);
+    return fminf(fmaxf(qround(x, P.qmagic), -P.qmax), P.qmax);
 }
 
-__device__ __forceinline__ float cn_w(const float *w, int code, int width, int t, int i, int e) {
-    if (code == 3) return __ldg(w + (size_t)t * width);
-    if (code == 2) return __ldg(w + (size_t)t * width + i);
-    return __ldg(w + (size_t)t * width + e);
+// weight of iteration t: staged copy in shared memory when it fits, else the global table
+__device__ __forceinline__ float wload(const KParams &P, int idx) {
+    return P.w_staged ? smem_f(P.off_w + idx) : __ldg(P.w_all + idx);
 }
-__device__ __forceinline__ float vn_w(const KParams &P, int t, int j) {
-    if (P.sharing2 == 3) return __ldg(P.w_vn + (size_t)t * P.wv);
-    if (P.sharing2 == 2) return __ldg(P.w_vn + (size_t)t * P.wv + j);
-    return 1.0f;
+__device__ __forceinline__ float cn_weight(const KParams &P, int t, int i, int e) {
+    if (P.sharing0 == 0) return 1.0f;
+    return wload(P, P.w_off_cn + t * P.wc + (P.sharing0 == 3 ? 0 : (P.sharing0 == 2 ? i : e)));
+}
+__device__ __forceinline__ float ucn_weight(const KParams &P, int t, int i, int e) {
+    return wload(P, P.w_off_ucn + t * P.wu + (P.sharing1 == 3 ? 0 : (P.sharing1 == 2 ? i : e)));
+}
+__device__ __forceinline__ float vn_weight(const KParams &P, int t, int j) {
+    return wload(P, P.w_off_vn + t * P.wv + (P.sharing2 == 3 ? 0 : j));
 }
 
 struct Ctx {
-    uint32_t *msg, *xq, *hb, *misc;
-    float *xa;
-    int lane, chunk, slot, q, qe;
-    bool active;
-    int f0, f1;   // frame(s) of this lane's slot (packed: f0 = 2fp, f1 = 2fp+1; float: f0 = f1 = fp)
+    int lane, chunk, slot, warp;
+    int q;        // lane index inside the interleaved block, 0..LP-1 (>= L: padding lane)
+    int act;      // 1 for q < L
+    int Lthr;     // L for active lanes, INT_MAX for padding lanes (they never wrap / rotate)
+    int f0, f1;   // frame(s) of this lane's slot (packed: 2fp, 2fp+1; float: fp, fp); padding lanes: 0
     int a_lane;   // circulant lane of q
     long long frame0;
     int nvalid;
 };
 
+// variable lane q -> word index of the message of CSR entry `ve` (rotation into the check lane frame)
+__device__ __forceinline__ int vn_addr(const Ctx &c, int2 ve, int L) {
+    int qq = c.q + ve.y * c.act;
+    qq = (qq >= c.Lthr) ? qq - L : qq;
+    return ve.x + qq;
+}
+
 // is frame f frozen as far as the VN phase of iteration t can tell?  (only used for the optional APP output)
-__device__ __forceinline__ bool app_frozen(const KParams &P, const Ctx &c, int t, int f) {
-    const uint32_t *ctrl = c.misc + MISC_CTRL;
-    bool frozen = (ctrl[CTRL_FROZEN + ((t + 1) & 1) * 2 + (f >> 5)] >> (f & 31)) & 1u;
-    if (P.early_term && t >= 1 && c.misc[MISC_SYND + (t & 1) * 64 + f] == 0u) frozen = true;
+__device__ __forceinline__ bool app_frozen(const KParams &P, int t, int f) {
+    const uint32_t *misc = nms_smem + P.off_misc;
+    bool frozen = (misc[MISC_CTRL + CTRL_FROZEN + ((t + 1) & 1) * 2 + (f >> 5)] >> (f & 31)) & 1u;
+    if (P.early_term && t >= 1 && misc[MISC_SYND + (t & 1) * 64 + f] == 0u) frozen = true;
     return frozen;
 }
 __device__ __forceinline__ void app_store(const KParams &P, const Ctx &c, int j, int t, int f, float v) {
-    if (f >= c.nvalid || app_frozen(P, c, t, f)) return;
+    if (!c.act || f >= c.nvalid || app_frozen(P, t, f)) return;
     const long long tt = P.app_all ? t : 0;
     P.app[tt * P.app_stride_t + (c.frame0 + f) * (long long)P.NZ + j * P.z + c.a_lane] = v;
 }
@@ -107,15 +122,16 @@ __device__ __forceinline__ void gen_llr4(const KParams &P, unsigned long long F,
 }
 
 template <bool H2>
-__device__ __forceinline__ void store_xa(const KParams &P, float *xa, int f, int k, float v) {
+__device__ __forceinline__ void store_xa(const KParams &P, int f, int k, float v) {
     const int j = k / P.z, a = k - j * P.z;
     if (P.qms) v = fminf(fmaxf(v, -XA_BOUND), XA_BOUND);
-    if (H2) {
-        const int qq = a * P.Fp + (f >> 1);
-        xa[(j * P.LP + qq) * 2 + (f & 1)] = v;
-    } else {
-        xa[j * P.LP + a * P.Fp + f] = v;
-    }
+    if (H2) smem_f(P.off_xa + (j * P.LP + a * P.Fp + (f >> 1)) * 2 + (f & 1)) = v;
+    else smem_f(P.off_xa + j * P.LP + a * P.Fp + f) = v;
+}
+template <bool H2>
+__device__ __forceinline__ float load_xa(const KParams &P, int f, int k) {
+    const int j = k / P.z, a = k - j * P.z;
+    return H2 ? smem_f(P.off_xa + (j * P.LP + a * P.Fp + (f >> 1)) * 2 + (f & 1)) : smem_f(P.off_xa + j * P.LP + a * P.Fp + f);
 }
 
 // gather the packed hard decision of the frames in `mask` from the ballot array `hbuf`
@@ -123,13 +139,14 @@ template <bool H2>
 __device__ __forceinline__ void copy_out(const KParams &P, const Ctx &c, const uint32_t mask[2], const uint32_t onesm[2],
                                          int hbuf) {
     const int nh = H2 ? 2 : 1;
+    uint32_t *misc = nms_smem + P.off_misc;
     for (int item = threadIdx.x; item < P.FB * P.HW; item += blockDim.x) {
         const int f = item / P.HW, w = item - f * P.HW;
         if (!((mask[f >> 5] >> (f & 31)) & 1u)) continue;
         uint32_t outw = 0;
         if ((onesm[f >> 5] >> (f & 31)) & 1u) {
             const int half = H2 ? (f & 1) : 0, fp = H2 ? (f >> 1) : f;
-            const uint32_t *hb = c.hb + (size_t)(hbuf * nh + half) * P.N * P.C;
+            const uint32_t *hb = nms_smem + P.off_hb + (hbuf * nh + half) * P.N * P.C;
             int k = 32 * w;
             int j = k / P.z, a = k - j * P.z;
             for (int b = 0; b < 32 && k < P.NZ; ++b, ++k) {
@@ -137,9 +154,17 @@ __device__ __forceinline__ void copy_out(const KParams &P, const Ctx &c, const u
                 outw |= ((hb[j * P.C + (qq >> 5)] >> (qq & 31)) & 1u) << b;
                 if (++a == P.z) { a = 0; ++j; }
             }
-            if (outw) atomicAdd(&c.misc[MISC_BITERR + f], (uint32_t)__popc(outw));
+            if (outw) atomicAdd(&misc[MISC_BITERR + f], (uint32_t)__popc(outw));
         }
         if (P.hard != nullptr) P.hard[(c.frame0 + f) * (long long)P.HW + w] = outw;
+    }
+}
+
+__device__ __forceinline__ void publish(const KParams &P, const Ctx &c, int base, uint32_t bits, bool h2) {
+    if (c.act) {
+        uint32_t *dst = nms_smem + P.off_misc + base;
+        if (bits & 1u) dst[c.f0] = 1u;
+        if (h2 && (bits & 0x10000u)) dst[c.f1] = 1u;
     }
 }
 
@@ -147,29 +172,30 @@ __device__ __forceinline__ void copy_out(const KParams &P, const Ctx &c, const u
 template <class Policy>
 __device__ __forceinline__ void nms_decode_body(const KParams &P) {
     constexpr bool H2 = Policy::H2;
-    extern __shared__ __align__(16) uint32_t smem[];
     Ctx c;
-    c.msg = smem + P.off_msg;
-    c.xa = reinterpret_cast<float *>(smem + P.off_xa);
-    c.xq = smem + P.off_xq;
-    c.hb = smem + P.off_hb;
-    c.misc = smem + P.off_misc;
     const int tid = threadIdx.x;
     c.lane = tid & 31;
-    const int warp = tid >> 5;
-    c.chunk = warp % P.C;
-    c.slot = warp / P.C;
+    c.warp = tid >> 5;
+    c.chunk = c.warp % P.C;
+    c.slot = c.warp / P.C;
     c.q = c.chunk * 32 + c.lane;
-    c.active = c.q < P.L;
-    c.qe = c.active ? c.q : 0;
-    c.a_lane = c.qe / P.Fp;
+    c.act = c.q < P.L ? 1 : 0;
+    c.Lthr = c.act ? P.L : 0x7fffffff;
+    c.a_lane = c.act ? c.q / P.Fp : 0;
     {
-        const int fp = c.qe - c.a_lane * P.Fp;
+        const int fp = c.act ? c.q - c.a_lane * P.Fp : 0;
         c.f0 = H2 ? 2 * fp : fp;
         c.f1 = H2 ? 2 * fp + 1 : fp;
     }
-    uint32_t *ctrl = c.misc + MISC_CTRL;
+    uint32_t *misc = nms_smem + P.off_misc;
+    uint32_t *ctrl = misc + MISC_CTRL;
     const long long nbatches = (P.n_frames + P.FB - 1) / P.FB;
+    if (P.w_staged)
+        for (int idx = tid; idx < P.w_words; idx += blockDim.x) smem_f(P.off_w + idx) = __ldg(P.w_all + idx);
+    // padding lanes read their own (otherwise unused) words: give those defined contents once
+    if (P.LP != P.L) {
+        for (int idx = tid; idx < P.off_hb; idx += blockDim.x) nms_smem[idx] = 0u;
+    }
 
     for (long long batch = blockIdx.x; batch < nbatches; batch += gridDim.x) {
         c.frame0 = batch * P.FB;
@@ -182,7 +208,7 @@ __device__ __forceinline__ void nms_decode_body(const KParams &P) {
             for (int idx = tid; idx < tot; idx += blockDim.x) {
                 const int f = idx / P.NZ, k = idx - f * P.NZ;
                 const float v = f < c.nvalid ? __ldg(P.llr + (c.frame0 + f) * (long long)P.NZ + k) : 0.0f;
-                store_xa<H2>(P, c.xa, f, k, v);
+                store_xa<H2>(P, f, k, v);
             }
         } else {
             const int nquads = (P.NZ + 3) >> 2, tot = P.FB * nquads;
@@ -190,11 +216,12 @@ __device__ __forceinline__ void nms_decode_body(const KParams &P) {
                 const int f = idx / nquads, quad = idx - f * nquads;
                 float v[4] = {0.0f, 0.0f, 0.0f, 0.0f};
                 if (f < c.nvalid) gen_llr4(P, P.frame_offset + (unsigned long long)(c.frame0 + f), quad, v);
+#pragma unroll
                 for (int k4 = 0; k4 < 4; ++k4)
-                    if (4 * quad + k4 < P.NZ) store_xa<H2>(P, c.xa, f, 4 * quad + k4, v[k4]);
+                    if (4 * quad + k4 < P.NZ) store_xa<H2>(P, f, 4 * quad + k4, v[k4]);
             }
         }
-        for (int idx = tid; idx < MISC_WORDS; idx += blockDim.x) c.misc[idx] = 0;
+        for (int idx = tid; idx < NMS_MISC_WORDS; idx += blockDim.x) misc[idx] = 0;
         // per-frame state lives in the registers of threads 0..63 (thread f owns frame f)
         bool st_frozen = tid >= c.nvalid, st_synd_ever = false, st_ever_correct = false;
         bool st_out_synd_ok = false, st_out_one = false;
@@ -202,13 +229,13 @@ __device__ __forceinline__ void nms_decode_body(const KParams &P) {
         __syncthreads();
         if (tid < 64) {
             const uint32_t fm = __ballot_sync(0xffffffffu, st_frozen);
-            if (c.lane == 0) { ctrl[CTRL_FROZEN + warp] = fm; ctrl[CTRL_FROZEN + 2 + warp] = fm; }
+            if (c.lane == 0) { ctrl[CTRL_FROZEN + c.warp] = fm; ctrl[CTRL_FROZEN + 2 + c.warp] = fm; }
         }
 
         // ---------------- init pass: xq, first V->C messages, hard bits of xin_0
         {
             uint32_t dummy = 0;
-            for (int n = c.slot; n < P.N; n += P.R) Policy::template vn_task<true>(P, c, P.vn_order[n], -1, dummy);
+            Policy::template vn_phase<true>(P, c, -1, true, dummy);
         }
         __syncthreads();
 
@@ -217,20 +244,16 @@ __device__ __forceinline__ void nms_decode_body(const KParams &P) {
         for (; t < P.T_run; ++t) {
             // ======== CN phase (also yields the syndrome of the previous hard decision)
             uint32_t bad = 0;
-            for (int n = c.slot; n < P.M; n += P.R) Policy::cn_task(P, c, P.cn_order[n], t, bad);
-            if (t >= 1 && c.active) {
-                uint32_t *sy = c.misc + MISC_SYND + (t & 1) * 64;
-                if (bad & 1u) sy[c.f0] = 1u;
-                if (H2 && (bad & 0x10000u)) sy[c.f1] = 1u;
-            }
+            Policy::cn_phase(P, c, t, bad);
+            if (t >= 1) publish(P, c, MISC_SYND + (t & 1) * 64, bad, H2);
             __syncthreads();   // A
             // ======== per-frame bookkeeping for APP_{t-1} (threads 0..63), concurrent with the VN phase
             if (tid < 64) {
                 bool newly = false;
                 if (t >= 1) {
-                    const bool fbad = c.misc[MISC_SYND + (t & 1) * 64 + tid] != 0u;
-                    const bool one = c.misc[MISC_ONES + ((t - 1) & 1) * 64 + tid] != 0u;
-                    c.misc[MISC_ONES + ((t - 1) & 1) * 64 + tid] = 0u;
+                    const bool fbad = misc[MISC_SYND + (t & 1) * 64 + tid] != 0u;
+                    const bool one = misc[MISC_ONES + ((t - 1) & 1) * 64 + tid] != 0u;
+                    misc[MISC_ONES + ((t - 1) & 1) * 64 + tid] = 0u;
                     if (!st_frozen) {
                         if (!one) st_ever_correct = true;
                         if (!fbad && !st_synd_ever) { st_synd_ever = true; st_iters = t; }
@@ -240,24 +263,23 @@ __device__ __forceinline__ void nms_decode_body(const KParams &P) {
                         }
                     }
                 }
-                c.misc[MISC_SYND + ((t + 1) & 1) * 64 + tid] = 0u;
-                const uint32_t nm = __ballot_sync(0xffffffffu, newly);
-                const uint32_t no = __ballot_sync(0xffffffffu, newly && st_out_one);
-                const uint32_t fm = __ballot_sync(0xffffffffu, st_frozen);
-                if (c.lane == 0) {
-                    ctrl[CTRL_NEWLY + warp] = nm;
-                    ctrl[CTRL_NEWONES + warp] = no;
-                    ctrl[CTRL_FROZEN + (t & 1) * 2 + warp] = fm;
+                misc[MISC_SYND + ((t + 1) & 1) * 64 + tid] = 0u;
+                if (P.early_term) {
+                    const uint32_t nm = __ballot_sync(0xffffffffu, newly);
+                    const uint32_t no = __ballot_sync(0xffffffffu, newly && st_out_one);
+                    const uint32_t fm = __ballot_sync(0xffffffffu, st_frozen);
+                    if (c.lane == 0) {
+                        ctrl[CTRL_NEWLY + c.warp] = nm;
+                        ctrl[CTRL_NEWONES + c.warp] = no;
+                        ctrl[CTRL_FROZEN + (t & 1) * 2 + c.warp] = fm;
+                    }
                 }
             }
-            // ======== VN phase
+            // ======== VN phase (hard-decision ballots only when a copy-out can follow)
             uint32_t ones = 0;
-            for (int n = c.slot; n < P.N; n += P.R) Policy::template vn_task<false>(P, c, P.vn_order[n], t, ones);
-            if (c.active) {
-                uint32_t *on = c.misc + MISC_ONES + (t & 1) * 64;
-                if (ones & 1u) on[c.f0] = 1u;
-                if (H2 && (ones & 0x10000u)) on[c.f1] = 1u;
-            }
+            const bool need_hb = !H2 || P.early_term || t == P.T_run - 1;
+            Policy::template vn_phase<false>(P, c, t, need_hb, ones);
+            publish(P, c, MISC_ONES + (t & 1) * 64, ones, H2);
             __syncthreads();   // B
             if (P.early_term) {
                 const uint32_t nm[2] = {ctrl[CTRL_NEWLY], ctrl[CTRL_NEWLY + 1]};
@@ -272,18 +294,13 @@ __device__ __forceinline__ void nms_decode_body(const KParams &P) {
 
         if (!alldone) {
             // ---------------- syndrome of the last hard decision APP_{T-1}
-            uint32_t bad = 0;
             const int tl = P.T_run;
-            for (int n = c.slot; n < P.M; n += P.R) bad |= Policy::synd_row(P, c, P.cn_order[n], tl);
-            if (c.active) {
-                uint32_t *sy = c.misc + MISC_SYND + (tl & 1) * 64;
-                if (bad & 1u) sy[c.f0] = 1u;
-                if (H2 && (bad & 0x10000u)) sy[c.f1] = 1u;
-            }
+            const uint32_t bad = Policy::synd_phase(P, c, tl);
+            publish(P, c, MISC_SYND + (tl & 1) * 64, bad, H2);
             __syncthreads();
             if (tid < 64) {
-                const bool fbad = c.misc[MISC_SYND + (tl & 1) * 64 + tid] != 0u;
-                const bool one = c.misc[MISC_ONES + ((tl - 1) & 1) * 64 + tid] != 0u;
+                const bool fbad = misc[MISC_SYND + (tl & 1) * 64 + tid] != 0u;
+                const bool one = misc[MISC_ONES + ((tl - 1) & 1) * 64 + tid] != 0u;
                 const bool pending = !st_frozen;
                 if (pending) {
                     if (!one) st_ever_correct = true;
@@ -292,7 +309,7 @@ __device__ __forceinline__ void nms_decode_body(const KParams &P) {
                 }
                 const uint32_t nm = __ballot_sync(0xffffffffu, pending);
                 const uint32_t no = __ballot_sync(0xffffffffu, pending && one);
-                if (c.lane == 0) { ctrl[CTRL_NEWLY + warp] = nm; ctrl[CTRL_NEWONES + warp] = no; }
+                if (c.lane == 0) { ctrl[CTRL_NEWLY + c.warp] = nm; ctrl[CTRL_NEWONES + c.warp] = no; }
             }
             __syncthreads();
             const uint32_t nm[2] = {ctrl[CTRL_NEWLY], ctrl[CTRL_NEWLY + 1]};
@@ -304,7 +321,7 @@ __device__ __forceinline__ void nms_decode_body(const KParams &P) {
         // ---------------- per-frame results, Monte-Carlo counters, harvest
         if (tid < 64) {
             const bool valid = tid < c.nvalid;
-            const uint32_t be = c.misc[MISC_BITERR + tid];
+            const uint32_t be = misc[MISC_BITERR + tid];
             const bool uncor_any = !st_ever_correct, uncor_last = st_out_one;
             if (valid) {
                 const long long F = c.frame0 + tid;
@@ -322,9 +339,9 @@ __device__ __forceinline__ void nms_decode_body(const KParams &P) {
                 hidx = atomicAdd(P.uncor_count, 1u);
                 if (hidx >= P.uncor_cap || P.uncor_buf == nullptr) hidx = 0xffffffffu;
             }
-            c.misc[MISC_HIDX + tid] = hidx;
+            misc[MISC_HIDX + tid] = hidx;
             const uint32_t hm = __ballot_sync(0xffffffffu, hidx != 0xffffffffu);
-            if (c.lane == 0) ctrl[CTRL_HARVEST + warp] = hm;
+            if (c.lane == 0) ctrl[CTRL_HARVEST + c.warp] = hm;
             if (P.counters != nullptr) {
                 const unsigned v0 = __reduce_add_sync(0xffffffffu, valid ? 1u : 0u);
                 const unsigned v1 = __reduce_add_sync(0xffffffffu, valid && uncor_last ? 1u : 0u);
@@ -352,20 +369,26 @@ __device__ __forceinline__ void nms_decode_body(const KParams &P) {
             if (hm[0] | hm[1]) {
                 for (int f = 0; f < P.FB; ++f) {
                     if (!((hm[f >> 5] >> (f & 31)) & 1u)) continue;
-                    const uint32_t row = c.misc[MISC_HIDX + f];
-                    for (int k = tid; k < P.NZ; k += blockDim.x) {
-                        const int j = k / P.z, a = k - j * P.z;
-                        const float v = H2 ? c.xa[(j * P.LP + a * P.Fp + (f >> 1)) * 2 + (f & 1)]
-                                           : c.xa[j * P.LP + a * P.Fp + f];
-                        P.uncor_buf[(size_t)row * P.NZ + k] = v;
-                    }
+                    const uint32_t row = misc[MISC_HIDX + f];
+                    for (int k = tid; k < P.NZ; k += blockDim.x)
+                        P.uncor_buf[(size_t)row * P.NZ + k] = load_xa<H2>(P, f, k);
                 }
             }
         }
     }
 }
 
-// fall-through chains: REP_DESC(X) expands X(31) X(30) ... X(0)
+// compile-time loops
+template <int V> struct IC { static constexpr int v = V; };
+template <int I0, int I1, class F>
+__device__ __forceinline__ void static_for(F &&f) {
+    if constexpr (I0 < I1) {
+        f(IC<I0>{});
+        static_for<I0 + 1, I1>(f);
+    }
+}
+
+// REP_DESC(X) expands X(31) X(30) ... X(0)
 #define NMS_REP_DESC(X)                                                                                        \
     X(31) X(30) X(29) X(28) X(27) X(26) X(25) X(24) X(23) X(22) X(21) X(20) X(19) X(18) X(17) X(16) X(15) X(14) \
     X(13) X(12) X(11) X(10) X(9) X(8) X(7) X(6) X(5) X(4) X(3) X(2) X(1) X(0)

@@ -21,9 +21,9 @@ namespace nms {
 // previous hard decision of the variable behind E(C) edge e, seen from check lane q
 __device__ __forceinline__ uint32_t f32_hbit(const KParams &P, const Ctx &c, int buf, int e) {
     const int jv = P.e_col[e];
-    int qv = c.qe + P.e_sF[e];
-    qv = (qv >= P.L) ? qv - P.L : qv;
-    return (c.hb[(buf * P.N + jv) * P.C + (qv >> 5)] >> (qv & 31)) & 1u;
+    int qv = c.q + P.e_sF[e] * c.act;
+    qv = (qv >= c.Lthr) ? qv - P.L : qv;
+    return (nms_smem[P.off_hb + (buf * P.N + jv) * P.C + (qv >> 5)] >> (qv & 31)) & 1u;
 }
 
 __device__ __forceinline__ float f32_cn_emit(const KParams &P, float raw, float m1, float m2, int npos, float w) {
@@ -39,16 +39,15 @@ __device__ __forceinline__ float f32_cn_emit(const KParams &P, float raw, float 
 
 __device__ __forceinline__ float f32_edge_w(const KParams &P, bool ucn, int t, int i, int e) {
     if (P.sharing0 == 0) return 1.0f;
-    return ucn ? cn_w(P.w_ucn, P.sharing1, P.wu, t, i, e) : cn_w(P.w_cn, P.sharing0, P.wc, t, i, e);
+    return ucn ? ucn_weight(P, t, i, e) : cn_weight(P, t, i, e);
 }
 
 template <int DC>
 __device__ __forceinline__ void cn_row_f32(const KParams &P, const Ctx &c, int i, int t, uint32_t &bad) {
-    const int e0 = P.row_ptr[i], LP = P.LP;
-    float *base = reinterpret_cast<float *>(c.msg) + e0 * LP + c.qe;
+    const int e0 = P.row_ptr[i], LP = P.LP, off = e0 * LP + c.q;
     float raw[DC];
 #pragma unroll
-    for (int p = 0; p < DC; ++p) raw[p] = base[p * LP];
+    for (int p = 0; p < DC; ++p) raw[p] = smem_f(off + p * LP);
     uint32_t par = 0;
     const int buf = (t + 1) & 1;   // hard bits of APP_{t-1} (the init pass wrote buffer 1)
 #pragma unroll
@@ -66,21 +65,18 @@ __device__ __forceinline__ void cn_row_f32(const KParams &P, const Ctx &c, int i
     }
     const bool ucn = P.sharing1 != 0 && par;
 #pragma unroll
-    for (int p = 0; p < DC; ++p) {
-        const float out = f32_cn_emit(P, raw[p], m1, m2, npos, f32_edge_w(P, ucn, t, i, e0 + p));
-        if (c.active) base[p * LP] = out;
-    }
+    for (int p = 0; p < DC; ++p)
+        smem_f(off + p * LP) = f32_cn_emit(P, raw[p], m1, m2, npos, f32_edge_w(P, ucn, t, i, e0 + p));
 }
 
 static __device__ __noinline__ void cn_row_f32_generic(const KParams &P, const Ctx &c, int i, int t, uint32_t &bad) {
-    const int e0 = P.row_ptr[i], dc = P.row_ptr[i + 1] - e0, LP = P.LP;
-    float *base = reinterpret_cast<float *>(c.msg) + e0 * LP + c.qe;
+    const int e0 = P.row_ptr[i], dc = P.row_ptr[i + 1] - e0, LP = P.LP, off = e0 * LP + c.q;
     uint32_t par = 0;
     const int buf = (t + 1) & 1;
     float m1 = 10000.0f, m2 = 10000.0f;
     int npos = 0;
     for (int p = 0; p < dc; ++p) {
-        const float r = base[p * LP];
+        const float r = smem_f(off + p * LP);
         par ^= f32_hbit(P, c, buf, e0 + p);
         const float a = fabsf(r);
         const float tmx = fmaxf(m1, a);
@@ -90,10 +86,8 @@ static __device__ __noinline__ void cn_row_f32_generic(const KParams &P, const C
     }
     bad |= par;
     const bool ucn = P.sharing1 != 0 && par;
-    for (int p = 0; p < dc; ++p) {
-        const float out = f32_cn_emit(P, base[p * LP], m1, m2, npos, f32_edge_w(P, ucn, t, i, e0 + p));
-        if (c.active) base[p * LP] = out;
-    }
+    for (int p = 0; p < dc; ++p)
+        smem_f(off + p * LP) = f32_cn_emit(P, smem_f(off + p * LP), m1, m2, npos, f32_edge_w(P, ucn, t, i, e0 + p));
 }
 
 __device__ __forceinline__ float f32_sat(const KParams &P, float v) {
@@ -109,15 +103,15 @@ struct F32Var {
 template <bool INIT>
 __device__ __forceinline__ F32Var f32_var(const KParams &P, const Ctx &c, int j, int t, float S, uint32_t &ones) {
     F32Var v;
-    const int slotw = j * P.LP + c.qe;
-    const float xa = c.xa[slotw];
+    const int slotw = j * P.LP + c.q;
+    const float xa = smem_f(P.off_xa + slotw);
     float xqv = xa;
     if (P.qms) {
         if (INIT) {
             xqv = qf(P, xa);                                         // :321-322
-            if (c.active) reinterpret_cast<float *>(c.xq)[slotw] = xqv;
+            smem_f(P.off_xq + slotw) = xqv;
         } else {
-            xqv = reinterpret_cast<float *>(c.xq)[slotw];
+            xqv = smem_f(P.off_xq + slotw);
         }
     }
     const float app = fminf(fmaxf(__fadd_rn(xqv, S), -P.clip), P.clip);   // :324-325
@@ -125,31 +119,27 @@ __device__ __forceinline__ F32Var f32_var(const KParams &P, const Ctx &c, int j,
     v.has_next = tn < P.T_run;
     v.xin = xa;
     if (v.has_next) {
-        if (P.sharing2 != 0) v.xin = __fmul_rn(xa, vn_w(P, tn, j)); // :168-169
-        if (P.qms) v.xin = qf(P, v.xin);                             // :176-177
+        if (P.sharing2 != 0) v.xin = __fmul_rn(xa, vn_weight(P, tn, j));  // :168-169
+        if (P.qms) v.xin = qf(P, v.xin);                                   // :176-177
     }
     const float hsrc = INIT ? v.xin : app;
     const bool hbit = hsrc >= 0.0f;                                  // Print_Functions.py:106
     if (!INIT && hbit) ones |= 1u;
-    const uint32_t b = __ballot_sync(0xffffffffu, c.active && hbit);
-    if (c.lane == 0) c.hb[((INIT ? 1 : (t & 1)) * P.N + j) * P.C + c.chunk] = b;
-    if (!INIT && P.app != nullptr && c.active) app_store(P, c, j, t, c.f0, app);
+    const uint32_t b = __ballot_sync(0xffffffffu, c.act && hbit);
+    if (c.lane == 0) nms_smem[P.off_hb + ((INIT ? 1 : (t & 1)) * P.N + j) * P.C + c.chunk] = b;
+    if (!INIT && P.app != nullptr) app_store(P, c, j, t, c.f0, app);
     return v;
 }
 
 template <int DV, bool INIT>
 __device__ __forceinline__ void vn_col_f32(const KParams &P, const Ctx &c, int j, int t, uint32_t &ones) {
     const int c0 = P.col_ptr[j], L = P.L;
-    float *msgf = reinterpret_cast<float *>(c.msg);
     int addr[DV];
     float cv[DV];
 #pragma unroll
     for (int u = 0; u < DV; ++u) {
-        const int2 ve = P.vn_edge[c0 + u];
-        int qq = c.qe + ve.y;
-        qq = (qq >= L) ? qq - L : qq;
-        addr[u] = ve.x + qq;
-        cv[u] = INIT ? 0.0f : msgf[addr[u]];
+        addr[u] = vn_addr(c, P.vn_edge[c0 + u], L);
+        cv[u] = INIT ? 0.0f : smem_f(addr[u]);
     }
     float S = 0.0f;
 #pragma unroll
@@ -162,8 +152,7 @@ __device__ __forceinline__ void vn_col_f32(const KParams &P, const Ctx &c, int j
 #pragma unroll
             for (int u2 = 0; u2 < DV; ++u2)
                 if (u2 != u) acc = __fadd_rn(acc, cv[u2]);
-            const float m = f32_sat(P, __fadd_rn(v.xin, acc));       // :215, :223-230
-            if (c.active) msgf[addr[u]] = m;
+            smem_f(addr[u]) = f32_sat(P, __fadd_rn(v.xin, acc));     // :215, :223-230
         }
     }
 }
@@ -172,14 +161,8 @@ __device__ __forceinline__ void vn_col_f32(const KParams &P, const Ctx &c, int j
 template <bool INIT>
 __device__ __noinline__ void vn_col_f32_generic(const KParams &P, const Ctx &c, int j, int t, uint32_t &ones) {
     const int c0 = P.col_ptr[j], dv = min(P.col_ptr[j + 1] - c0, 64), L = P.L;
-    float *msgf = reinterpret_cast<float *>(c.msg);
     float cv[64];
-    for (int u = 0; u < dv; ++u) {
-        const int2 ve = P.vn_edge[c0 + u];
-        int qq = c.qe + ve.y;
-        qq = (qq >= L) ? qq - L : qq;
-        cv[u] = INIT ? 0.0f : msgf[ve.x + qq];
-    }
+    for (int u = 0; u < dv; ++u) cv[u] = INIT ? 0.0f : smem_f(vn_addr(c, P.vn_edge[c0 + u], L));
     float S = 0.0f;
     for (int u = 0; u < dv; ++u) S = __fadd_rn(S, cv[u]);
     const F32Var v = f32_var<INIT>(P, c, j, t, S, ones);
@@ -188,11 +171,7 @@ __device__ __noinline__ void vn_col_f32_generic(const KParams &P, const Ctx &c, 
             float acc = 0.0f;
             for (int u2 = 0; u2 < dv; ++u2)
                 if (u2 != u) acc = __fadd_rn(acc, cv[u2]);
-            const float m = f32_sat(P, __fadd_rn(v.xin, acc));
-            const int2 ve = P.vn_edge[c0 + u];
-            int qq = c.qe + ve.y;
-            qq = (qq >= L) ? qq - L : qq;
-            if (c.active) msgf[ve.x + qq] = m;
+            smem_f(vn_addr(c, P.vn_edge[c0 + u], L)) = f32_sat(P, __fadd_rn(v.xin, acc));
         }
     }
 }
@@ -201,46 +180,57 @@ template <int DCB, int DVB>
 struct F32Policy {
     static constexpr bool H2 = false;
 
-    static __device__ __forceinline__ void cn_task(const KParams &P, const Ctx &c, int i, int t, uint32_t &bad) {
-        if constexpr (DCB == 0) {
-            cn_row_f32_generic(P, c, i, t, bad);
-        } else {
-            const int dc = P.row_ptr[i + 1] - P.row_ptr[i];
-            switch (dc) {
+    static __device__ __forceinline__ void cn_phase(const KParams &P, const Ctx &c, int t, uint32_t &bad) {
+        for (int n = c.slot; n < P.M; n += P.R) {
+            const int i = P.cn_order[n];
+            if constexpr (DCB == 0) {
+                cn_row_f32_generic(P, c, i, t, bad);
+            } else {
+                const int dc = P.row_ptr[i + 1] - P.row_ptr[i];
+                switch (dc) {
 #define X(p)                                                        \
     case (p) + 1:                                                   \
         if constexpr ((p) < DCB) cn_row_f32<(p) + 1>(P, c, i, t, bad); \
         break;
-                NMS_REP_DESC(X)
+                    NMS_REP_DESC(X)
 #undef X
-            default: break;
+                default: break;
+                }
             }
         }
     }
 
     template <bool INIT>
-    static __device__ __forceinline__ void vn_task(const KParams &P, const Ctx &c, int j, int t, uint32_t &ones) {
-        if constexpr (DVB == 0) {
-            vn_col_f32_generic<INIT>(P, c, j, t, ones);
-        } else {
-            const int dv = P.col_ptr[j + 1] - P.col_ptr[j];
-            switch (dv) {
+    static __device__ __forceinline__ void vn_phase(const KParams &P, const Ctx &c, int t, bool need_hb, uint32_t &ones) {
+        for (int n = c.slot; n < P.N; n += P.R) {
+            const int j = P.vn_order[n];
+            if constexpr (DVB == 0) {
+                vn_col_f32_generic<INIT>(P, c, j, t, ones);
+            } else {
+                const int dv = P.col_ptr[j + 1] - P.col_ptr[j];
+                switch (dv) {
 #define X(p)                                                                 \
     case (p) + 1:                                                            \
         if constexpr ((p) < DVB) vn_col_f32<(p) + 1, INIT>(P, c, j, t, ones); \
         break;
-                NMS_REP_DESC(X)
+                    NMS_REP_DESC(X)
 #undef X
-            default: break;
+                default: break;
+                }
             }
         }
     }
 
-    static __device__ __forceinline__ uint32_t synd_row(const KParams &P, const Ctx &c, int i, int tl) {
-        const int e0 = P.row_ptr[i], dc = P.row_ptr[i + 1] - e0;
-        uint32_t par = 0;
-        for (int p = 0; p < dc; ++p) par ^= f32_hbit(P, c, (tl + 1) & 1, e0 + p);
-        return par;
+    static __device__ __forceinline__ uint32_t synd_phase(const KParams &P, const Ctx &c, int tl) {
+        uint32_t bad = 0;
+        for (int n = c.slot; n < P.M; n += P.R) {
+            const int i = P.cn_order[n];
+            const int e0 = P.row_ptr[i], dc = P.row_ptr[i + 1] - e0;
+            uint32_t par = 0;
+            for (int p = 0; p < dc; ++p) par ^= f32_hbit(P, c, (tl + 1) & 1, e0 + p);
+            bad |= par;
+        }
+        return bad;
     }
 };
 

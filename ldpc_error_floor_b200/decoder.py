@@ -111,6 +111,7 @@ class NMSDecoder:
             graph._h, sh, T, *[b.ctypes.data if b is not None else None for b in blocks],
             self.decoding_type, self.q_bit, self.clip_llr, self.device_index, ctypes.byref(self._h)))
         self.packed = bool(lib.ldpc_decoder_uses_packed_kernel(self._h))
+        self.kernel_name = lib.ldpc_decoder_kernel_name(self._h).decode()
         fb, cps, thr, smem = (ctypes.c_int32() for _ in range(4))
         _lib.check(lib.ldpc_decoder_geometry(self._h, ctypes.byref(fb), ctypes.byref(cps), ctypes.byref(thr),
                                              ctypes.byref(smem)))
