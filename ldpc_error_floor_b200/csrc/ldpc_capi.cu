@@ -35,6 +35,11 @@ const void *nms_f32_func_0_0();
 
 namespace {
 
+bool env_on(const char *name) {
+    const char *v = getenv(name);
+    return v && *v && *v != '0';
+}
+
 thread_local std::string g_err;
 int fail(int code, const char *fmt, ...) {
     char buf[512];
@@ -191,25 +196,31 @@ int weight_width(int code, int kind, int M, int N, int E) {   // Main_Functions.
     return 0;
 }
 
-// degree-balanced visiting order: sort by degree (descending), deal to R slots boustrophedon
-void snake_order(const std::vector<int> &deg, int R, unsigned short *out) {
+// visiting order: sort by degree (descending, stable); returns the runs of equal degree.  Slot s of R owns the
+// positions p with p % R == s, so every slot gets the same number of tasks (+-1) of about the same degrees.
+int degree_classes(const std::vector<int> &deg, unsigned short *order, ushort4 *cls, int max_cls) {
     const int n = (int)deg.size();
     std::vector<int> idx(n);
     std::iota(idx.begin(), idx.end(), 0);
     std::stable_sort(idx.begin(), idx.end(), [&](int a, int b) { return deg[a] > deg[b]; });
-    for (int k = 0; k * R < n; ++k)
-        for (int s = 0; s < R && k * R + s < n; ++s) {
-            const int lim = std::min(R, n - k * R);
-            const int src = (k & 1) ? k * R + (lim - 1 - s) : k * R + s;
-            out[k * R + s] = (unsigned short)idx[src];
+    int nc = 0;
+    for (int p = 0; p < n; ++p) {
+        order[p] = (unsigned short)idx[p];
+        if (p == 0 || deg[idx[p]] != deg[idx[p - 1]]) {
+            if (nc == max_cls) return -1;
+            cls[nc] = make_ushort4((unsigned short)deg[idx[p]], (unsigned short)p, (unsigned short)p, 0);
+            ++nc;
         }
+        cls[nc - 1].z = (unsigned short)(p + 1);
+    }
+    return nc;
 }
 
 const void *pick_kernel(bool packed, int max_dc, int max_dv, int *dcb, int *dvb) {
     int dc = max_dc <= 16 ? 16 : (max_dc <= 32 ? 32 : 0);
     int dv = max_dv <= 8 ? 8 : (max_dv <= 16 ? 16 : 0);
     if (dc == 0 || dv == 0) dc = dv = 0;
-    if (getenv("LDPC_B200_FORCE_GENERIC")) dc = dv = 0;
+    if (env_on("LDPC_B200_FORCE_GENERIC")) dc = dv = 0;
     *dcb = dc; *dvb = dv;
     if (packed) {
         if (dc == 16 && dv == 8) return nms_h2_func_16_8();
@@ -353,7 +364,7 @@ extern "C" int ldpc_decoder_create(const ldpc_graph_t *g, const int32_t sharing[
     d->T = T; d->decoding_type = decoding_type; d->q_bit = q_bit; d->clip = clip_llr; d->device = device;
     const bool qms = decoding_type == 2;
     // packed fp16x2 kernel: uniform quantiser grids closed under addition, no per-edge weights
-    d->packed = qms && q_bit != 6 && sharing[0] != 1 && g->info.max_dv <= 30 && !getenv("LDPC_B200_FORCE_F32");
+    d->packed = qms && q_bit != 6 && sharing[0] != 1 && g->info.max_dv <= 30 && !env_on("LDPC_B200_FORCE_F32");
     if (!d->packed && g->info.max_dv > 64) { delete d; return fail(LDPC_E_LIMIT, "column degree > 64 in float mode"); }
     cudaDeviceProp prop;
     if (cudaGetDeviceProperties(&prop, device) != cudaSuccess) { delete d; return fail(LDPC_E_CUDA, "cudaGetDeviceProperties"); }
@@ -374,7 +385,7 @@ extern "C" int ldpc_decoder_create(const ldpc_graph_t *g, const int32_t sharing[
     // a graph known at build time gets its specialised kernel (gen_spec.py); anything else the generic buckets
     int rc = LDPC_E_LIMIT;
     d->func = nullptr;
-    if (d->packed && !getenv("LDPC_B200_NO_SPEC")) {
+    if (d->packed && !env_on("LDPC_B200_NO_SPEC")) {
         int n = 0;
         const NmsSpecEntry *tab = nms_spec_table(&n);
         const unsigned long long h = graph_hash(d->g);
@@ -420,8 +431,9 @@ extern "C" int ldpc_decoder_create(const ldpc_graph_t *g, const int32_t sharing[
         std::vector<int> dc(g->M), dv(g->N);
         for (int i = 0; i < g->M; ++i) dc[i] = g->row_ptr[i + 1] - g->row_ptr[i];
         for (int j = 0; j < g->N; ++j) dv[j] = g->col_ptr[j + 1] - g->col_ptr[j];
-        snake_order(dc, P.R, P.cn_order);
-        snake_order(dv, P.R, P.vn_order);
+        P.n_cn_cls = degree_classes(dc, P.cn_order, P.cn_cls, 32);
+        P.n_vn_cls = degree_classes(dv, P.vn_order, P.vn_cls, 32);
+        if (P.n_cn_cls < 0 || P.n_vn_cls < 0) { delete d; return fail(LDPC_E_LIMIT, "more than 32 distinct node degrees"); }
     }
     for (int e = 0; e < g->E; ++e) {
         P.e_col[e] = (unsigned short)g->col[e];
@@ -429,8 +441,10 @@ extern "C" int ldpc_decoder_create(const ldpc_graph_t *g, const int32_t sharing[
     }
     for (int k = 0; k < g->E; ++k) {
         const int e = g->col_edge[k];
-        P.vn_edge[k].x = e * P.LP;
-        P.vn_edge[k].y = (P.L - g->shift[e] * P.Fp) % P.L;   // variable lane q -> check lane (q - s*Fp) mod L
+        // variable lane q -> check lane (q - s*Fp) mod L; packed kernels address shared memory in bytes
+        const int unit = d->packed ? 4 : 1;
+        P.vn_edge[k].x = e * P.LP * unit;
+        P.vn_edge[k].y = ((P.L - g->shift[e] * P.Fp) % P.L) * unit;
     }
     if (!wh.empty()) {
         if (cudaMalloc(&d->d_w, wh.size() * sizeof(float)) != cudaSuccess ||

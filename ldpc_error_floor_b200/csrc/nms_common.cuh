@@ -62,11 +62,13 @@ struct KParams {
     // tables
     unsigned short row_ptr[LDPC_MAX_M + 1];   // E(C) edges of proto row i: [row_ptr[i], row_ptr[i+1])
     unsigned short col_ptr[LDPC_MAX_N + 1];   // CSR by proto column into vn_edge
-    unsigned short cn_order[LDPC_MAX_M];      // row visiting order (degree-balanced)
-    unsigned short vn_order[LDPC_MAX_N];
+    unsigned short cn_order[LDPC_MAX_M];      // rows sorted by degree (descending); slot s owns positions p % R == s
+    unsigned short vn_order[LDPC_MAX_N];      // columns likewise
+    int n_cn_cls, n_vn_cls;                   // runs of equal degree inside cn_order / vn_order
+    ushort4 cn_cls[32], vn_cls[32];           // {degree, first position, end position, 0}
     unsigned short e_col[LDPC_MAX_E];         // proto column of E(C) edge e
     unsigned short e_sF[LDPC_MAX_E];          // s_e*Fp: check lane q -> variable lane (q + sF) mod L
-    int2 vn_edge[LDPC_MAX_E];                 // column-sorted: {e*LP (words), (L - s_e*Fp) mod L}
+    int2 vn_edge[LDPC_MAX_E];                 // column-sorted: {e*LP, (L - s_e*Fp) mod L} in words (float kernel) / bytes (packed)
 };
 
 struct LaunchGeom {

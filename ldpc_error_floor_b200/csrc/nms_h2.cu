@@ -16,19 +16,39 @@ template <int DCB, int DVB>
 struct H2Policy {
     static constexpr bool H2 = true;
 
+    template <int DC>
+    static __device__ __forceinline__ void cn_class(const KParams &P, const H2Ctx &h, int &p, int end, uint32_t LP4,
+                                                    uint32_t wcrow, uint32_t wurow, uint32_t &bad) {
+        do {
+            const int i = P.cn_order[p];
+            const uint32_t a0 = h.sb + (uint32_t)P.row_ptr[i] * LP4 + h.q4;
+            cn_row_h2<DC>(P, a0, LP4, h2_w(wcrow, i, P.h2_mc), h2_w(wurow, i, P.h2_mu), bad);
+            p += P.R;
+        } while (p < end);
+    }
+
+    // rows are sorted by degree; slot s owns positions p % R == s: one dispatch per degree class
     static __device__ __forceinline__ void cn_phase(const KParams &P, const Ctx &c, int t, uint32_t &bad) {
-        for (int n = c.slot; n < P.M; n += P.R) {
-            const int i = P.cn_order[n];
-            const int e0 = P.row_ptr[i], dc = P.row_ptr[i + 1] - e0;
-            const int off = e0 * P.LP + c.q;
-            const float w0 = h2_wcn(P, t, i), w1 = h2_wucn(P, t, i);
-            if constexpr (DCB == 0) {
-                cn_row_h2_generic(P, off, P.LP, dc, w0, w1, bad);
-            } else {
-                switch (dc) {
-#define X(p)                                                              \
-    case (p) + 1:                                                         \
-        if constexpr ((p) < DCB) cn_row_h2<(p) + 1>(P, off, P.LP, w0, w1, bad); \
+        const H2Ctx h = h2_ctx(P, c);
+        const uint32_t LP4 = (uint32_t)P.LP * 4u;
+        const uint32_t wcrow = h2_wrow(h, P.h2w_c, t, P.h2_wc), wurow = h2_wrow(h, P.h2w_u, t, P.h2_wu);
+        if constexpr (DCB == 0) {
+            for (int n = c.slot; n < P.M; n += P.R) {
+                const int i = P.cn_order[n];
+                const int e0 = P.row_ptr[i], dc = P.row_ptr[i + 1] - e0;
+                cn_row_h2_generic(P, h.sb + (uint32_t)e0 * LP4 + h.q4, LP4, dc, h2_w(wcrow, i, P.h2_mc),
+                                  h2_w(wurow, i, P.h2_mu), bad);
+            }
+        } else {
+            int p = c.slot;
+            for (int k = 0; k < P.n_cn_cls; ++k) {
+                const ushort4 cl = P.cn_cls[k];
+                const int end = cl.z;
+                if (p >= end) continue;
+                switch (cl.x) {
+#define X(d)                                                                             \
+    case (d) + 1:                                                                        \
+        if constexpr ((d) < DCB) cn_class<(d) + 1>(P, h, p, end, LP4, wcrow, wurow, bad); \
         break;
                     NMS_REP_DESC(X)
 #undef X
@@ -40,36 +60,12 @@ struct H2Policy {
 
     template <bool INIT>
     static __device__ __forceinline__ void vn_phase(const KParams &P, const Ctx &c, int t, bool need_hb, uint32_t &ones) {
-        for (int n = c.slot; n < P.N; n += P.R) {
-            const int j = P.vn_order[n];
-            if constexpr (DVB == 0) {
-                vn_col_h2_generic<INIT>(P, c, j, t, need_hb, ones);
-            } else {
-                const int dv = P.col_ptr[j + 1] - P.col_ptr[j];
-                switch (dv) {
-#define X(p)                                                                         \
-    case (p) + 1:                                                                    \
-        if constexpr ((p) < DVB) vn_col_h2<(p) + 1, INIT>(P, c, j, t, need_hb, ones); \
-        break;
-                    NMS_REP_DESC(X)
-#undef X
-                default: break;
-                }
-            }
-        }
+        const H2Ctx h = h2_ctx(P, c);
+        h2_vn_phase_tab<DVB, INIT>(P, c, h, t, need_hb, ones);
     }
 
-    // syndrome parity of the hard bits parked in the message LSBs after the last VN phase
     static __device__ __forceinline__ uint32_t synd_phase(const KParams &P, const Ctx &c, int tl) {
-        uint32_t bad = 0;
-        for (int n = c.slot; n < P.M; n += P.R) {
-            const int i = P.cn_order[n];
-            const int e0 = P.row_ptr[i], dc = P.row_ptr[i + 1] - e0;
-            uint32_t par = 0;
-            for (int p = 0; p < dc; ++p) par ^= nms_smem[(e0 + p) * P.LP + c.q];
-            bad |= par;
-        }
-        return bad;
+        return h2_synd_phase(P, c);
     }
 };
 

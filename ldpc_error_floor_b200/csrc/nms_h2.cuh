@@ -15,6 +15,8 @@
 //  * the V->C saturation Q() of :223-224 is a clamp of an on-grid value; clamping commutes with the
 //    minimum and does not touch the sign, so it is applied once per check to (min1, min2) instead of
 //    once per edge.
+// All shared-memory traffic of the inner loops goes through ld/st.shared with 32-bit byte addresses
+// (H2Ctx::sb + offset), so every access is one LDS/STS [reg + immediate].
 #pragma once
 #include "nms_device.cuh"
 
@@ -23,9 +25,61 @@ namespace nms {
 __device__ __forceinline__ uint32_t h2u(__half2 h) { return *reinterpret_cast<uint32_t *>(&h); }
 __device__ __forceinline__ __half2 u2h(uint32_t u) { return *reinterpret_cast<__half2 *>(&u); }
 
-__device__ __forceinline__ float h2_wcn(const KParams &P, int t, int i) { return smem_f(P.h2w_c + t * P.h2_wc + (i & P.h2_mc)); }
-__device__ __forceinline__ float h2_wucn(const KParams &P, int t, int i) { return smem_f(P.h2w_u + t * P.h2_wu + (i & P.h2_mu)); }
-__device__ __forceinline__ float h2_wvn(const KParams &P, int t, int j) { return smem_f(P.h2w_v + t * P.h2_wv + (j & P.h2_mv)); }
+__device__ __forceinline__ uint32_t lds32(uint32_t a) {
+    uint32_t v;
+    asm volatile("ld.shared.u32 %0, [%1];" : "=r"(v) : "r"(a));
+    return v;
+}
+__device__ __forceinline__ float ldsf(uint32_t a) {
+    float v;
+    asm volatile("ld.shared.f32 %0, [%1];" : "=f"(v) : "r"(a));
+    return v;
+}
+__device__ __forceinline__ float2 lds64f(uint32_t a) {
+    float2 v;
+    asm volatile("ld.shared.v2.f32 {%0, %1}, [%2];" : "=f"(v.x), "=f"(v.y) : "r"(a));
+    return v;
+}
+__device__ __forceinline__ void sts32(uint32_t a, uint32_t v) { asm volatile("st.shared.u32 [%0], %1;" ::"r"(a), "r"(v)); }
+
+// per-thread constants of the packed kernels (byte units)
+struct H2Ctx {
+    uint32_t sb;      // shared-window byte address of nms_smem[0]
+    uint32_t q4;      // q * 4
+    uint32_t amask;   // all ones for active lanes, 0 for padding lanes (they never rotate)
+    uint32_t Lthr4;   // L*4 for active lanes, 2^30 for padding lanes (they never wrap)
+    uint32_t xa8;     // sb + off_xa*4 + q*8   (+ j*LP*8 per column)
+    uint32_t xq4;     // sb + off_xq*4 + q*4   (+ j*LP*4 per column)
+};
+
+__device__ __forceinline__ H2Ctx h2_ctx(const KParams &P, const Ctx &c) {
+    H2Ctx h;
+    h.sb = (uint32_t)__cvta_generic_to_shared(nms_smem);   // warp-uniform: ends up in a uniform register
+    h.q4 = (uint32_t)c.q * 4u;
+    h.amask = c.act ? 0xffffffffu : 0u;
+    h.Lthr4 = c.act ? (uint32_t)P.L * 4u : 0x40000000u;
+    h.xa8 = h.sb + (uint32_t)P.off_xa * 4u + (uint32_t)c.q * 8u;
+    h.xq4 = h.sb + (uint32_t)P.off_xq * 4u + h.q4;
+    return h;
+}
+
+// byte address of the weight row of iteration t (branch-free: "no weight" is a staged row of ones)
+__device__ __forceinline__ uint32_t h2_wrow(const H2Ctx &h, int base_word, int t, int width) {
+    return h.sb + (uint32_t)(base_word + t * width) * 4u;
+}
+__device__ __forceinline__ float h2_w(uint32_t row, int node, int mask) { return ldsf(row + (uint32_t)((node & mask) * 4)); }
+
+// variable lane -> byte offset of the rotated check lane: (q + rot) mod L, padding lanes stay put
+template <bool PAD>
+__device__ __forceinline__ uint32_t h2_rot(const H2Ctx &h, uint32_t rot4, uint32_t L4) {
+    if (PAD) {
+        const uint32_t t1 = h.q4 + (rot4 & h.amask);
+        return min(t1, t1 - h.Lthr4);          // t1 - Lthr4 wraps high unless the lane must wrap
+    } else {
+        const uint32_t t1 = h.q4 + rot4;
+        return min(t1, t1 - L4);
+    }
+}
 
 // Q() of two float32 values -> half2 (round to step in fp32, saturate after packing; +-inf saturate too)
 __device__ __forceinline__ __half2 q2(const KParams &P, float lo, float hi) {
@@ -56,40 +110,63 @@ __device__ __forceinline__ void h2_row_mags(const KParams &P, float w0, float w1
     B = h2u(magB) ^ s0;
 }
 
-// one check row held in registers.  `off`: word index of msg[e0][q]; `stride`: words between edges (LP)
+// one check row held in registers.  a0: byte address of msg[e0][q]; stride4: bytes between edges (LP*4)
 template <int DC>
-__device__ __forceinline__ void cn_row_h2(const KParams &P, int off, int stride, float w0, float w1, uint32_t &bad) {
+__device__ __forceinline__ void cn_row_h2(const KParams &P, uint32_t a0, uint32_t stride4, float w0, float w1,
+                                          uint32_t &bad) {
     uint32_t raw[DC];
 #pragma unroll
-    for (int p = 0; p < DC; ++p) raw[p] = nms_smem[off + p * stride];
+    for (int p = 0; p < DC; ++p) raw[p] = lds32(a0 + p * stride4);
     uint32_t par = 0;
 #pragma unroll
     for (int p = 0; p < DC; ++p) par ^= raw[p];
     bad |= par;
-    __half2 m1 = __float2half2_rn(10000.0f), m2 = m1;   // all-masked row -> 10000 (:248)
+    const __half2 big = __float2half2_rn(10000.0f);   // all-masked row -> 10000 (:248)
+    __half2 m1 = big, m2 = big;
+    if constexpr (DC >= 6) {
+        // two independent (min1, min2) chains over even / odd edges, merged at the end: half the dependency depth
+        __half2 n1 = big, n2 = big;
 #pragma unroll
-    for (int p = 0; p < DC; ++p) {
-        const __half2 a = __habs2(u2h(raw[p]));
-        const __half2 tmx = __hmax2(m1, a);
-        m1 = __hmin2(m1, a);
-        m2 = __hmin2(m2, tmx);
+        for (int p = 0; p < DC; p += 2) {
+            const __half2 a = __habs2(u2h(raw[p]));
+            const __half2 tmx = __hmax2(m1, a);
+            m1 = __hmin2(m1, a);
+            m2 = __hmin2(m2, tmx);
+            if (p + 1 < DC) {
+                const __half2 b = __habs2(u2h(raw[p + 1]));
+                const __half2 tnx = __hmax2(n1, b);
+                n1 = __hmin2(n1, b);
+                n2 = __hmin2(n2, tnx);
+            }
+        }
+        const __half2 hi = __hmax2(m1, n1);
+        m1 = __hmin2(m1, n1);
+        m2 = __hmin2(hi, __hmin2(m2, n2));
+    } else {
+#pragma unroll
+        for (int p = 0; p < DC; ++p) {
+            const __half2 a = __habs2(u2h(raw[p]));
+            const __half2 tmx = __hmax2(m1, a);
+            m1 = __hmin2(m1, a);
+            m2 = __hmin2(m2, tmx);
+        }
     }
     uint32_t A, B;
     h2_row_mags(P, w0, w1, (DC & 1) != 0, par, m1, m2, A, B);
 #pragma unroll
     for (int p = 0; p < DC; ++p) {
         const uint32_t gt = __hgt2_mask(__habs2(u2h(raw[p])), m1);   // |v| > min1 -> others' min is min1, else min2
-        nms_smem[off + p * stride] = ((gt & A) | (~gt & B)) ^ (raw[p] & SIGN2);
+        sts32(a0 + p * stride4, ((gt & A) | (~gt & B)) ^ (raw[p] & SIGN2));
     }
 }
 
 // any degree: two passes over shared memory instead of a register array
-static __device__ __noinline__ void cn_row_h2_generic(const KParams &P, int off, int stride, int dc, float w0, float w1,
-                                                      uint32_t &bad) {
+__device__ __forceinline__ void cn_row_h2_generic(const KParams &P, uint32_t a0, uint32_t stride4, int dc, float w0,
+                                                      float w1, uint32_t &bad) {
     uint32_t par = 0;
     __half2 m1 = __float2half2_rn(10000.0f), m2 = m1;
     for (int p = 0; p < dc; ++p) {
-        const uint32_t r = nms_smem[off + p * stride];
+        const uint32_t r = lds32(a0 + p * stride4);
         par ^= r;
         const __half2 a = __habs2(u2h(r));
         const __half2 tmx = __hmax2(m1, a);
@@ -100,103 +177,236 @@ static __device__ __noinline__ void cn_row_h2_generic(const KParams &P, int off,
     uint32_t A, B;
     h2_row_mags(P, w0, w1, (dc & 1) != 0, par, m1, m2, A, B);
     for (int p = 0; p < dc; ++p) {
-        const uint32_t r = nms_smem[off + p * stride];
+        const uint32_t r = lds32(a0 + p * stride4);
         const uint32_t gt = __hgt2_mask(__habs2(u2h(r)), m1);
-        nms_smem[off + p * stride] = ((gt & A) | (~gt & B)) ^ (r & SIGN2);
+        sts32(a0 + p * stride4, ((gt & A) | (~gt & B)) ^ (r & SIGN2));
     }
 }
 
-// per-variable part of the VN phase
+// ---- cold path (hard-decision ballots for a possible copy-out, optional float APP output), kept out of
+// line with minimal arguments so the iteration loop stays small in the instruction cache
+static __device__ __noinline__ void h2_cold(const KParams &P, int j, int t, uint32_t hbw, uint32_t app, int what,
+                                            long long frame0, int nvalid) {
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, chunk = warp % P.C, q = chunk * 32 + lane;
+    const int act = q < P.L;
+    if (what & 1) {   // ballots -> hb[buf][half][j][chunk]
+        const int buf = t < 0 ? 1 : (t & 1);
+        const uint32_t lo = __ballot_sync(0xffffffffu, act && (hbw & 1u));
+        const uint32_t hi = __ballot_sync(0xffffffffu, act && (hbw >> 16));
+        if (lane == 0) {
+            nms_smem[P.off_hb + ((buf * 2 + 0) * P.N + j) * P.C + chunk] = lo;
+            nms_smem[P.off_hb + ((buf * 2 + 1) * P.N + j) * P.C + chunk] = hi;
+        }
+    }
+    if ((what & 2) && act) {   // ya_output{t} = clip(APP) (:324-327)
+        Ctx c;
+        c.act = act; c.a_lane = q / P.Fp; c.frame0 = frame0; c.nvalid = nvalid;
+        const int fp = q - c.a_lane * P.Fp;
+        app_store(P, c, j, t, 2 * fp, fminf(fmaxf(__low2float(u2h(app)), -P.clip), P.clip));
+        app_store(P, c, j, t, 2 * fp + 1, fminf(fmaxf(__high2float(u2h(app)), -P.clip), P.clip));
+    }
+}
+
+// per-variable part of the VN phase, for NC independent columns at once (NC = 2 doubles the ILP)
 struct H2Var {
     __half2 xin;      // next iteration's weighted + quantised channel value
     uint32_t hbw;     // hard bits (bit 0 / bit 16) of this slot's two frames
-    bool has_next;
 };
 
-// slotw: word index j*LP + q.  wv_next: VN weight of the next iteration (ignored when sharing2 == 0)
-template <bool INIT>
-__device__ __forceinline__ H2Var h2_var(const KParams &P, const Ctx &c, int j, int t, int slotw, __half2 S,
-                                        bool need_hb, uint32_t &ones) {
-    H2Var v;
-    const float2 x = *reinterpret_cast<const float2 *>(&smem_f(P.off_xa + 2 * slotw));
-    __half2 xqh;
-    if (INIT) {
-        xqh = q2(P, x.x, x.y);                                   // Q(xa), :321-322
-        nms_smem[P.off_xq + slotw] = h2u(xqh);
-    } else {
-        xqh = u2h(nms_smem[P.off_xq + slotw]);
-    }
-    const __half2 app = __hadd2(xqh, S);   // unclipped APP; clip_LLR never changes its sign
-    const int tn = INIT ? 0 : t + 1;
-    v.has_next = tn < P.T_run;
-    v.xin = xqh;
-    if (v.has_next && P.sharing2 != 0) {
-        const float w = h2_wvn(P, tn, j);
-        v.xin = q2(P, __fmul_rn(x.x, w), __fmul_rn(x.y, w));     // Q(xa * w), :168-177
-    }
-    const __half2 hsrc = INIT ? v.xin : app;   // iteration 0 takes the syndrome of xin_0 (:181-182)
-    v.hbw = (~h2u(hsrc) >> 15) & LSB2;         // bit = (value >= 0); a zero here is always +0
-    if (!INIT) ones |= v.hbw;
-    if (need_hb) {
-        const uint32_t lo = __ballot_sync(0xffffffffu, c.act && (v.hbw & 1u));
-        const uint32_t hi = __ballot_sync(0xffffffffu, c.act && (v.hbw >> 16));
-        if (c.lane == 0) {
-            const int buf = INIT ? 1 : (t & 1);
-            nms_smem[P.off_hb + ((buf * 2 + 0) * P.N + j) * P.C + c.chunk] = lo;
-            nms_smem[P.off_hb + ((buf * 2 + 1) * P.N + j) * P.C + c.chunk] = hi;
+// j[k]: column, jlp[k] = j*LP (words); wvrow: byte address of the next iteration's VN weight row; cold: bit 0 =
+// ballots wanted, bit 1 = APP output wanted.  INIT: the pass before iteration 0 (C->V = 0): writes xq, and the
+// hard bit is taken from xin_0.  Returns has_next.
+template <bool INIT, int NC>
+__device__ __forceinline__ bool h2_var(const KParams &P, const Ctx &c, const H2Ctx &h, const int (&j)[NC],
+                                       const int (&jlp)[NC], int t, const __half2 (&S)[NC], uint32_t wvrow, int cold,
+                                       uint32_t &ones, H2Var (&v)[NC]) {
+    float2 x[NC];
+    __half2 xqh[NC], app[NC];
+#pragma unroll
+    for (int k = 0; k < NC; ++k) x[k] = lds64f(h.xa8 + (uint32_t)jlp[k] * 8u);
+#pragma unroll
+    for (int k = 0; k < NC; ++k) {
+        if (INIT) {
+            xqh[k] = q2(P, x[k].x, x[k].y);                       // Q(xa), :321-322
+            sts32(h.xq4 + (uint32_t)jlp[k] * 4u, h2u(xqh[k]));
+        } else {
+            xqh[k] = u2h(lds32(h.xq4 + (uint32_t)jlp[k] * 4u));
         }
     }
-    if (!INIT && P.app != nullptr) {   // optional float APP output (ya_output{t}, :324-327)
-        app_store(P, c, j, t, c.f0, fminf(fmaxf(__low2float(app), -P.clip), P.clip));
-        app_store(P, c, j, t, c.f1, fminf(fmaxf(__high2float(app), -P.clip), P.clip));
+    const int tn = INIT ? 0 : t + 1;
+    const bool has_next = tn < P.T_run;
+#pragma unroll
+    for (int k = 0; k < NC; ++k) {
+        app[k] = __hadd2(xqh[k], S[k]);   // unclipped APP; clip_LLR never changes its sign
+        v[k].xin = xqh[k];
     }
-    return v;
+    if (has_next && P.sharing2 != 0) {
+        float w[NC];
+#pragma unroll
+        for (int k = 0; k < NC; ++k) w[k] = h2_w(wvrow, j[k], P.h2_mv);
+#pragma unroll
+        for (int k = 0; k < NC; ++k)
+            v[k].xin = q2(P, __fmul_rn(x[k].x, w[k]), __fmul_rn(x[k].y, w[k]));   // Q(xa * w), :168-177
+    }
+#pragma unroll
+    for (int k = 0; k < NC; ++k) {
+        const __half2 hsrc = INIT ? v[k].xin : app[k];   // iteration 0 takes the syndrome of xin_0 (:181-182)
+        v[k].hbw = (~h2u(hsrc) >> 15) & LSB2;            // bit = (value >= 0); a zero here is always +0
+        if (!INIT) ones |= v[k].hbw;
+    }
+    if (cold) {
+#pragma unroll
+        for (int k = 0; k < NC; ++k) h2_cold(P, j[k], t, v[k].hbw, h2u(app[k]), cold, c.frame0, c.nvalid);
+    }
+    return has_next;
 }
 
-// INIT: the pass before iteration 0 (C->V = 0): writes xq, V->C = Q(xa*wv_0), hard bit of xin_0.
-template <int DV, bool INIT>
-__device__ __forceinline__ void vn_col_h2(const KParams &P, const Ctx &c, int j, int t, bool need_hb, uint32_t &ones) {
-    const int c0 = P.col_ptr[j], L = P.L;
-    int addr[DV];
-    uint32_t cv[DV];
+// NC variable columns of degree DV held in registers; table-driven (generic kernels): P.vn_edge = {e*LP*4, rot*4}
+template <int DV, bool INIT, bool PAD, int NC>
+__device__ __forceinline__ void vn_col_h2(const KParams &P, const Ctx &c, const H2Ctx &h, const int (&j)[NC], int t,
+                                          uint32_t wvrow, int cold, uint32_t &ones) {
+    const uint32_t L4 = (uint32_t)P.L * 4u;
+    uint32_t addr[NC][DV], cv[NC][DV];
+    int jlp[NC];
 #pragma unroll
-    for (int u = 0; u < DV; ++u) {
-        addr[u] = vn_addr(c, P.vn_edge[c0 + u], L);
-        cv[u] = INIT ? 0u : nms_smem[addr[u]];
-    }
-    __half2 S = __float2half2_rn(0.0f);
-    if (!INIT) {
-#pragma unroll
-        for (int u = 0; u < DV; ++u) S = __hadd2(S, u2h(cv[u]));
-    }
-    const H2Var v = h2_var<INIT>(P, c, j, t, j * P.LP + c.q, S, need_hb, ones);
-    if (v.has_next) {
-        const __half2 SX = __hadd2(v.xin, S);
+    for (int k = 0; k < NC; ++k) {
+        const int c0 = P.col_ptr[j[k]];
+        jlp[k] = j[k] * P.LP;
 #pragma unroll
         for (int u = 0; u < DV; ++u) {
-            const __half2 m = INIT ? v.xin : __hsub2(SX, u2h(cv[u]));   // total - self: exact on the grid (:213-215)
-            nms_smem[addr[u]] = h2u(m) | v.hbw;
+            const int2 ve = P.vn_edge[c0 + u];
+            addr[k][u] = h.sb + (uint32_t)ve.x + h2_rot<PAD>(h, (uint32_t)ve.y, L4);
+            cv[k][u] = INIT ? 0u : lds32(addr[k][u]);
+        }
+    }
+    __half2 S[NC];
+#pragma unroll
+    for (int k = 0; k < NC; ++k) {
+        S[k] = __float2half2_rn(0.0f);
+        if (!INIT) {
+#pragma unroll
+            for (int u = 0; u < DV; ++u) S[k] = __hadd2(S[k], u2h(cv[k][u]));
+        }
+    }
+    H2Var v[NC];
+    const bool has_next = h2_var<INIT, NC>(P, c, h, j, jlp, t, S, wvrow, cold, ones, v);
+    if (has_next) {
+#pragma unroll
+        for (int k = 0; k < NC; ++k) {
+            const __half2 SX = __hadd2(v[k].xin, S[k]);
+#pragma unroll
+            for (int u = 0; u < DV; ++u) {
+                const __half2 m = INIT ? v[k].xin : __hsub2(SX, u2h(cv[k][u]));   // total - self: exact on the grid
+                sts32(addr[k][u], h2u(m) | v[k].hbw);
+            }
         }
     } else {
 #pragma unroll
-        for (int u = 0; u < DV; ++u) nms_smem[addr[u]] = v.hbw;         // only the final syndrome pass reads these
+        for (int k = 0; k < NC; ++k)
+#pragma unroll
+            for (int u = 0; u < DV; ++u) sts32(addr[k][u], v[k].hbw);   // only the final syndrome pass reads these
     }
 }
 
 template <bool INIT>
-__device__ __noinline__ void vn_col_h2_generic(const KParams &P, const Ctx &c, int j, int t, bool need_hb,
-                                               uint32_t &ones) {
-    const int c0 = P.col_ptr[j], dv = P.col_ptr[j + 1] - c0, L = P.L;
-    __half2 S = __float2half2_rn(0.0f);
+__device__ __forceinline__ void vn_col_h2_generic(const KParams &P, const Ctx &c, const H2Ctx &h, int j, int t,
+                                                  uint32_t wvrow, int cold, uint32_t &ones) {
+    const int c0 = P.col_ptr[j], dv = P.col_ptr[j + 1] - c0;
+    const uint32_t L4 = (uint32_t)P.L * 4u;
+    __half2 S[1] = {__float2half2_rn(0.0f)};
     if (!INIT)
-        for (int u = 0; u < dv; ++u) S = __hadd2(S, u2h(nms_smem[vn_addr(c, P.vn_edge[c0 + u], L)]));
-    const H2Var v = h2_var<INIT>(P, c, j, t, j * P.LP + c.q, S, need_hb, ones);
-    const __half2 SX = __hadd2(v.xin, S);
+        for (int u = 0; u < dv; ++u) {
+            const int2 ve = P.vn_edge[c0 + u];
+            S[0] = __hadd2(S[0], u2h(lds32(h.sb + (uint32_t)ve.x + h2_rot<true>(h, (uint32_t)ve.y, L4))));
+        }
+    const int jj[1] = {j}, jlp[1] = {j * P.LP};
+    H2Var v[1];
+    const bool has_next = h2_var<INIT, 1>(P, c, h, jj, jlp, t, S, wvrow, cold, ones, v);
+    const __half2 SX = __hadd2(v[0].xin, S[0]);
     for (int u = 0; u < dv; ++u) {
-        const int a = vn_addr(c, P.vn_edge[c0 + u], L);
-        uint32_t o = v.hbw;
-        if (v.has_next) o |= h2u(INIT ? v.xin : __hsub2(SX, u2h(nms_smem[a])));
-        nms_smem[a] = o;
+        const int2 ve = P.vn_edge[c0 + u];
+        const uint32_t a = h.sb + (uint32_t)ve.x + h2_rot<true>(h, (uint32_t)ve.y, L4);
+        uint32_t o = v[0].hbw;
+        if (has_next) o |= h2u(INIT ? v[0].xin : __hsub2(SX, u2h(lds32(a))));
+        sts32(a, o);
+    }
+}
+
+// syndrome parity of the hard bits parked in the message LSBs after the last VN phase
+__device__ __forceinline__ uint32_t h2_synd_phase(const KParams &P, const Ctx &c) {
+    uint32_t bad = 0;
+    for (int n = c.slot; n < P.M; n += P.R) {
+        const int i = P.cn_order[n];
+        const int e0 = P.row_ptr[i], dc = P.row_ptr[i + 1] - e0;
+        uint32_t par = 0;
+        for (int p = 0; p < dc; ++p) par ^= nms_smem[(e0 + p) * P.LP + c.q];
+        bad |= par;
+    }
+    return bad;
+}
+
+// per-phase constants of the VN phase
+__device__ __forceinline__ int h2_cold_mask(const KParams &P, bool init, bool need_hb) {
+    return (need_hb ? 1 : 0) | ((!init && P.app != nullptr) ? 2 : 0);
+}
+
+// table-driven VN phase over this warp's columns (generic kernels; INIT pass of the specialised ones).
+// Columns are sorted by degree; slot s owns positions p % R == s, walked with one running position, so the degree
+// dispatch happens once per degree class and columns of one class are processed two at a time.
+template <int DV, bool INIT, bool PAD>
+__device__ __forceinline__ void h2_vn_class(const KParams &P, const Ctx &c, const H2Ctx &h, int &p, int end, int t,
+                                            uint32_t wvrow, int cold, uint32_t &ones) {
+    const int R = P.R;
+    if constexpr (DV <= 3) {
+        while (p + R < end) {
+            const int jj[2] = {P.vn_order[p], P.vn_order[p + R]};
+            vn_col_h2<DV, INIT, PAD, 2>(P, c, h, jj, t, wvrow, cold, ones);
+            p += 2 * R;
+        }
+    }
+    while (p < end) {
+        const int jj[1] = {P.vn_order[p]};
+        vn_col_h2<DV, INIT, PAD, 1>(P, c, h, jj, t, wvrow, cold, ones);
+        p += R;
+    }
+}
+
+template <int DVB, bool INIT>
+__device__ __forceinline__ void h2_vn_phase_tab(const KParams &P, const Ctx &c, const H2Ctx &h, int t, bool need_hb,
+                                                uint32_t &ones) {
+    const bool pad = P.L != P.LP;
+    const uint32_t wvrow = h2_wrow(h, P.h2w_v, INIT ? 0 : t + 1, P.h2_wv);
+    const int cold = h2_cold_mask(P, INIT, need_hb);
+    if constexpr (DVB == 0) {
+        for (int n = c.slot; n < P.N; n += P.R) vn_col_h2_generic<INIT>(P, c, h, P.vn_order[n], t, wvrow, cold, ones);
+    } else {
+        int p = c.slot;
+        for (int k = 0; k < P.n_vn_cls; ++k) {
+            const ushort4 cl = P.vn_cls[k];
+            const int end = cl.z;
+            if (p >= end) continue;
+            if (pad) {
+                switch (cl.x) {
+#define X(d)                                                                                          \
+    case (d) + 1:                                                                                     \
+        if constexpr ((d) < DVB) h2_vn_class<(d) + 1, INIT, true>(P, c, h, p, end, t, wvrow, cold, ones); \
+        break;
+                    NMS_REP_DESC(X)
+#undef X
+                default: break;
+                }
+            } else {
+                switch (cl.x) {
+#define X(d)                                                                                           \
+    case (d) + 1:                                                                                      \
+        if constexpr ((d) < DVB) h2_vn_class<(d) + 1, INIT, false>(P, c, h, p, end, t, wvrow, cold, ones); \
+        break;
+                    NMS_REP_DESC(X)
+#undef X
+                default: break;
+                }
+            }
+        }
     }
 }
 
