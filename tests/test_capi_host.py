@@ -1,0 +1,141 @@
+"""CPU: the C-ABI library loads, exports every symbol include/ldpc_b200.h declares, and its host-only
+entry points (base-graph compiler) reproduce Main_Functions.init_parameter on every shipped graph.
+No compute call is made: there is no GPU here and the library has no CPU fallback."""
+import ctypes
+import os
+import re
+
+import numpy as np
+import pytest
+
+import ldpc_error_floor_b200 as L
+from ldpc_error_floor_b200 import _lib
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+GRAPHS = ["wimax", "wifi", "mackay", "bch", "polar", "5g_r033_z32", "5g_r050_z32", "5g_r050_z64", "5g_r073_z32",
+          "5g_r073_z72"]
+
+
+def test_header_symbols_are_exported():
+    header = open(os.path.join(ROOT, "include", "ldpc_b200.h")).read()
+    declared = set(re.findall(r"\b(ldpc_[a-z_0-9]+)\s*\(", header))
+    assert len(declared) >= 18
+    lib = ctypes.CDLL(_lib.LIB_PATH)
+    for name in sorted(declared):
+        assert hasattr(lib, name), f"{name} declared in include/ldpc_b200.h but not exported"
+    assert declared == set(_lib.SYMBOLS), "python binding and header disagree"
+    assert _lib.load().ldpc_version() >= 100
+
+
+def make_graph(codes, key):
+    z, ps, pe, ss, se, E = (int(v) for v in codes[f"graph/{key}/meta"])
+    return L.BaseGraph(codes[f"graph/{key}/proto"].astype(np.int32), z, (ps, pe), (ss, se)), E
+
+
+@pytest.mark.parametrize("key", GRAPHS)
+def test_graph_compiler_matches_init_parameter(codes, key):
+    g, E = make_graph(codes, key)
+    assert g.E == E
+    assert g.rate_ref == pytest.approx(float(codes[f"graph/{key}/rate_ref"]), rel=0, abs=0)
+    assert np.array_equal(g.cn_deg, codes[f"graph/{key}/cn_deg"])
+    assert np.array_equal(g.vn_deg, codes[f"graph/{key}/vn_deg"])
+    sig = g.sigma(codes["snr_grid"])
+    assert np.allclose(sig, codes[f"graph/{key}/sigma_ref"], rtol=1e-15, atol=0)
+    # E(C) edge tables: row-major order, shift = entry mod z (Main_Functions.py:69-75)
+    proto = codes[f"graph/{key}/proto"]
+    rows, cols = np.nonzero(proto != -1)
+    assert np.array_equal(g.edge_row, rows) and np.array_equal(g.edge_col, cols)
+    assert np.array_equal(g.edge_shift, proto[rows, cols] % g.z)
+    assert g.info.max_dc == g.cn_deg.max() and g.info.max_dv == g.vn_deg.max()
+
+
+def test_rate_quirk_and_true_rate(codes):
+    g, _ = make_graph(codes, "wimax")
+    assert g.rate_ref == pytest.approx(431 / 574)         # the "+1" when nothing is punctured
+    assert g.rate_true == pytest.approx(0.75) and g.k_true == 432 and g.n_true == 576
+    assert g.sigma([3.0], use_ref_rate=False)[0] == pytest.approx(np.sqrt(1 / (2 * 0.75 * 10 ** 0.3)))
+    g5, _ = make_graph(codes, "5g_r050_z64")
+    assert g5.rate_ref == 0.5 == g5.rate_true and g5.k_true == 512 and g5.n_true == 1024
+
+
+def test_init_parameter_dropin(codes):
+    proto = codes["graph/wimax/proto"].astype(np.int32)
+    M, N, base, cn, vn, E, rate, sigma = L.init_parameter(proto, np.array([2, 2.5, 3.0, 3.5, 4.0]), 24, 0, 0, 0, 0)
+    assert (M, N, E) == (6, 24, 88) and base.sum() == 88 and rate == pytest.approx(0.7508710801393729)
+    assert np.allclose(sigma, [0.64818998, 0.6119308, 0.57769993, 0.5453839, 0.5148756], atol=1e-8)
+
+
+def test_error_codes_not_exceptions(codes):
+    lib = _lib.load()
+    h = ctypes.c_void_p()
+    proto = np.zeros((2, 3), np.int32)
+    assert lib.ldpc_graph_create(proto.ctypes.data, 2, 3, 0, 0, 0, 0, 0, ctypes.byref(h)) == -1    # z <= 0
+    assert b"bad arguments" in lib.ldpc_last_error()
+    assert lib.ldpc_graph_create(proto.ctypes.data, 2, 3, 4, 5, 2, 0, 0, ctypes.byref(h)) == -1    # pe < ps
+    assert lib.ldpc_graph_create(None, 2, 3, 4, 0, 0, 0, 0, ctypes.byref(h)) == -1
+    with pytest.raises(L.LdpcError):
+        L.BaseGraph(proto, -3)
+    assert lib.ldpc_graph_info(None, None) == -1
+    assert lib.ldpc_decode(None, None, 1, 0, 0, None, 0, None, None, None, None, None) == -1
+
+
+def test_no_cpu_fallback(codes):
+    """Without a CUDA device the product path must fail loudly, not decode on the host."""
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip("a GPU is present")
+    g, _ = make_graph(codes, "wimax")
+    ws = L.WeightSet([3, 3, 3], {i: codes[f"weights/wimax_base20/block{i}"] for i in range(3)})
+    with pytest.raises(L.LdpcError) as e:
+        L.NMSDecoder(g, ws)
+    assert e.value.code == -3 and "no CPU fallback" in str(e.value)
+
+
+def test_decoder_argument_checks(codes):
+    """check_params rules (Main_Functions.py:515-521) are enforced by ldpc_decoder_create before any CUDA call."""
+    lib = _lib.load()
+    g, _ = make_graph(codes, "wimax")
+    w = np.ones((5, 88), np.float32)
+    out = ctypes.c_void_p()
+
+    def create(sharing, dt=2, qb=5, T=5, clip=20.0):
+        sh = (ctypes.c_int32 * 3)(*sharing)
+        return lib.ldpc_decoder_create(g._h, sh, T, w.ctypes.data, w.ctypes.data, w.ctypes.data, dt, qb,
+                                       ctypes.c_float(clip), 0, ctypes.byref(out))
+    assert create([3, 3, 1]) == -1 and b"sharing[2]" in lib.ldpc_last_error()
+    assert create([3, 2, 3]) == -1 and b"sharing[1]" in lib.ldpc_last_error()
+    assert create([4, 0, 3]) == -2                      # temporal sharing: not on the decode path
+    assert create([3, 3, 3], dt=0) == -2                # sum-product: "next" row N3
+    assert create([3, 3, 3], qb=7) == -1
+    assert create([3, 3, 3], T=0) == -1
+    assert create([3, 3, 3], clip=0.0) == -1
+
+
+def test_host_logic_helpers():
+    from ldpc_error_floor_b200 import decoder as D
+    import torch
+    snr = D.check_params(1, np.array([2.0, 3.0]), [3, 3, 3], 30, 20, 10)
+    assert np.array_equal(snr, [0.0])                   # sampling_type 1 collapses the SNR list (:499-501)
+    with pytest.raises(ValueError):
+        D.check_params(2, np.array([2.0, 3.0]), [3, 0, 3], 20, 0, 20)
+    with pytest.raises(ValueError):
+        D.check_params(0, np.array([2.0]), [0, 0, 0], 20, 0, 20)
+    with pytest.raises(ValueError):
+        D.check_params(0, np.array([2.0]), [4, 0, 3], 25, 0, 20)
+    with pytest.raises(ValueError):
+        D.check_params(0, np.array([2.0]), [3, 0, 1], 20, 0, 20)
+    with pytest.raises(ValueError):
+        D.check_params(0, np.array([2.0]), [3, 2, 3], 20, 0, 20)
+    packed = torch.tensor([[0b1011, 1 << 31], [0, 5]], dtype=torch.int64).to(torch.int32)
+    bits = D.unpack_bits(packed, 40)
+    assert bits.shape == (2, 40) and bits[0, :4].tolist() == [1, 1, 0, 1] and int(bits[1, 32]) == 1
+
+
+def test_snr_point_statistics():
+    from ldpc_error_floor_b200.montecarlo import SnrPoint
+    pt = SnrPoint(3.0, 0.577, bits_per_frame=576)
+    pt.add([1000, 55, 54, 1456, 20000, 55, 0, 54])
+    assert pt.fer == 0.054 and pt.fer_last == 0.055 and pt.avg_iters == 20.0
+    assert pt.ber_last == pytest.approx(1456 / 576000)
+    lo, hi = pt.fer_ci95()
+    assert lo < 0.054 < hi and hi - lo < 0.03
