@@ -280,7 +280,7 @@ int choose_geometry(const ldpc_graph &g, bool packed, bool qms, int w_words, con
         fill_smem_layout(&tmp, packed);
         const int smem = tmp.smem_words * 4;
         if (smem > max_smem) break;
-        for (int R = 1; R * C <= 16; ++R) {
+        for (int R = 1; R * C <= 24; ++R) {
             if (forced_r && R != forced_r) continue;
             const int W = C * R;
             if (W < 2) continue;   // the per-frame bookkeeping uses two warps
@@ -389,8 +389,11 @@ extern "C" int ldpc_decoder_create(const ldpc_graph_t *g, const int32_t sharing[
         int n = 0;
         const NmsSpecEntry *tab = nms_spec_table(&n);
         const unsigned long long h = graph_hash(d->g);
+        const int want_fp = getenv("LDPC_B200_FP") ? atoi(getenv("LDPC_B200_FP")) : 0;
+        const int want_r = getenv("LDPC_B200_R") ? atoi(getenv("LDPC_B200_R")) : 0;
         for (int k = 0; k < n; ++k) {
             if (tab[k].graph_hash != h || tab[k].M != g->M || tab[k].N != g->N || tab[k].z != g->z) continue;
+            if ((want_fp && tab[k].Fp != want_fp) || (want_r && tab[k].R != want_r)) continue;   // tuning override
             const void *f = tab[k].func();
             LaunchGeom geo{};
             if (choose_geometry(d->g, true, qms, w_words, f, tab[k].Fp, tab[k].R, &geo) == LDPC_OK) {

@@ -203,7 +203,10 @@ __device__ __forceinline__ void nms_decode_body(const KParams &P) {
         __syncthreads();   // previous batch fully retired before shared memory is reused
 
         // ---------------- load channel LLRs into xa (zero for padding frames)
-        if (P.llr != nullptr) {
+        bool fused = false;   // graph-specialised kernels load global LLRs inside their unrolled init pass
+        if constexpr (Policy::FUSED_LOAD) fused = P.llr != nullptr;
+        if (fused) {
+        } else if (P.llr != nullptr) {
             const int tot = P.FB * P.NZ;
             for (int idx = tid; idx < tot; idx += blockDim.x) {
                 const int f = idx / P.NZ, k = idx - f * P.NZ;
@@ -233,7 +236,14 @@ __device__ __forceinline__ void nms_decode_body(const KParams &P) {
         }
 
         // ---------------- init pass: xq, first V->C messages, hard bits of xin_0
-        {
+        if constexpr (Policy::FUSED_LOAD) {
+            if (fused) {
+                Policy::load_init(P, c);
+            } else {
+                uint32_t dummy = 0;
+                Policy::template vn_phase<true>(P, c, -1, true, dummy);
+            }
+        } else {
             uint32_t dummy = 0;
             Policy::template vn_phase<true>(P, c, -1, true, dummy);
         }

@@ -179,6 +179,7 @@ __device__ __noinline__ void vn_col_f32_generic(const KParams &P, const Ctx &c, 
 template <int DCB, int DVB>
 struct F32Policy {
     static constexpr bool H2 = false;
+    static constexpr bool FUSED_LOAD = false;
 
     static __device__ __forceinline__ void cn_phase(const KParams &P, const Ctx &c, int t, uint32_t &bad) {
         for (int n = c.slot; n < P.M; n += P.R) {

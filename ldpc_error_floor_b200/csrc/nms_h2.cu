@@ -15,6 +15,7 @@ namespace nms {
 template <int DCB, int DVB>
 struct H2Policy {
     static constexpr bool H2 = true;
+    static constexpr bool FUSED_LOAD = false;
 
     template <int DC>
     static __device__ __forceinline__ void cn_class(const KParams &P, const H2Ctx &h, int &p, int end, uint32_t LP4,

@@ -1,15 +1,22 @@
 // nms_h2_spec.cuh -- graph-specialised packed kernels.  `G` is a generated struct of constexpr tables
-// (csrc/gen_spec.py, one per known base graph and launch geometry).  In the iteration loop
-//   * the VN phase is unrolled per column with every message row offset and circulant rotation as an
-//     immediate (the rotated lane offsets are loop-invariant and end up hoisted into registers);
-//   * the CN phase keeps ONE body per distinct row degree (it needs no per-edge constants, only the row's
-//     base offset), which keeps the loop small enough for the instruction cache;
-//   * the once-per-batch INIT pass and all cold paths use the compact table-driven code of nms_h2.cuh.
+// (csrc/gen_spec.py, one per known base graph and launch geometry).
+//   * VN phase: unrolled per column with every message row offset and circulant rotation as an immediate
+//     (the rotated lane offsets are loop-invariant and end up hoisted into registers).  The same unrolled
+//     column code serves the iteration loop (with or without hard-decision ballots, i.e. with or without
+//     early termination), the pass before iteration 0, and the fused "load channel LLRs from global memory +
+//     first V->C messages" prologue -- no table-driven code is left on the path of a decode without APP output.
+//   * CN phase: ONE body per distinct row degree (it needs no per-edge constants, only the row's base offset),
+//     which keeps the loop small enough for the 32 KB instruction cache.
+//   * final syndrome pass: unrolled per row.
 // Arithmetic is the shared code of nms_h2.cuh -- results are bit-identical to the generic kernels.
 #pragma once
 #include "nms_h2.cuh"
 
 namespace nms {
+
+__device__ __forceinline__ void sts64f(uint32_t a, float2 v) {
+    asm volatile("st.shared.v2.f32 [%0], {%1, %2};" ::"r"(a), "f"(v.x), "f"(v.y));
+}
 
 template <class G, int ROT>
 __device__ __forceinline__ uint32_t spec_rot(const H2Ctx &h) {
@@ -23,11 +30,16 @@ __device__ __forceinline__ uint32_t spec_rot(const H2Ctx &h) {
     }
 }
 
+enum { VN_ITER = 0, VN_INIT_SMEM = 1, VN_INIT_GLOBAL = 2 };
+
 template <class G>
 struct H2SpecPolicy {
     static constexpr bool H2 = true;
+    static constexpr bool FUSED_LOAD = true;
     static constexpr uint32_t LP4 = G::LP * 4u;
+    static constexpr bool PAD = G::L != G::LP;
 
+    // ------------------------------------------------------------------------------ CN phase
     // rows of one degree share a body; the row's base offset and weights are the only per-row values
     static __device__ __forceinline__ void cn_phase(const KParams &P, const Ctx &c, int t, uint32_t &bad) {
         const H2Ctx h = h2_ctx(P, c);
@@ -45,69 +57,162 @@ struct H2SpecPolicy {
         }
     }
 
-    // one column, everything constant-folded.  Only used for iterations that are followed by another one and
-    // need no cold-path work (ballots / APP output): no branches, no calls.  VNW: VN weights present.
-    template <int J, bool VNW>
-    static __device__ __forceinline__ void vn_col(const KParams &P, const H2Ctx &h, uint32_t wvrow, uint32_t &ones) {
+    // ------------------------------------------------------------------------------ VN phase
+    // One column, everything constant-folded: no branches, no calls.
+    //   MODE VN_ITER        iteration t: sum the C->V words, APP sign -> hard bit, xin of iteration t+1, V->C out
+    //        VN_INIT_SMEM   pass before iteration 0 (C->V = 0), channel values already in the xa array
+    //        VN_INIT_GLOBAL same, channel values `xg` just loaded from global memory (also fills the xa array)
+    //   VNW: VN weights present.  HB: publish the hard decisions as ballots (a copy-out may follow).
+    template <int J, int MODE, bool VNW, bool HB>
+    static __device__ __forceinline__ void vn_col(const KParams &P, const H2Ctx &h, uint32_t wvrow, uint32_t hbrow,
+                                                  float2 xg, uint32_t &ones) {
         constexpr int C0 = G::col_ptr[J], DV = G::col_ptr[J + 1] - C0;
+        constexpr bool INIT = MODE != VN_ITER;
         uint32_t addr[DV], cv[DV];
         static_for<0, DV>([&](auto u) {
             constexpr int U = decltype(u)::v;
             constexpr uint32_t X4 = (uint32_t)G::vn_e[C0 + U] * LP4;
             constexpr int ROT = G::vn_rot[C0 + U];
             addr[U] = h.sb + spec_rot<G, ROT>(h) + X4;
-            cv[U] = lds32(addr[U]);
+            if constexpr (!INIT) cv[U] = lds32(addr[U]);
         });
         __half2 S = __float2half2_rn(0.0f);
+        if constexpr (!INIT) {
+            S = u2h(cv[0]);
 #pragma unroll
-        for (int u = 0; u < DV; ++u) S = __hadd2(S, u2h(cv[u]));
-        const __half2 xqh = u2h(lds32(h.xq4 + (uint32_t)(J * G::LP) * 4u));
-        const __half2 app = __hadd2(xqh, S);
+            for (int u = 1; u < DV; ++u) S = __hadd2(S, u2h(cv[u]));
+        }
+        constexpr uint32_t XA8 = (uint32_t)(J * G::LP) * 8u, XQ4 = (uint32_t)(J * G::LP) * 4u;
+        float2 x = xg;
+        __half2 xqh;
+        if constexpr (MODE == VN_INIT_GLOBAL) {
+            x.x = fminf(fmaxf(x.x, -XA_BOUND), XA_BOUND);
+            x.y = fminf(fmaxf(x.y, -XA_BOUND), XA_BOUND);
+            sts64f(h.xa8 + XA8, x);
+        }
+        if constexpr (MODE == VN_INIT_SMEM || (MODE == VN_ITER && VNW)) x = lds64f(h.xa8 + XA8);
+        if constexpr (INIT) {
+            xqh = q2(P, x.x, x.y);                       // Q(xa), :321-322
+            sts32(h.xq4 + XQ4, h2u(xqh));
+        } else {
+            xqh = u2h(lds32(h.xq4 + XQ4));
+        }
         __half2 xin = xqh;
         if constexpr (VNW) {
-            const float2 x = lds64f(h.xa8 + (uint32_t)(J * G::LP) * 8u);
             const float w = h2_w(wvrow, J, P.h2_mv);
             xin = q2(P, __fmul_rn(x.x, w), __fmul_rn(x.y, w));   // Q(xa * w), :168-177
         }
-        const uint32_t hbw = (~h2u(app) >> 15) & LSB2;
-        ones |= hbw;
-        const __half2 SX = __hadd2(xin, S);
+        // hard bit = (value >= 0): of xin_0 before iteration 0 (:181-182), of the APP afterwards (a zero is +0)
+        const __half2 hsrc = INIT ? xin : __hadd2(xqh, S);
+        const uint32_t hbw = ~(h2u(hsrc) >> 15) & LSB2;
+        if constexpr (!INIT) ones |= hbw;
+        if constexpr (HB) {
+            const bool act = !PAD || h.amask != 0u;
+            const uint32_t lo = __ballot_sync(0xffffffffu, act && (hbw & 1u));
+            const uint32_t hi = __ballot_sync(0xffffffffu, act && (hbw >> 16));
+            if ((threadIdx.x & 31) == 0) {
+                sts32(hbrow + (uint32_t)(J * G::C) * 4u, lo);
+                sts32(hbrow + (uint32_t)((G::N + J) * G::C) * 4u, hi);
+            }
+        }
+        if constexpr (INIT) {
 #pragma unroll
-        for (int u = 0; u < DV; ++u) sts32(addr[u], h2u(__hsub2(SX, u2h(cv[u]))) | hbw);
+            for (int u = 0; u < DV; ++u) sts32(addr[u], h2u(xin) | hbw);
+        } else {
+            const __half2 SX = __hadd2(xin, S);
+#pragma unroll
+            for (int u = 0; u < DV; ++u) sts32(addr[u], h2u(__hsub2(SX, u2h(cv[u]))) | hbw);   // total - self: exact
+        }
     }
 
-    template <int SLOT, bool VNW>
-    static __device__ __forceinline__ void vn_slot(const KParams &P, const H2Ctx &h, uint32_t wvrow, uint32_t &ones) {
+    template <int SLOT, int MODE, bool VNW, bool HB>
+    static __device__ __forceinline__ void vn_slot(const KParams &P, const Ctx &c, const H2Ctx &h, uint32_t wvrow,
+                                                   uint32_t hbrow, uint32_t &ones) {
         constexpr int NT = (G::N - SLOT + G::R - 1) / G::R;
-        static_for<0, NT>([&](auto n) {
-            constexpr int J = G::vn_order[SLOT + decltype(n)::v * G::R];
-            vn_col<J, VNW>(P, h, wvrow, ones);
-        });
+        if constexpr (MODE == VN_INIT_GLOBAL) {
+            // this lane's two frames: all of the slot's loads are issued before the first use
+            const bool v0 = c.act && c.f0 < c.nvalid, v1 = c.act && c.f1 < c.nvalid;
+            const float *p0 = P.llr + (c.frame0 + (v0 ? c.f0 : 0)) * (long long)P.NZ + c.a_lane;
+            const float *p1 = P.llr + (c.frame0 + (v1 ? c.f1 : 0)) * (long long)P.NZ + c.a_lane;
+            float2 x[NT];
+            static_for<0, NT>([&](auto n) {
+                constexpr int J = G::vn_order[SLOT + decltype(n)::v * G::R];
+                x[decltype(n)::v].x = v0 ? __ldg(p0 + J * G::z) : 0.0f;
+                x[decltype(n)::v].y = v1 ? __ldg(p1 + J * G::z) : 0.0f;
+            });
+            static_for<0, NT>([&](auto n) {
+                constexpr int J = G::vn_order[SLOT + decltype(n)::v * G::R];
+                vn_col<J, MODE, VNW, HB>(P, h, wvrow, hbrow, x[decltype(n)::v], ones);
+            });
+        } else {
+            static_for<0, NT>([&](auto n) {
+                constexpr int J = G::vn_order[SLOT + decltype(n)::v * G::R];
+                vn_col<J, MODE, VNW, HB>(P, h, wvrow, hbrow, make_float2(0.0f, 0.0f), ones);
+            });
+        }
+    }
+
+    template <int MODE, bool HB>
+    static __device__ __forceinline__ void vn_dispatch(const KParams &P, const Ctx &c, const H2Ctx &h, int trow, int tbuf,
+                                                       uint32_t &ones) {
+        const uint32_t wvrow = h2_wrow(h, P.h2w_v, trow, P.h2_wv);
+        // ballots go to hb[buf][half][j][chunk]
+        const uint32_t hbrow = h.sb + (uint32_t)(P.off_hb + tbuf * 2 * G::N * G::C + c.chunk) * 4u;
+        if (P.sharing2 != 0) {
+            static_for<0, G::R>([&](auto s) {
+                if (c.slot == decltype(s)::v) vn_slot<decltype(s)::v, MODE, true, HB>(P, c, h, wvrow, hbrow, ones);
+            });
+        } else {
+            static_for<0, G::R>([&](auto s) {
+                if (c.slot == decltype(s)::v) vn_slot<decltype(s)::v, MODE, false, HB>(P, c, h, wvrow, hbrow, ones);
+            });
+        }
     }
 
     template <bool INIT>
     static __device__ __forceinline__ void vn_phase(const KParams &P, const Ctx &c, int t, bool need_hb, uint32_t &ones) {
         const H2Ctx h = h2_ctx(P, c);
-        const int cold = h2_cold_mask(P, INIT, need_hb);
-        if (INIT || cold != 0 || t + 1 >= P.T_run) {
-            // init pass, last iteration, ballots or APP output wanted: the compact table-driven code
-            h2_vn_phase_tab<0, INIT>(P, c, h, t, need_hb, ones);
+        if (!INIT && P.app != nullptr) {
+            h2_vn_phase_tab<0, INIT>(P, c, h, t, need_hb, ones);   // APP output wanted: the compact table-driven code
+            return;
+        }
+        if constexpr (INIT) {
+            vn_dispatch<VN_INIT_SMEM, false>(P, c, h, 0, 0, ones);
         } else {
-            const uint32_t wvrow = h2_wrow(h, P.h2w_v, t + 1, P.h2_wv);
-            if (P.sharing2 != 0) {
-                static_for<0, G::R>([&](auto s) {
-                    if (c.slot == decltype(s)::v) vn_slot<decltype(s)::v, true>(P, h, wvrow, ones);
-                });
-            } else {
-                static_for<0, G::R>([&](auto s) {
-                    if (c.slot == decltype(s)::v) vn_slot<decltype(s)::v, false>(P, h, wvrow, ones);
-                });
-            }
+            // the last iteration has no successor: it reuses its own weight row, and its V->C words only carry the
+            // hard bits (mantissa LSB) into the final syndrome pass
+            const int trow = min(t + 1, P.T_run - 1);
+            if (need_hb) vn_dispatch<VN_ITER, true>(P, c, h, trow, t & 1, ones);
+            else vn_dispatch<VN_ITER, false>(P, c, h, trow, t & 1, ones);
         }
     }
 
+    // channel LLRs straight from global memory into the first V->C messages (replaces load + init pass)
+    static __device__ __forceinline__ void load_init(const KParams &P, const Ctx &c) {
+        const H2Ctx h = h2_ctx(P, c);
+        uint32_t dummy = 0;
+        vn_dispatch<VN_INIT_GLOBAL, false>(P, c, h, 0, 0, dummy);
+    }
+
+    // ------------------------------------------------------------------ final syndrome pass
     static __device__ __forceinline__ uint32_t synd_phase(const KParams &P, const Ctx &c, int tl) {
-        return h2_synd_phase(P, c);
+        const uint32_t a0 = (uint32_t)__cvta_generic_to_shared(nms_smem) + (uint32_t)c.q * 4u;
+        uint32_t bad = 0;
+        static_for<0, G::R>([&](auto s) {
+            constexpr int SLOT = decltype(s)::v;
+            constexpr int NT = (G::M - SLOT + G::R - 1) / G::R;
+            if (c.slot == SLOT) {
+                static_for<0, NT>([&](auto n) {
+                    constexpr int I = G::cn_order[SLOT + decltype(n)::v * G::R];
+                    constexpr int E0 = G::row_ptr[I], DC = G::row_ptr[I + 1] - E0;
+                    uint32_t par = 0;
+#pragma unroll
+                    for (int p = 0; p < DC; ++p) par ^= lds32(a0 + (uint32_t)(E0 + p) * LP4);
+                    bad |= par;
+                });
+            }
+        });
+        return bad;
     }
 };
 
