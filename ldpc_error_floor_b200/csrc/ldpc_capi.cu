@@ -85,6 +85,12 @@ struct HostScratch {
     int *iters[2] = {nullptr, nullptr};
     uint8_t *flags[2] = {nullptr, nullptr};
     int *biterr[2] = {nullptr, nullptr};
+    // pinned host staging of the per-frame outputs, so the device-to-host copies stay asynchronous even when
+    // the caller's result arrays are pageable (one blocking copy would serialise the two-stream pipeline)
+    uint32_t *h_hard[2] = {nullptr, nullptr};
+    int *h_iters[2] = {nullptr, nullptr};
+    uint8_t *h_flags[2] = {nullptr, nullptr};
+    int *h_biterr[2] = {nullptr, nullptr};
     cudaStream_t st[2] = {nullptr, nullptr};
     unsigned long long *counters = nullptr;
     unsigned int *ucount = nullptr;
@@ -260,7 +266,7 @@ unsigned long long graph_hash(const ldpc_graph &g) {   // FNV-1a over (M, N, z, 
 
 // pick (Fp, R): lane efficiency x task balance x achievable warps/SM (from the real occupancy calculator)
 int choose_geometry(const ldpc_graph &g, bool packed, bool qms, int w_words, const void *func, int force_fp,
-                    int force_r, LaunchGeom *out) {
+                    int force_r, int max_warps, LaunchGeom *out) {
     const int max_smem = 227 * 1024;
     double best = -1.0;
     int forced_fp = force_fp, forced_r = force_r;
@@ -280,7 +286,7 @@ int choose_geometry(const ldpc_graph &g, bool packed, bool qms, int w_words, con
         fill_smem_layout(&tmp, packed);
         const int smem = tmp.smem_words * 4;
         if (smem > max_smem) break;
-        for (int R = 1; R * C <= 24; ++R) {
+        for (int R = 1; R * C <= max_warps; ++R) {
             if (forced_r && R != forced_r) continue;
             const int W = C * R;
             if (W < 2) continue;   // the per-frame bookkeeping uses two warps
@@ -396,7 +402,7 @@ extern "C" int ldpc_decoder_create(const ldpc_graph_t *g, const int32_t sharing[
             if ((want_fp && tab[k].Fp != want_fp) || (want_r && tab[k].R != want_r)) continue;   // tuning override
             const void *f = tab[k].func();
             LaunchGeom geo{};
-            if (choose_geometry(d->g, true, qms, w_words, f, tab[k].Fp, tab[k].R, &geo) == LDPC_OK) {
+            if (choose_geometry(d->g, true, qms, w_words, f, tab[k].Fp, tab[k].R, 32, &geo) == LDPC_OK) {
                 d->func = f; d->geom = geo; d->spec_name = tab[k].name; rc = LDPC_OK;
                 break;
             }
@@ -404,7 +410,7 @@ extern "C" int ldpc_decoder_create(const ldpc_graph_t *g, const int32_t sharing[
     }
     if (d->func == nullptr) {
         d->func = pick_kernel(d->packed, g->info.max_dc, g->info.max_dv, &d->dcb, &d->dvb);
-        rc = choose_geometry(d->g, d->packed, qms, w_words, d->func, 0, 0, &d->geom);
+        rc = choose_geometry(d->g, d->packed, qms, w_words, d->func, 0, 0, 16, &d->geom);   // generic kernels: __launch_bounds__(512)
     }
     if (rc != LDPC_OK) { delete d; return rc; }
 
@@ -438,6 +444,20 @@ extern "C" int ldpc_decoder_create(const ldpc_graph_t *g, const int32_t sharing[
         P.n_vn_cls = degree_classes(dv, P.vn_order, P.vn_cls, 32);
         if (P.n_cn_cls < 0 || P.n_vn_cls < 0) { delete d; return fail(LDPC_E_LIMIT, "more than 32 distinct node degrees"); }
     }
+    {
+        const int NT = (g->M + P.R - 1) / P.R;   // rows per task slot (slot s owns positions s, s+R, ... of cn_order)
+        for (int s = 0; s < P.R && s * NT < LDPC_MAX_M; ++s)
+            for (int n = 0; n < NT && s * NT + n < LDPC_MAX_M; ++n) {
+                const int p = s + n * P.R;
+                uint2 tk = make_uint2(0u, 0u);
+                if (p < g->M) {
+                    const int i = P.cn_order[p];
+                    tk.x = (unsigned)(g->row_ptr[i] * P.LP * 4);
+                    tk.y = (unsigned)(g->row_ptr[i + 1] - g->row_ptr[i]) | ((unsigned)i << 16);
+                }
+                P.cn_task[s * NT + n] = tk;
+            }
+    }
     for (int e = 0; e < g->E; ++e) {
         P.e_col[e] = (unsigned short)g->col[e];
         P.e_sF[e] = (unsigned short)(g->shift[e] * P.Fp);
@@ -467,6 +487,7 @@ void free_scratch(HostScratch &h) {
     for (int i = 0; i < 2; ++i) {
         cudaFree(h.llr[i]); cudaFree(h.app[i]); cudaFree(h.hard[i]); cudaFree(h.iters[i]);
         cudaFree(h.flags[i]); cudaFree(h.biterr[i]);
+        cudaFreeHost(h.h_hard[i]); cudaFreeHost(h.h_iters[i]); cudaFreeHost(h.h_flags[i]); cudaFreeHost(h.h_biterr[i]);
         if (h.st[i]) cudaStreamDestroy(h.st[i]);
     }
     cudaFree(h.counters); cudaFree(h.ucount); cudaFree(h.ubuf);
@@ -539,6 +560,10 @@ int ensure_host_scratch(ldpc_decoder *d, size_t chunk, bool with_app, int app_it
         CUDA_TRY(cudaMalloc(&h.iters[i], chunk * sizeof(int)));
         CUDA_TRY(cudaMalloc(&h.flags[i], chunk));
         CUDA_TRY(cudaMalloc(&h.biterr[i], chunk * sizeof(int)));
+        CUDA_TRY(cudaMallocHost(&h.h_hard[i], chunk * P.HW * sizeof(uint32_t)));
+        CUDA_TRY(cudaMallocHost(&h.h_iters[i], chunk * sizeof(int)));
+        CUDA_TRY(cudaMallocHost(&h.h_flags[i], chunk));
+        CUDA_TRY(cudaMallocHost(&h.h_biterr[i], chunk * sizeof(int)));
         if (with_app) CUDA_TRY(cudaMalloc(&h.app[i], (size_t)app_iters * chunk * P.NZ * sizeof(float)));
     }
     h.cap_frames = chunk; h.with_app = with_app; h.app_iters = app_iters;
@@ -567,10 +592,27 @@ extern "C" int ldpc_decode_host(const ldpc_decoder_t *dc, const float *llr_host,
     int rc = ensure_host_scratch(d, chunk, app_iters > 0, app_iters);
     if (rc != LDPC_OK) return rc;
     HostScratch &h = d->hs;
+    // results of the chunk that last used buffer pair k: staged in pinned memory, handed to the caller once
+    // stream k has drained (which the next use of pair k, two chunks later, has to wait for anyway)
+    int64_t pend_off[2] = {0, 0}, pend_n[2] = {0, 0};
+    auto drain = [&](int k) -> int {
+        CUDA_TRY(cudaStreamSynchronize(h.st[k]));
+        const int64_t off = pend_off[k], nb = pend_n[k];
+        if (nb > 0) {
+            if (hard_host) std::memcpy(hard_host + off * P0.HW, h.h_hard[k], (size_t)nb * P0.HW * 4);
+            if (iters_host) std::memcpy(iters_host + off, h.h_iters[k], (size_t)nb * 4);
+            if (flags_host) std::memcpy(flags_host + off, h.h_flags[k], (size_t)nb);
+            if (biterr_host) std::memcpy(biterr_host + off, h.h_biterr[k], (size_t)nb * 4);
+        }
+        pend_n[k] = 0;
+        return LDPC_OK;
+    };
     int k = 0;
     for (int64_t off = 0; off < B; off += (int64_t)chunk, k ^= 1) {
         const int64_t nb = std::min<int64_t>((int64_t)chunk, B - off);
         cudaStream_t st = h.st[k];
+        rc = drain(k);
+        if (rc != LDPC_OK) return rc;
         CUDA_TRY(cudaMemcpyAsync(h.llr[k], llr_host + off * P0.NZ, (size_t)nb * P0.NZ * sizeof(float),
                                  cudaMemcpyHostToDevice, st));
         KParams P = P0;
@@ -581,21 +623,20 @@ extern "C" int ldpc_decode_host(const ldpc_decoder_t *dc, const float *llr_host,
         P.flags = flags_host ? h.flags[k] : nullptr; P.biterr = biterr_host ? h.biterr[k] : nullptr;
         rc = launch(d, P, st);
         if (rc != LDPC_OK) return rc;
-        if (hard_host)
-            CUDA_TRY(cudaMemcpyAsync(hard_host + off * P.HW, h.hard[k], (size_t)nb * P.HW * 4, cudaMemcpyDeviceToHost, st));
-        if (iters_host) CUDA_TRY(cudaMemcpyAsync(iters_host + off, h.iters[k], (size_t)nb * 4, cudaMemcpyDeviceToHost, st));
-        if (flags_host) CUDA_TRY(cudaMemcpyAsync(flags_host + off, h.flags[k], (size_t)nb, cudaMemcpyDeviceToHost, st));
-        if (biterr_host) CUDA_TRY(cudaMemcpyAsync(biterr_host + off, h.biterr[k], (size_t)nb * 4, cudaMemcpyDeviceToHost, st));
+        if (hard_host) CUDA_TRY(cudaMemcpyAsync(h.h_hard[k], h.hard[k], (size_t)nb * P.HW * 4, cudaMemcpyDeviceToHost, st));
+        if (iters_host) CUDA_TRY(cudaMemcpyAsync(h.h_iters[k], h.iters[k], (size_t)nb * 4, cudaMemcpyDeviceToHost, st));
+        if (flags_host) CUDA_TRY(cudaMemcpyAsync(h.h_flags[k], h.flags[k], (size_t)nb, cudaMemcpyDeviceToHost, st));
+        if (biterr_host) CUDA_TRY(cudaMemcpyAsync(h.h_biterr[k], h.biterr[k], (size_t)nb * 4, cudaMemcpyDeviceToHost, st));
+        pend_off[k] = off; pend_n[k] = nb;
         if (app_iters) {
             const size_t row = (size_t)nb * P.NZ * sizeof(float);
             CUDA_TRY(cudaMemcpy2DAsync(app_host + off * P.NZ, (size_t)B * P.NZ * sizeof(float), h.app[k], row, row,
                                        (size_t)app_iters, cudaMemcpyDeviceToHost, st));
         }
-        // buffer pair k is tied to stream k, so its reuse two chunks later is ordered by the stream itself
     }
-    CUDA_TRY(cudaStreamSynchronize(h.st[0]));
-    CUDA_TRY(cudaStreamSynchronize(h.st[1]));
-    return LDPC_OK;
+    rc = drain(k);          // older chunk first, so the caller's arrays fill in order
+    if (rc != LDPC_OK) return rc;
+    return drain(k ^ 1);
 }
 
 // ------------------------------------------------------------------- generator / Monte-Carlo

@@ -66,6 +66,7 @@ struct KParams {
     unsigned short vn_order[LDPC_MAX_N];      // columns likewise
     int n_cn_cls, n_vn_cls;                   // runs of equal degree inside cn_order / vn_order
     ushort4 cn_cls[32], vn_cls[32];           // {degree, first position, end position, 0}
+    uint2 cn_task[LDPC_MAX_M];                // slot-major row list: [slot * ceil(M/R) + n] = {e0*LP*4, dc | row << 16}; dc 0 = none
     unsigned short e_col[LDPC_MAX_E];         // proto column of E(C) edge e
     unsigned short e_sF[LDPC_MAX_E];          // s_e*Fp: check lane q -> variable lane (q + sF) mod L
     int2 vn_edge[LDPC_MAX_E];                 // column-sorted: {e*LP, (L - s_e*Fp) mod L} in words (float kernel) / bytes (packed)

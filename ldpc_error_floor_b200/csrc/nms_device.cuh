@@ -26,8 +26,8 @@ constexpr uint32_t SIGN2 = 0x80008000u;
 constexpr uint32_t LSB2 = 0x00010001u;
 
 // misc shared words
-constexpr int MISC_SYND = 0;      // [2][64] syndrome-bad flag of the previous APP, by iteration parity
-constexpr int MISC_ONES = 128;    // [2][64] "hard decision has a one" flag, by iteration parity
+constexpr int MISC_SYND = 0;      // [2][2] frame masks "syndrome of the previous APP is bad", by iteration parity
+constexpr int MISC_ONES = 8;      // [2][2] frame masks "hard decision has a one", by iteration parity
 constexpr int MISC_BITERR = 256;  // [64]
 constexpr int MISC_HIDX = 320;    // [64] harvest row index (or 0xffffffff)
 constexpr int MISC_CTRL = 384;    // [16]
@@ -68,6 +68,7 @@ struct Ctx {
     int act;      // 1 for q < L
     int Lthr;     // L for active lanes, INT_MAX for padding lanes (they never wrap / rotate)
     int f0, f1;   // frame(s) of this lane's slot (packed: 2fp, 2fp+1; float: fp, fp); padding lanes: 0
+    int fword, fsh;   // f0 / 32, f0 % 32: where this lane's frames sit in the per-CTA frame masks
     int a_lane;   // circulant lane of q
     long long frame0;
     int nvalid;
@@ -84,7 +85,7 @@ __device__ __forceinline__ int vn_addr(const Ctx &c, int2 ve, int L) {
 __device__ __forceinline__ bool app_frozen(const KParams &P, int t, int f) {
     const uint32_t *misc = nms_smem + P.off_misc;
     bool frozen = (misc[MISC_CTRL + CTRL_FROZEN + ((t + 1) & 1) * 2 + (f >> 5)] >> (f & 31)) & 1u;
-    if (P.early_term && t >= 1 && misc[MISC_SYND + (t & 1) * 64 + f] == 0u) frozen = true;
+    if (P.early_term && t >= 1 && ((misc[MISC_SYND + (t & 1) * 2 + (f >> 5)] >> (f & 31)) & 1u) == 0u) frozen = true;
     return frozen;
 }
 __device__ __forceinline__ void app_store(const KParams &P, const Ctx &c, int j, int t, int f, float v) {
@@ -160,13 +161,28 @@ __device__ __forceinline__ void copy_out(const KParams &P, const Ctx &c, const u
     }
 }
 
+// OR this lane's per-frame bits (bit 0: frame f0, bit 16: frame f1 = f0 + 1) into the CTA's frame mask at `base`:
+// one warp reduction + at most one shared atomic per warp and mask word
 __device__ __forceinline__ void publish(const KParams &P, const Ctx &c, int base, uint32_t bits, bool h2) {
-    if (c.act) {
-        uint32_t *dst = nms_smem + P.off_misc + base;
-        if (bits & 1u) dst[c.f0] = 1u;
-        if (h2 && (bits & 0x10000u)) dst[c.f1] = 1u;
+    uint32_t m = h2 ? ((bits & 1u) | ((bits >> 15) & 2u)) : (bits & 1u);
+    m = c.act ? m << c.fsh : 0u;
+    uint32_t *dst = nms_smem + P.off_misc + base;
+    if (P.FB <= 32) {
+        const uint32_t r = __reduce_or_sync(0xffffffffu, m);
+        if (c.lane == 0 && r) atomicOr(dst, r);
+    } else {
+        const uint32_t r0 = __reduce_or_sync(0xffffffffu, c.fword == 0 ? m : 0u);
+        const uint32_t r1 = __reduce_or_sync(0xffffffffu, c.fword == 1 ? m : 0u);
+        if (c.lane == 0 && r0) atomicOr(dst, r0);
+        if (c.lane == 0 && r1) atomicOr(dst + 1, r1);
     }
 }
+
+// per-frame decoding state of thread f < 64, packed into one register
+constexpr uint32_t ST_FROZEN = 1u, ST_SYND_EVER = 2u, ST_EVER_CORRECT = 4u, ST_OUT_SYND_OK = 8u, ST_OUT_ONE = 16u;
+constexpr int ST_ITERS_SH = 8, ST_EXEC_SH = 18;   // 10-bit fields: first zero-syndrome iteration, iterations executed
+__device__ __forceinline__ uint32_t st_set(uint32_t st, int sh, int v) { return (st & ~(0x3ffu << sh)) | ((uint32_t)v << sh); }
+__device__ __forceinline__ int st_get(uint32_t st, int sh) { return (int)((st >> sh) & 0x3ffu); }
 
 // =============================================================================== main kernel
 template <class Policy>
@@ -186,6 +202,8 @@ __device__ __forceinline__ void nms_decode_body(const KParams &P) {
         const int fp = c.act ? c.q - c.a_lane * P.Fp : 0;
         c.f0 = H2 ? 2 * fp : fp;
         c.f1 = H2 ? 2 * fp + 1 : fp;
+        c.fword = c.f0 >> 5;
+        c.fsh = c.f0 & 31;
     }
     uint32_t *misc = nms_smem + P.off_misc;
     uint32_t *ctrl = misc + MISC_CTRL;
@@ -226,12 +244,10 @@ __device__ __forceinline__ void nms_decode_body(const KParams &P) {
         }
         for (int idx = tid; idx < NMS_MISC_WORDS; idx += blockDim.x) misc[idx] = 0;
         // per-frame state lives in the registers of threads 0..63 (thread f owns frame f)
-        bool st_frozen = tid >= c.nvalid, st_synd_ever = false, st_ever_correct = false;
-        bool st_out_synd_ok = false, st_out_one = false;
-        int st_iters = P.T_run, st_executed = P.T_run;
+        uint32_t st = (tid >= c.nvalid ? ST_FROZEN : 0u) | ((uint32_t)P.T_run << ST_ITERS_SH) | ((uint32_t)P.T_run << ST_EXEC_SH);
         __syncthreads();
         if (tid < 64) {
-            const uint32_t fm = __ballot_sync(0xffffffffu, st_frozen);
+            const uint32_t fm = __ballot_sync(0xffffffffu, (st & ST_FROZEN) != 0u);
             if (c.lane == 0) { ctrl[CTRL_FROZEN + c.warp] = fm; ctrl[CTRL_FROZEN + 2 + c.warp] = fm; }
         }
 
@@ -255,29 +271,32 @@ __device__ __forceinline__ void nms_decode_body(const KParams &P) {
             // ======== CN phase (also yields the syndrome of the previous hard decision)
             uint32_t bad = 0;
             Policy::cn_phase(P, c, t, bad);
-            if (t >= 1) publish(P, c, MISC_SYND + (t & 1) * 64, bad, H2);
+            if (t >= 1) publish(P, c, MISC_SYND + (t & 1) * 2, bad, H2);
             __syncthreads();   // A
             // ======== per-frame bookkeeping for APP_{t-1} (threads 0..63), concurrent with the VN phase
             if (tid < 64) {
                 bool newly = false;
                 if (t >= 1) {
-                    const bool fbad = misc[MISC_SYND + (t & 1) * 64 + tid] != 0u;
-                    const bool one = misc[MISC_ONES + ((t - 1) & 1) * 64 + tid] != 0u;
-                    misc[MISC_ONES + ((t - 1) & 1) * 64 + tid] = 0u;
-                    if (!st_frozen) {
-                        if (!one) st_ever_correct = true;
-                        if (!fbad && !st_synd_ever) { st_synd_ever = true; st_iters = t; }
+                    const bool fbad = (misc[MISC_SYND + (t & 1) * 2 + c.warp] >> c.lane) & 1u;
+                    const bool one = (misc[MISC_ONES + ((t - 1) & 1) * 2 + c.warp] >> c.lane) & 1u;
+                    if (!(st & ST_FROZEN)) {
+                        if (!one) st |= ST_EVER_CORRECT;
+                        if (!fbad && !(st & ST_SYND_EVER)) st = st_set(st, ST_ITERS_SH, t) | ST_SYND_EVER;
                         if (P.early_term && !fbad) {
-                            st_frozen = true; newly = true;
-                            st_out_synd_ok = true; st_out_one = one; st_executed = t;
+                            newly = true;
+                            st = st_set(st, ST_EXEC_SH, t) | ST_FROZEN | ST_OUT_SYND_OK | (one ? ST_OUT_ONE : 0u);
                         }
                     }
                 }
-                misc[MISC_SYND + ((t + 1) & 1) * 64 + tid] = 0u;
+                __syncwarp();
+                if (c.lane == 0) {   // masks consumed: clear them for their next use
+                    misc[MISC_ONES + ((t + 1) & 1) * 2 + c.warp] = 0u;
+                    misc[MISC_SYND + ((t + 1) & 1) * 2 + c.warp] = 0u;
+                }
                 if (P.early_term) {
                     const uint32_t nm = __ballot_sync(0xffffffffu, newly);
-                    const uint32_t no = __ballot_sync(0xffffffffu, newly && st_out_one);
-                    const uint32_t fm = __ballot_sync(0xffffffffu, st_frozen);
+                    const uint32_t no = __ballot_sync(0xffffffffu, newly && (st & ST_OUT_ONE));
+                    const uint32_t fm = __ballot_sync(0xffffffffu, (st & ST_FROZEN) != 0u);
                     if (c.lane == 0) {
                         ctrl[CTRL_NEWLY + c.warp] = nm;
                         ctrl[CTRL_NEWONES + c.warp] = no;
@@ -289,7 +308,7 @@ __device__ __forceinline__ void nms_decode_body(const KParams &P) {
             uint32_t ones = 0;
             const bool need_hb = !H2 || P.early_term || t == P.T_run - 1;
             Policy::template vn_phase<false>(P, c, t, need_hb, ones);
-            publish(P, c, MISC_ONES + (t & 1) * 64, ones, H2);
+            publish(P, c, MISC_ONES + (t & 1) * 2, ones, H2);
             __syncthreads();   // B
             if (P.early_term) {
                 const uint32_t nm[2] = {ctrl[CTRL_NEWLY], ctrl[CTRL_NEWLY + 1]};
@@ -306,16 +325,16 @@ __device__ __forceinline__ void nms_decode_body(const KParams &P) {
             // ---------------- syndrome of the last hard decision APP_{T-1}
             const int tl = P.T_run;
             const uint32_t bad = Policy::synd_phase(P, c, tl);
-            publish(P, c, MISC_SYND + (tl & 1) * 64, bad, H2);
+            publish(P, c, MISC_SYND + (tl & 1) * 2, bad, H2);
             __syncthreads();
             if (tid < 64) {
-                const bool fbad = misc[MISC_SYND + (tl & 1) * 64 + tid] != 0u;
-                const bool one = misc[MISC_ONES + ((tl - 1) & 1) * 64 + tid] != 0u;
-                const bool pending = !st_frozen;
+                const bool fbad = (misc[MISC_SYND + (tl & 1) * 2 + c.warp] >> c.lane) & 1u;
+                const bool one = (misc[MISC_ONES + ((tl - 1) & 1) * 2 + c.warp] >> c.lane) & 1u;
+                const bool pending = !(st & ST_FROZEN);
                 if (pending) {
-                    if (!one) st_ever_correct = true;
-                    if (!fbad && !st_synd_ever) { st_synd_ever = true; st_iters = tl; }
-                    st_out_synd_ok = !fbad; st_out_one = one; st_executed = tl;
+                    if (!one) st |= ST_EVER_CORRECT;
+                    if (!fbad && !(st & ST_SYND_EVER)) st = st_set(st, ST_ITERS_SH, tl) | ST_SYND_EVER;
+                    st = st_set(st, ST_EXEC_SH, tl) | (fbad ? 0u : ST_OUT_SYND_OK) | (one ? ST_OUT_ONE : 0u);
                 }
                 const uint32_t nm = __ballot_sync(0xffffffffu, pending);
                 const uint32_t no = __ballot_sync(0xffffffffu, pending && one);
@@ -332,13 +351,15 @@ __device__ __forceinline__ void nms_decode_body(const KParams &P) {
         if (tid < 64) {
             const bool valid = tid < c.nvalid;
             const uint32_t be = misc[MISC_BITERR + tid];
-            const bool uncor_any = !st_ever_correct, uncor_last = st_out_one;
+            const bool uncor_any = !(st & ST_EVER_CORRECT), uncor_last = (st & ST_OUT_ONE) != 0u;
+            const bool st_out_synd_ok = (st & ST_OUT_SYND_OK) != 0u;
+            const int st_executed = st_get(st, ST_EXEC_SH);
             if (valid) {
                 const long long F = c.frame0 + tid;
-                if (P.iters) P.iters[F] = st_iters;
+                if (P.iters) P.iters[F] = st_get(st, ST_ITERS_SH);
                 if (P.flags)
                     P.flags[F] = (uint8_t)((st_out_synd_ok ? 1u : 0u) | (uncor_any ? 2u : 0u) | (uncor_last ? 4u : 0u) |
-                                           (st_synd_ever ? 8u : 0u));
+                                           ((st & ST_SYND_EVER) ? 8u : 0u));
                 if (P.biterr) P.biterr[F] = (int)be;
             }
             bool harvest = false;

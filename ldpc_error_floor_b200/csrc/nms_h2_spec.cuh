@@ -44,11 +44,14 @@ struct H2SpecPolicy {
     static __device__ __forceinline__ void cn_phase(const KParams &P, const Ctx &c, int t, uint32_t &bad) {
         const H2Ctx h = h2_ctx(P, c);
         const uint32_t wcrow = h2_wrow(h, P.h2w_c, t, P.h2_wc), wurow = h2_wrow(h, P.h2w_u, t, P.h2_wu);
+        constexpr int NT = (G::M + G::R - 1) / G::R;
+        const uint2 *task = P.cn_task + c.slot * NT;   // host-built: {row offset in bytes, degree | row index << 16}
 #pragma unroll 1
-        for (int n = c.slot; n < G::M; n += G::R) {
-            const int i = P.cn_order[n];
-            const int e0 = P.row_ptr[i], dc = P.row_ptr[i + 1] - e0;
-            const uint32_t a0 = h.sb + (uint32_t)e0 * LP4 + h.q4;
+        for (int n = 0; n < NT; ++n) {
+            const uint2 tk = task[n];
+            const int dc = (int)(tk.y & 0xffffu), i = (int)(tk.y >> 16);
+            if (dc == 0) break;
+            const uint32_t a0 = h.sb + tk.x + h.q4;
             const float w0 = h2_w(wcrow, i, P.h2_mc), w1 = h2_w(wurow, i, P.h2_mu);
             static_for<0, G::NDEG>([&](auto k) {
                 constexpr int DC = G::cn_degs[decltype(k)::v];
