@@ -294,13 +294,14 @@ def main():
     mcnt = torch.zeros(_lib.NUM_COUNTERS, dtype=torch.int64, device=dev)
     dec.mc_run(sigma, mc_frames, 7, counters=mcnt)
     torch.cuda.synchronize()
-    m0, m1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    m0, m1, m2 = (torch.cuda.Event(enable_timing=True) for _ in range(3))
     m0.record()
     dec.mc_run(sigma, mc_frames, 8, frame_offset=mc_frames, counters=mcnt)
-    dec.mc_run(sigma, mc_frames, 8, frame_offset=2 * mc_frames, early_term=True, counters=mcnt)
     m1.record()
+    dec.mc_run(sigma, mc_frames, 8, frame_offset=2 * mc_frames, early_term=True, counters=mcnt)
+    m2.record()
     torch.cuda.synchronize()
-    mc_ms = m0.elapsed_time(m1)
+    mc_ms, mc_et_ms = m0.elapsed_time(m1), m1.elapsed_time(m2)
 
     if rank != 0:
         if world > 1:
@@ -313,14 +314,29 @@ def main():
     ach = (eu_per_launch / (k_ms / 1e3)) * OPS_PER_EDGE_UPDATE_QMS / 1e12
     sm_now = clocks.get("sm_mhz") or sm_max
     hbm_bytes = B * (NZ * 4 + dec.hard_words * 4 + 4 + 1)
+    # DRAM bytes per launch from the committed `ncu --set full` capture (dram__bytes_read + dram__bytes_write per
+    # frame of the profiled launch, scaled to this launch's frames)
+    traffic, traffic_src, ncu_info = None, None, None
+    tpath = os.path.join(ROOT, "profiles", "traffic.json")
+    if os.path.exists(tpath):
+        tj = json.load(open(tpath))
+        ent = next((v for k, v in tj.items() if dec.kernel_name.startswith(k)), None)   # same bytes for any geometry
+        if ent:
+            traffic = ent["dram_bytes_per_frame"] * B
+            traffic_src = ent["source"]
+            ncu_info = ent.get("ncu")
     roofline = {
         "bound": "alu", "kernel": dec.kernel_name,
         "achieved": ach, "peak": alu_peak, "unit": "Tlaneop/s", "frac": ach / alu_peak,
         "peak_source": f"148 SMs x 128 lanes x clocks.max.sm {sm_max:.0f} MHz (issue-slot roof; MEASURED_PEAKS.json "
                        f"carries no ALU figure)",
         "frac_at_observed_clock": ach / (SM_COUNT * LANES_PER_SM * sm_now * 1e6 / 1e12),
+        "frac_of_packed_roof": ach / (2 * alu_peak) if dec.packed else ach / alu_peak,
+        "note": "peak = scalar lane-op issue roof; the packed fp16x2 kernel does two frames per lane-op, so its own "
+                "roof is 2x peak (frac_of_packed_roof)",
+        "ncu": ncu_info,
         "ops_per_edge_update": OPS_PER_EDGE_UPDATE_QMS, "edge_updates_per_launch": eu_per_launch,
-        "kernel_ms": k_ms, "traffic": None,
+        "kernel_ms": k_ms, "traffic": traffic, "traffic_source": traffic_src,
         "hbm": {"achieved": hbm_bytes / (k_ms / 1e3) / 1e9, "peak": pk["hbm_gbs"], "unit": "GB/s",
                 "frac": hbm_bytes / (k_ms / 1e3) / 1e9 / pk["hbm_gbs"], "peak_source": pk_src,
                 "algorithmic_bytes_per_launch": hbm_bytes},
@@ -341,8 +357,10 @@ def main():
         "gpu_launches": launches, "clocks": clocks, "roofline": roofline,
         "check": {"frames": int(cnt[0]), "frame_err_last": int(cnt[1]), "frame_err_any": int(cnt[2]),
                   "expect": "every word of the set is uncorrectable by construction"},
-        "mc": {"frames": 2 * mc_frames, "ms": mc_ms, "frames_per_s": 2 * mc_frames / (mc_ms / 1e3),
-               "note": f"fused Philox generate+decode at {HARVEST_SNR_DB} dB, half without / half with early stop",
+        "mc": {"frames_per_launch": mc_frames, "frames_per_s": mc_frames / (mc_ms / 1e3),
+               "frames_per_s_early_stop": mc_frames / (mc_et_ms / 1e3),
+               "note": f"fused Philox generate+decode+count at {HARVEST_SNR_DB} dB (ldpc_mc_run), 20 iterations fixed / "
+                       f"with per-frame early termination",
                "fer_any": float(mcnt[2].item()) / float(mcnt[0].item())},
         "geometry": {"packed_fp16x2": dec.packed, "frames_per_cta": dec.frames_per_cta, "ctas_per_sm": dec.ctas_per_sm,
                      "threads_per_cta": dec.threads_per_cta, "smem_bytes": dec.smem_bytes},

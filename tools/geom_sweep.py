@@ -19,7 +19,7 @@ if wkey is None:
 g = L.BaseGraph(proto, z, (int(meta[1]), int(meta[2])), (int(meta[3]), int(meta[4])))
 if wkey:
     ws = L.WeightSet([int(v) for v in d[f"weights/{wkey}/sharing"]], {i: d[f"weights/{wkey}/block{i}"] for i in range(3)})
-    T = None
+    T = int(os.environ.get("SWEEP_ITERS", "20"))
 else:
     ws = L.WeightSet([3, 0, 0], {0: np.full((20, 1), 0.8, np.float32)}); T = 20
 B = int(os.environ.get("SWEEP_FRAMES", 1 << 18))
