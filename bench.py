@@ -122,7 +122,7 @@ def synth_words_cpu(n, N, z, seed=1):
     return np.clip(np.rint(x * 2) / 2, -7.5, 7.5).astype(np.float32)
 
 
-def run_reference(args, rank):
+def run_reference(args, rank, emit=print):
     if rank != 0:
         return
     proto, z, sharing, blocks = load_config()
@@ -156,7 +156,7 @@ def run_reference(args, rank):
                                    f"TensorFlow graph cannot run here (TF not installable)"},
         "e2e": {"value": val, "unit": "Gbit/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     }
-    print(json.dumps(line))
+    emit(json.dumps(line))
 
 
 def harvest_uncorrected(dec, g, sigma, want, torch):
@@ -176,7 +176,21 @@ def harvest_uncorrected(dec, g, sigma, want, torch):
     return buf[:n].clone(), cnt.cpu().numpy(), offset
 
 
+def _claim_stdout():
+    """Keep stdout clean for the ONE JSON line: anything libraries print to fd 1 meanwhile (NCCL's version
+    banner, torchrun notices) goes to stderr; returns a writer for the real stdout."""
+    sys.stdout.flush()
+    real = os.dup(1)
+    os.dup2(2, 1)
+    sys.stdout = os.fdopen(os.dup(2), "w", buffering=1)
+
+    def emit(text):
+        os.write(real, (text + "\n").encode())
+    return emit
+
+
 def main():
+    emit = _claim_stdout()
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=20)
@@ -192,7 +206,7 @@ def main():
     world = int(os.environ.get("WORLD_SIZE", "1"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
     if args.impl == "reference":
-        run_reference(args, rank)
+        run_reference(args, rank, emit)
         return
 
     import torch
@@ -372,7 +386,7 @@ def main():
                                 "frames_per_s": cfps,
                                 "sample": f"{n} of the same uncorrected words, {dt:.1f} s, oracle/nms_oracle.c (C port "
                                           f"of the reference arithmetic, OpenMP over frames)"}
-    print(json.dumps(line))
+    emit(json.dumps(line))
     if world > 1:
         dist.destroy_process_group()
 

@@ -166,7 +166,7 @@ class MonteCarlo:
             if ubuf is not None:
                 n = min(int(self._to_numpy(ucnt)[0]), max_uncor)
                 rows = self._rows(ubuf, n)
-            rows = _all_gather_rows(rows, self.dec.device, self.group)
+            rows = _all_gather_rows(rows, self.dec.device, self.group)[:max_uncor]   # the cap is global, not per rank
         pt.seconds = time.time() - t0
         return pt, rows
 
