@@ -303,6 +303,23 @@ def main():
     h2d = Be * NZ * 4
     d2h = Be * (dec.hard_words * 4 + 4 + 1 + 4)
 
+    # ---- the same end-to-end leg on the compact int8 form of the same words (ldpc_decode_q8_host, N2)
+    q8_host = torch.empty((Be, NZ), dtype=torch.int8).pin_memory()
+    q8_host.copy_(torch.round(host_llr / dec.q8_step).to(torch.int8))
+    for _ in range(2):
+        dec.decode_q8_host(q8_host)
+    sync_all()
+    tq0 = time.perf_counter()
+    for _ in range(e_steps):
+        hq = dec.decode_q8_host(q8_host)
+    torch.cuda.synchronize()
+    tq = time.perf_counter() - tq0
+    ttq = torch.tensor([tq], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(ttq, op=dist.ReduceOp.MAX)
+    e2e_q8_fps = world * Be * e_steps / float(ttq.item())
+    q8_same = bool(np.array_equal(hq["flags"], he["flags"]) and np.array_equal(hq["hard_packed"], he["hard_packed"]))
+
     # ---- secondary: fused Monte-Carlo (in-kernel Philox LLRs, counters only), same decoder
     mc_frames = 1 << 21
     mcnt = torch.zeros(_lib.NUM_COUNTERS, dtype=torch.int64, device=dev)
@@ -368,6 +385,9 @@ def main():
         "frames_per_s": fps, "edge_updates_per_s": fps * E * z * T,
         "e2e": {"value": e2e_fps * k_info / 1e9, "unit": "Gbit/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                 "frames_per_s": e2e_fps, "frames_per_step_per_gpu": Be, "api": "ldpc_decode_host (pinned host buffers)"},
+        "e2e_q8": {"value": e2e_q8_fps * k_info / 1e9, "unit": "Gbit/s", "h2d_bytes_per_step": Be * NZ,
+                   "d2h_bytes_per_step": d2h, "frames_per_s": e2e_q8_fps, "same_results_as_f32": q8_same,
+                   "api": "ldpc_decode_q8_host: the same words as int8 multiples of the quantiser step (pinned host)"},
         "gpu_launches": launches, "clocks": clocks, "roofline": roofline,
         "check": {"frames": int(cnt[0]), "frame_err_last": int(cnt[1]), "frame_err_any": int(cnt[2]),
                   "expect": "every word of the set is uncorrectable by construction"},

@@ -142,6 +142,22 @@ int ldpc_decode_host(const ldpc_decoder_t *d, const float *llr_host, int64_t B, 
                      uint32_t *hard_host, int32_t *iters_host, uint8_t *flags_host,
                      int32_t *biterr_host);
 
+/* ---- compact (int8) words ---------------------------------------------------------------
+ * On the quantised path every decoder input of Print_Functions.create_mix_epoch (:49-50) and every
+ * row of an Inputs/[Uncor]_* file (:120-126, '%.1f' of values on the 0.5 grid) is a small multiple of
+ * the quantiser step, so a word fits in N*z int8: llr = q * step.  step = 0 selects the decoder's
+ * own quantiser step (ldpc_decoder_q8_step: 0.5 for q_bit 5, 1 for 6/-5/4, 2 for 3; float decoders
+ * need an explicit step).  Same outputs as ldpc_decode (no APP), plus optional accumulated
+ * counters_dev (u64[LDPC_NUM_COUNTERS]).  A quarter of the bytes of the float32 form over PCIe / HBM;
+ * formats.py keeps the matching binary sidecar of the text files ("next" row N2 of SURVEY.md 8f). */
+float ldpc_decoder_q8_step(const ldpc_decoder_t *d);
+int ldpc_decode_q8(const ldpc_decoder_t *d, const int8_t *llr_q8_dev, float step, int64_t B, int32_t iters,
+                   int32_t early_term, uint32_t *hard_dev, int32_t *iters_dev, uint8_t *flags_dev,
+                   int32_t *biterr_dev, uint64_t *counters_dev, void *stream);
+int ldpc_decode_q8_host(const ldpc_decoder_t *d, const int8_t *llr_q8_host, float step, int64_t B,
+                        int32_t iters, int32_t early_term, uint32_t *hard_host, int32_t *iters_host,
+                        uint8_t *flags_host, int32_t *biterr_host);
+
 /* ---- channel-sample generator ----------------------------------------------------------
  * Replaces Print_Functions.create_mix_epoch (:29-72) for the all-zero codeword:
  * llr = 2*(sigma*n - 1)/sigma^2, n ~ N(0,1) from Philox4x32-10 (key = seed, counter =

@@ -527,21 +527,49 @@ extern "C" int ldpc_decoder_geometry(const ldpc_decoder_t *d, int32_t *frames_pe
 }
 
 // ----------------------------------------------------------------------------------- decode
-extern "C" int ldpc_decode(const ldpc_decoder_t *d, const float *llr_dev, int64_t B, int32_t iters, int32_t early_term,
-                           float *app_dev, int32_t app_all_iters, uint32_t *hard_dev, int32_t *iters_dev,
-                           uint8_t *flags_dev, int32_t *biterr_dev, void *stream) {
-    if (!d || (!llr_dev && B > 0) || B < 0) return fail(LDPC_E_INVALID, "decode: bad arguments");
+namespace {
+float quantiser_step(const ldpc_decoder *d) {   // 1/qk of Main_Functions.py:483-492; 0 for the float decoders
+    if (d->decoding_type != 2) return 0.0f;
+    return d->q_bit == 5 ? 0.5f : (d->q_bit == 3 ? 2.0f : 1.0f);
+}
+
+int decode_dev(const ldpc_decoder *d, const float *llr_dev, const int8_t *llr_q8_dev, float step, int64_t B,
+               int32_t iters, int32_t early_term, float *app_dev, int32_t app_all_iters, uint32_t *hard_dev,
+               int32_t *iters_dev, uint8_t *flags_dev, int32_t *biterr_dev, uint64_t *counters_dev, void *stream) {
+    if (!d || (!llr_dev && !llr_q8_dev && B > 0) || B < 0) return fail(LDPC_E_INVALID, "decode: bad arguments");
     if (iters < 0 || iters > d->T) return fail(LDPC_E_INVALID, "decode: iters %d outside 0..%d", iters, d->T);
+    if (llr_q8_dev && !(step > 0.0f)) return fail(LDPC_E_INVALID, "decode_q8: step must be positive for a float decoder");
     if (B == 0) return LDPC_OK;
     DeviceGuard guard(d->device);
     if (!guard.ok) return fail(LDPC_E_CUDA, "cudaSetDevice(%d) failed", d->device);
     KParams P = d->base;
     P.T_run = iters == 0 ? d->T : iters;
     P.early_term = early_term ? 1 : 0;
-    P.llr = llr_dev; P.n_frames = B;
+    P.llr = llr_dev; P.llr_q8 = (const signed char *)llr_q8_dev; P.q8_step = step; P.n_frames = B;
     P.app = app_dev; P.app_all = app_all_iters ? 1 : 0; P.app_stride_t = (long long)B * P.NZ;
     P.hard = hard_dev; P.iters = iters_dev; P.flags = flags_dev; P.biterr = biterr_dev;
+    P.counters = (unsigned long long *)counters_dev;
     return launch(d, P, (cudaStream_t)stream);
+}
+}   // namespace
+
+extern "C" int ldpc_decode(const ldpc_decoder_t *d, const float *llr_dev, int64_t B, int32_t iters, int32_t early_term,
+                           float *app_dev, int32_t app_all_iters, uint32_t *hard_dev, int32_t *iters_dev,
+                           uint8_t *flags_dev, int32_t *biterr_dev, void *stream) {
+    if (!llr_dev && B > 0) return fail(LDPC_E_INVALID, "decode: bad arguments");
+    return decode_dev(d, llr_dev, nullptr, 0.0f, B, iters, early_term, app_dev, app_all_iters, hard_dev, iters_dev,
+                      flags_dev, biterr_dev, nullptr, stream);
+}
+
+extern "C" float ldpc_decoder_q8_step(const ldpc_decoder_t *d) { return d ? quantiser_step(d) : 0.0f; }
+
+extern "C" int ldpc_decode_q8(const ldpc_decoder_t *d, const int8_t *llr_q8_dev, float step, int64_t B, int32_t iters,
+                              int32_t early_term, uint32_t *hard_dev, int32_t *iters_dev, uint8_t *flags_dev,
+                              int32_t *biterr_dev, uint64_t *counters_dev, void *stream) {
+    if (!d || (!llr_q8_dev && B > 0)) return fail(LDPC_E_INVALID, "decode_q8: bad arguments");
+    if (step == 0.0f) step = quantiser_step(d);
+    return decode_dev(d, nullptr, llr_q8_dev, step, B, iters, early_term, nullptr, 0, hard_dev, iters_dev, flags_dev,
+                      biterr_dev, counters_dev, stream);
 }
 
 namespace {
@@ -571,11 +599,16 @@ int ensure_host_scratch(ldpc_decoder *d, size_t chunk, bool with_app, int app_it
 }
 }   // namespace
 
-extern "C" int ldpc_decode_host(const ldpc_decoder_t *dc, const float *llr_host, int64_t B, int32_t iters,
-                                int32_t early_term, float *app_host, int32_t app_all_iters, uint32_t *hard_host,
-                                int32_t *iters_host, uint8_t *flags_host, int32_t *biterr_host) {
+namespace {
+int decode_host_impl(const ldpc_decoder_t *dc, const void *src_host, bool q8, float step, int64_t B, int32_t iters,
+                     int32_t early_term, float *app_host, int32_t app_all_iters, uint32_t *hard_host,
+                     int32_t *iters_host, uint8_t *flags_host, int32_t *biterr_host) {
     ldpc_decoder *d = const_cast<ldpc_decoder *>(dc);
+    const float *llr_host = (const float *)src_host;
+    const size_t elem = q8 ? 1 : sizeof(float);
     if (!d || (!llr_host && B > 0) || B < 0) return fail(LDPC_E_INVALID, "decode_host: bad arguments");
+    if (q8 && step == 0.0f) step = quantiser_step(d);
+    if (q8 && !(step > 0.0f)) return fail(LDPC_E_INVALID, "decode_q8_host: step must be positive for a float decoder");
     if (iters < 0 || iters > d->T) return fail(LDPC_E_INVALID, "decode_host: iters %d outside 0..%d", iters, d->T);
     if (B == 0) return LDPC_OK;
     DeviceGuard guard(d->device);
@@ -613,11 +646,12 @@ extern "C" int ldpc_decode_host(const ldpc_decoder_t *dc, const float *llr_host,
         cudaStream_t st = h.st[k];
         rc = drain(k);
         if (rc != LDPC_OK) return rc;
-        CUDA_TRY(cudaMemcpyAsync(h.llr[k], llr_host + off * P0.NZ, (size_t)nb * P0.NZ * sizeof(float),
+        CUDA_TRY(cudaMemcpyAsync(h.llr[k], (const char *)src_host + (size_t)off * P0.NZ * elem, (size_t)nb * P0.NZ * elem,
                                  cudaMemcpyHostToDevice, st));
         KParams P = P0;
         P.T_run = T_run; P.early_term = early_term ? 1 : 0;
-        P.llr = h.llr[k]; P.n_frames = nb;
+        P.llr = q8 ? nullptr : h.llr[k]; P.llr_q8 = q8 ? (const signed char *)h.llr[k] : nullptr; P.q8_step = step;
+        P.n_frames = nb;
         P.app = app_iters ? h.app[k] : nullptr; P.app_all = app_all_iters ? 1 : 0; P.app_stride_t = (long long)nb * P.NZ;
         P.hard = hard_host ? h.hard[k] : nullptr; P.iters = iters_host ? h.iters[k] : nullptr;
         P.flags = flags_host ? h.flags[k] : nullptr; P.biterr = biterr_host ? h.biterr[k] : nullptr;
@@ -637,6 +671,21 @@ extern "C" int ldpc_decode_host(const ldpc_decoder_t *dc, const float *llr_host,
     rc = drain(k);          // older chunk first, so the caller's arrays fill in order
     if (rc != LDPC_OK) return rc;
     return drain(k ^ 1);
+}
+}   // namespace
+
+extern "C" int ldpc_decode_host(const ldpc_decoder_t *d, const float *llr_host, int64_t B, int32_t iters,
+                                int32_t early_term, float *app_host, int32_t app_all_iters, uint32_t *hard_host,
+                                int32_t *iters_host, uint8_t *flags_host, int32_t *biterr_host) {
+    return decode_host_impl(d, llr_host, false, 0.0f, B, iters, early_term, app_host, app_all_iters, hard_host,
+                            iters_host, flags_host, biterr_host);
+}
+
+extern "C" int ldpc_decode_q8_host(const ldpc_decoder_t *d, const int8_t *llr_q8_host, float step, int64_t B,
+                                   int32_t iters, int32_t early_term, uint32_t *hard_host, int32_t *iters_host,
+                                   uint8_t *flags_host, int32_t *biterr_host) {
+    return decode_host_impl(d, llr_q8_host, true, step, B, iters, early_term, nullptr, 0, hard_host, iters_host,
+                            flags_host, biterr_host);
 }
 
 // ------------------------------------------------------------------- generator / Monte-Carlo

@@ -222,13 +222,16 @@ __device__ __forceinline__ void nms_decode_body(const KParams &P) {
 
         // ---------------- load channel LLRs into xa (zero for padding frames)
         bool fused = false;   // graph-specialised kernels load global LLRs inside their unrolled init pass
-        if constexpr (Policy::FUSED_LOAD) fused = P.llr != nullptr;
+        const bool from_global = P.llr != nullptr || P.llr_q8 != nullptr;
+        if constexpr (Policy::FUSED_LOAD) fused = from_global;
         if (fused) {
-        } else if (P.llr != nullptr) {
+        } else if (from_global) {
             const int tot = P.FB * P.NZ;
             for (int idx = tid; idx < tot; idx += blockDim.x) {
                 const int f = idx / P.NZ, k = idx - f * P.NZ;
-                const float v = f < c.nvalid ? __ldg(P.llr + (c.frame0 + f) * (long long)P.NZ + k) : 0.0f;
+                const long long g = (c.frame0 + f) * (long long)P.NZ + k;
+                float v = 0.0f;
+                if (f < c.nvalid) v = P.llr != nullptr ? __ldg(P.llr + g) : (float)__ldg(P.llr_q8 + g) * P.q8_step;
                 store_xa<H2>(P, f, k, v);
             }
         } else {

@@ -135,14 +135,24 @@ struct H2SpecPolicy {
         if constexpr (MODE == VN_INIT_GLOBAL) {
             // this lane's two frames: all of the slot's loads are issued before the first use
             const bool v0 = c.act && c.f0 < c.nvalid, v1 = c.act && c.f1 < c.nvalid;
-            const float *p0 = P.llr + (c.frame0 + (v0 ? c.f0 : 0)) * (long long)P.NZ + c.a_lane;
-            const float *p1 = P.llr + (c.frame0 + (v1 ? c.f1 : 0)) * (long long)P.NZ + c.a_lane;
+            const long long o0 = (c.frame0 + (v0 ? c.f0 : 0)) * (long long)P.NZ + c.a_lane;
+            const long long o1 = (c.frame0 + (v1 ? c.f1 : 0)) * (long long)P.NZ + c.a_lane;
             float2 x[NT];
-            static_for<0, NT>([&](auto n) {
-                constexpr int J = G::vn_order[SLOT + decltype(n)::v * G::R];
-                x[decltype(n)::v].x = v0 ? __ldg(p0 + J * G::z) : 0.0f;
-                x[decltype(n)::v].y = v1 ? __ldg(p1 + J * G::z) : 0.0f;
-            });
+            if (P.llr != nullptr) {
+                const float *p0 = P.llr + o0, *p1 = P.llr + o1;
+                static_for<0, NT>([&](auto n) {
+                    constexpr int J = G::vn_order[SLOT + decltype(n)::v * G::R];
+                    x[decltype(n)::v].x = v0 ? __ldg(p0 + J * G::z) : 0.0f;
+                    x[decltype(n)::v].y = v1 ? __ldg(p1 + J * G::z) : 0.0f;
+                });
+            } else {   // int8 words in units of q8_step
+                const signed char *p0 = P.llr_q8 + o0, *p1 = P.llr_q8 + o1;
+                static_for<0, NT>([&](auto n) {
+                    constexpr int J = G::vn_order[SLOT + decltype(n)::v * G::R];
+                    x[decltype(n)::v].x = v0 ? (float)__ldg(p0 + J * G::z) * P.q8_step : 0.0f;
+                    x[decltype(n)::v].y = v1 ? (float)__ldg(p1 + J * G::z) * P.q8_step : 0.0f;
+                });
+            }
             static_for<0, NT>([&](auto n) {
                 constexpr int J = G::vn_order[SLOT + decltype(n)::v * G::R];
                 vn_col<J, MODE, VNW, HB>(P, h, wvrow, hbrow, x[decltype(n)::v], ones);

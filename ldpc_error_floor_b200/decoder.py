@@ -202,6 +202,52 @@ class NMSDecoder:
             it.ctypes.data, fl.ctypes.data, be.ctypes.data))
         return {"hard_packed": hard, "iters": it, "flags": fl, "biterr": be, "app": app_a}
 
+    # -------------------------------------------------------------- compact int8 words (N2)
+    @property
+    def q8_step(self) -> float:
+        """LLR units of one int8 count: the quantiser step of this decoder (0.0 for float decoders)."""
+        return float(_lib.load().ldpc_decoder_q8_step(self._h))
+
+    def decode_q8(self, words: torch.Tensor, iters: int = 0, early_term: bool = False, step: float = 0.0,
+                  counters: Optional[torch.Tensor] = None) -> DecodeResult:
+        """words: CUDA int8 [B, N*z], llr = words * step (step 0 = the quantiser step).  Same outputs as
+        decode() without APP; `counters` (int64[8], accumulated) as in mc_run."""
+        g = self.graph
+        if not words.is_cuda or words.dtype != torch.int8:
+            raise ValueError("decode_q8: words must be a CUDA int8 tensor")
+        B = words.shape[0]
+        if words.numel() != B * g.NZ:
+            raise ValueError(f"decode_q8: {words.numel()} elements, expected {B}x{g.NZ}")
+        words = words.contiguous()
+        dev = self.device
+        hard = torch.empty((B, self.hard_words), dtype=torch.int32, device=dev)
+        it = torch.empty((B,), dtype=torch.int32, device=dev)
+        fl = torch.empty((B,), dtype=torch.uint8, device=dev)
+        be = torch.empty((B,), dtype=torch.int32, device=dev)
+        stream = torch.cuda.current_stream(dev).cuda_stream
+        _lib.check(_lib.load().ldpc_decode_q8(self._h, _ptr(words), float(step), B, int(iters), 1 if early_term else 0,
+                                              _ptr(hard), _ptr(it), _ptr(fl), _ptr(be), _ptr(counters),
+                                              ctypes.c_void_p(stream)))
+        return DecodeResult(None, hard, it, fl, be, None)
+
+    def decode_q8_host(self, words, iters: int = 0, early_term: bool = False, step: float = 0.0) -> Dict:
+        """End-to-end call on host int8 words (numpy or CPU tensor, pinned or not); results in numpy arrays."""
+        g = self.graph
+        arr = words.contiguous().numpy() if isinstance(words, torch.Tensor) else np.ascontiguousarray(words)
+        if arr.dtype != np.int8:
+            raise ValueError("decode_q8_host takes int8 words")
+        B = arr.shape[0]
+        if arr.size != B * g.NZ:
+            raise ValueError(f"decode_q8_host: {arr.size} elements, expected {B}x{g.NZ}")
+        hard = np.empty((B, self.hard_words), dtype=np.uint32)
+        it = np.empty((B,), dtype=np.int32)
+        fl = np.empty((B,), dtype=np.uint8)
+        be = np.empty((B,), dtype=np.int32)
+        _lib.check(_lib.load().ldpc_decode_q8_host(self._h, arr.ctypes.data, float(step), B, int(iters),
+                                                   1 if early_term else 0, hard.ctypes.data, it.ctypes.data,
+                                                   fl.ctypes.data, be.ctypes.data))
+        return {"hard_packed": hard, "iters": it, "flags": fl, "biterr": be, "app": None}
+
     # --------------------------------------------------------------------- generator / MC / post
     def generate(self, sigma: float, n_frames: int, seed: int, frame_offset: int = 0) -> torch.Tensor:
         """BPSK/AWGN LLRs of the all-zero codeword, CUDA float32 [n_frames, N, z]

@@ -180,3 +180,89 @@ def uncor_filenames(filename: str) -> Tuple[str, str, str]:
     """Inputs/[Uncor]_{filename}{,_Valid,_Test}.txt (Main_Functions.py:529,543,559)."""
     base = f"./Inputs/[Uncor]_{filename}"
     return base + ".txt", base + "_Valid.txt", base + "_Test.txt"
+
+
+# ------------------------------------------ F3b  binary sidecar of the uncorrected-word sets ("next" row N2)
+# The text format costs ~6 bytes and a float parse per value; at 10^6 words it is the bottleneck.  On the
+# quantised path every stored value is a small multiple of the quantiser step, so a word is N*z int8.
+# Layout (little endian): magic "LDPCQ8\0\1", u32 version, u32 words-per-row (N*z), u64 rows, f32 step,
+# f32 Eb/N0 in dB at which the words were harvested (NaN = unknown; the text format cannot record it),
+# u64 Philox seed, 24 reserved bytes (64-byte header); then rows * N*z int8 = DECODER-INPUT LLR / step
+# (log p1/p0: NOT negated, unlike the text file).
+
+_Q8_MAGIC = b"LDPCQ8\x00\x01"
+_Q8_HEADER = 64
+
+
+def llr_to_q8(llr: np.ndarray, step: float = 0.5) -> np.ndarray:
+    """Decoder-input LLRs -> int8 counts; raises if a value is off the grid or out of range."""
+    llr = np.asarray(llr, dtype=np.float32)
+    q = llr.reshape(llr.shape[0], -1) / np.float32(step)
+    r = np.rint(q)
+    if not np.array_equal(q, r) or np.abs(r).max(initial=0) > 127:
+        raise ValueError("LLRs are not int8 multiples of the step")
+    return r.astype(np.int8)
+
+
+def q8_to_llr(words: np.ndarray, step: float = 0.5) -> np.ndarray:
+    return np.asarray(words, dtype=np.int8).astype(np.float32) * np.float32(step)
+
+
+def write_uncor_q8(path: str, words: np.ndarray, step: float = 0.5, snr_db: float = float("nan"), seed: int = 0,
+                   append: bool = False) -> int:
+    """Write / append int8 words [n, N*z] (decoder-input sign convention)."""
+    import struct
+    words = np.ascontiguousarray(np.asarray(words, dtype=np.int8))
+    n, width = words.shape
+    if append and os.path.exists(path):
+        with open(path, "r+b") as fh:
+            head = fh.read(_Q8_HEADER)
+            if head[:8] != _Q8_MAGIC:
+                raise ValueError(f"{path}: not an LDPCQ8 file")
+            _, w0, rows = struct.unpack_from("<IIQ", head, 8)
+            if w0 != width:
+                raise ValueError(f"{path}: row width {w0} != {width}")
+            fh.seek(0, os.SEEK_END)
+            fh.write(words.tobytes())
+            fh.seek(16)
+            fh.write(struct.pack("<Q", rows + n))
+        return rows + n
+    head = _Q8_MAGIC + struct.pack("<IIQffQ", 1, width, n, step, snr_db, seed & (2 ** 64 - 1))
+    with open(path, "wb") as fh:
+        fh.write(head.ljust(_Q8_HEADER, b"\0"))
+        fh.write(words.tobytes())
+    return n
+
+
+def read_uncor_q8(path: str, limit: Optional[int] = None, offset: int = 0):
+    """Returns (int8 [n, N*z] memory-mapped, meta dict(step, snr_db, seed, rows))."""
+    import struct
+    with open(path, "rb") as fh:
+        head = fh.read(_Q8_HEADER)
+    if head[:8] != _Q8_MAGIC:
+        raise ValueError(f"{path}: not an LDPCQ8 file")
+    version, width, rows, step, snr_db, seed = struct.unpack_from("<IIQffQ", head, 8)
+    if version != 1:
+        raise ValueError(f"{path}: version {version}")
+    n = rows - offset if limit is None else limit
+    if offset + n > rows:
+        raise ValueError(f"{path}: {rows} rows < requested {offset + n}")
+    data = np.memmap(path, dtype=np.int8, mode="r", offset=_Q8_HEADER + offset * width, shape=(n, width))
+    return data, {"step": step, "snr_db": snr_db, "seed": seed, "rows": rows}
+
+
+def uncor_text_to_q8(text_path: str, q8_path: str, step: float = 0.5, snr_db: float = float("nan"), dedup: bool = False) -> int:
+    """Inputs/[Uncor]_*.txt -> sidecar.  The text rows are negated LLRs (Print_Functions.py:124); the sidecar holds
+    decoder inputs.  dedup drops repeated words (keeps the first occurrence, order preserved)."""
+    rows = read_uncor(text_path)
+    words = llr_to_q8(-rows, step)
+    if dedup:
+        _, first = np.unique(words, axis=0, return_index=True)
+        words = words[np.sort(first)]
+    return write_uncor_q8(q8_path, words, step, snr_db)
+
+
+def uncor_q8_to_text(q8_path: str, text_path: str) -> int:
+    """Sidecar -> the reference's text format (appends, like write_uncor_file)."""
+    words, meta = read_uncor_q8(q8_path)
+    return append_uncor(text_path, q8_to_llr(words, meta["step"]))

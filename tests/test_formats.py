@@ -139,3 +139,33 @@ def test_uncor_matches_reference_writer():
         p = os.path.join(tmp, "Uncor.txt")
         formats.append_uncor(p, llr)
         assert open(p).read() == text                           # byte-identical, "-0.0" included
+
+
+def test_uncor_q8_sidecar_round_trip(tmp_path):
+    """N2: int8 binary sidecar of the Inputs/[Uncor] text format -- exact on the quantiser grid (the sign of a
+    zero, which the '%.1f' text keeps as '-0.0' / '0.0', is the one thing it drops; the decoder ignores it)."""
+    from ldpc_error_floor_b200 import formats as F
+    rng = np.random.RandomState(0)
+    llr = np.clip(np.rint(rng.normal(-3, 3, (50, 576)) * 2) / 2, -7.5, 7.5).astype(np.float32)
+    llr[7] = llr[3]
+    txt, q8 = str(tmp_path / "u.txt"), str(tmp_path / "u.q8")
+    F.append_uncor(txt, llr)
+    assert F.uncor_text_to_q8(txt, q8, snr_db=3.5) == 50
+    w, meta = F.read_uncor_q8(q8)
+    assert w.dtype == np.int8 and w.shape == (50, 576)
+    assert meta == {"step": 0.5, "snr_db": 3.5, "seed": 0, "rows": 50}
+    assert np.array_equal(F.q8_to_llr(w, 0.5), llr)
+    assert os.path.getsize(q8) == 64 + 50 * 576 and os.path.getsize(txt) > 4 * os.path.getsize(q8)
+    assert F.write_uncor_q8(q8, w[:5], append=True) == 55
+    w2, m2 = F.read_uncor_q8(q8)
+    assert m2["rows"] == 55 and np.array_equal(w2[50:], w[:5])
+    part, _ = F.read_uncor_q8(q8, limit=10, offset=20)
+    assert np.array_equal(part, w[20:30])
+    assert F.uncor_text_to_q8(txt, str(tmp_path / "d.q8"), dedup=True) == 49
+    back = str(tmp_path / "back.txt")
+    F.uncor_q8_to_text(q8, back)
+    assert np.array_equal(F.read_uncor(back)[:50], F.read_uncor(txt))       # numerically identical rows
+    with pytest.raises(ValueError):
+        F.llr_to_q8(np.array([[0.25]], np.float32), 0.5)                     # off the grid
+    with pytest.raises(ValueError):
+        F.read_uncor_q8(txt)                                                  # not a sidecar

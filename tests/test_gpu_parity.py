@@ -130,3 +130,31 @@ def test_against_c_oracle_large(name, B):
     h = dec.decode_host(xa, app=None)
     assert np.array_equal(h["hard_packed"].view(np.int32), r.hard_packed.cpu().numpy())
     assert np.array_equal(h["flags"], r.flags.cpu().numpy())
+
+
+@pytest.mark.parametrize("name", ["wimax_qms_333_t20", "5g_r050_z64_qms_222_t50", "mackay_qms_300_t20", "polar_qms_223_t6"])
+def test_q8_words_decode_like_float_words(name):
+    """ldpc_decode_q8 / ldpc_decode_q8_host on int8 words == ldpc_decode on the same words as float32."""
+    import torch
+    import ldpc_error_floor_b200 as L
+    from ldpc_error_floor_b200 import formats as F
+    case = load_case(name)
+    g = L.BaseGraph(case["proto"], case["z"], case["punct"], case["short"])
+    dec = L.NMSDecoder(g, L.WeightSet(case["sharing"], dict(case["weights"])), iters=case["T"], decoding_type=2,
+                       q_bit=case["q_bit"], clip_llr=case["clip"])
+    assert dec.q8_step == 0.5
+    x = dec.generate(float(g.sigma([2.5])[0]), 1500, seed=11).reshape(1500, -1)
+    x = torch.clamp(x, -7.5, 7.5)                         # shortened bits are -clip_LLR = -20: Q() clamps them anyway
+    words = torch.from_numpy(F.llr_to_q8(x.cpu().numpy(), 0.5)).cuda()
+    for et in (False, True):
+        a = dec.decode(x, early_term=et)
+        cnt = torch.zeros(8, dtype=torch.int64, device="cuda")
+        b = dec.decode_q8(words, early_term=et, counters=cnt)
+        h = dec.decode_q8_host(words.cpu().numpy(), early_term=et)
+        for r in (b,):
+            assert torch.equal(a.hard_packed, r.hard_packed) and torch.equal(a.iters, r.iters)
+            assert torch.equal(a.flags, r.flags) and torch.equal(a.biterr, r.biterr)
+        assert np.array_equal(h["hard_packed"].view(np.int32), a.hard_packed.cpu().numpy())
+        assert np.array_equal(h["flags"], a.flags.cpu().numpy()) and np.array_equal(h["iters"], a.iters.cpu().numpy())
+        c = cnt.cpu().numpy()
+        assert c[0] == 1500 and c[3] == int(a.biterr.sum().item()) and c[2] == int(((a.flags & 2) != 0).sum().item())
