@@ -107,6 +107,16 @@ int ldpc_decoder_create(const ldpc_graph_t *g, const int32_t sharing[3], int32_t
                         const float *w_cn, const float *w_ucn, const float *w_vn,
                         int32_t decoding_type, int32_t q_bit, float clip_llr, int32_t device,
                         ldpc_decoder_t **out);
+/* Same with the `systematic` switch of main_Base.py:29, 83-86: target_node > 0 restricts the error metrics
+ * (LDPC_FLAG_UNCOR_*, biterr, the FER/BER counters) to the first target_node proto columns, which is what
+ * ya_output_all / calc_ber_fer see when systematic = 1 (Main_Functions.py:329-335, Print_Functions.py:101-107);
+ * 0 = all N columns.  Syndrome flags and hard-decision outputs always cover the whole word.
+ * Sharing code 4 (temporal sharing of per-edge CN weights, Main_Functions.py:299-304) is accepted for
+ * sharing[0] with the T expanded rows print_weight writes (Print_Functions.py:87-94). */
+int ldpc_decoder_create2(const ldpc_graph_t *g, const int32_t sharing[3], int32_t T,
+                         const float *w_cn, const float *w_ucn, const float *w_vn,
+                         int32_t decoding_type, int32_t q_bit, float clip_llr, int32_t device,
+                         int32_t target_node, ldpc_decoder_t **out);
 int ldpc_decoder_destroy(ldpc_decoder_t *d);
 /* 1 if the packed-fp16x2 kernel serves this decoder, 0 if the float32 kernel does */
 int ldpc_decoder_uses_packed_kernel(const ldpc_decoder_t *d);

@@ -49,6 +49,8 @@ SYMBOLS = {
     "ldpc_graph_sigma": (ctypes.c_int, [_P, _P, _I32, _I32, _P]),
     "ldpc_decoder_create": (ctypes.c_int, [_P, _P, _I32, _P, _P, _P, _I32, _I32, ctypes.c_float, _I32,
                                            ctypes.POINTER(_P)]),
+    "ldpc_decoder_create2": (ctypes.c_int, [_P, _P, _I32, _P, _P, _P, _I32, _I32, ctypes.c_float, _I32, _I32,
+                                            ctypes.POINTER(_P)]),
     "ldpc_decoder_destroy": (ctypes.c_int, [_P]),
     "ldpc_decoder_uses_packed_kernel": (ctypes.c_int, [_P]),
     "ldpc_decoder_kernel_name": (ctypes.c_char_p, [_P]),

@@ -327,14 +327,25 @@ int launch(const ldpc_decoder *d, const KParams &P, cudaStream_t st) {
 extern "C" int ldpc_decoder_create(const ldpc_graph_t *g, const int32_t sharing[3], int32_t T, const float *w_cn,
                                    const float *w_ucn, const float *w_vn, int32_t decoding_type, int32_t q_bit,
                                    float clip_llr, int32_t device, ldpc_decoder_t **out) {
-    if (!g || !sharing || !out || T <= 0 || T > LDPC_MAX_T) return fail(LDPC_E_INVALID, "decoder_create: bad arguments");
+    return ldpc_decoder_create2(g, sharing, T, w_cn, w_ucn, w_vn, decoding_type, q_bit, clip_llr, device, 0, out);
+}
+
+extern "C" int ldpc_decoder_create2(const ldpc_graph_t *g, const int32_t sharing_in[3], int32_t T, const float *w_cn,
+                                    const float *w_ucn, const float *w_vn, int32_t decoding_type, int32_t q_bit,
+                                    float clip_llr, int32_t device, int32_t target_node, ldpc_decoder_t **out) {
+    if (!g || !sharing_in || !out || T <= 0 || T > LDPC_MAX_T) return fail(LDPC_E_INVALID, "decoder_create: bad arguments");
+    if (target_node < 0 || target_node > g->N) return fail(LDPC_E_INVALID, "target_node %d outside 0..%d", target_node, g->N);
     // check_params (Main_Functions.py:507-521)
     for (int i = 0; i < 3; ++i)
-        if (sharing[i] < 0 || sharing[i] > 3)
-            return fail(LDPC_E_UNSUPPORTED, "sharing code %d (temporal sharing 4/5 is not on the decode path)", sharing[i]);
-    if (sharing[2] == 1) return fail(LDPC_E_INVALID, "sharing[2] in [1,4] (Main_Functions.py:515-517)");
-    if (sharing[1] != 0 && sharing[1] != sharing[0])
+        if (sharing_in[i] < 0 || sharing_in[i] > 4)
+            return fail(LDPC_E_UNSUPPORTED, "sharing code %d (code 5 has no branch in build_neural_network)", sharing_in[i]);
+    if (sharing_in[2] == 1 || sharing_in[2] == 4) return fail(LDPC_E_INVALID, "sharing[2] in [1,4] (Main_Functions.py:515-517)");
+    if (sharing_in[1] != 0 && sharing_in[1] != sharing_in[0])
         return fail(LDPC_E_INVALID, "sharing[1] != 0 and sharing[0] != sharing[1] (Main_Functions.py:519-521)");
+    // temporal sharing (code 4): the caller passes the T expanded rows (what print_weight writes, Print_Functions.py:
+    // 87-94), which makes it per-edge sharing; its UCN twin has no branch in build_neural_network (:299-304)
+    int32_t sharing[3] = {sharing_in[0], sharing_in[1], sharing_in[2]};
+    if (sharing[0] == 4) { sharing[0] = 1; sharing[1] = 0; }
     if (decoding_type != 1 && decoding_type != 2)
         return fail(LDPC_E_UNSUPPORTED, "decoding_type %d (1 = min-sum, 2 = quantised min-sum)", decoding_type);
     float qk = 1.f, qmax = 0.f;
@@ -424,6 +435,7 @@ extern "C" int ldpc_decoder_create(const ldpc_graph_t *g, const int32_t sharing[
     P.w_words = (int)wh.size(); P.w_staged = P.w_words > 0 && P.w_words <= NMS_WSTAGE_MAX_WORDS;
     P.w_off_cn = 0; P.w_off_ucn = T * wc; P.w_off_vn = T * (wc + wu);
     P.T_run = T;
+    P.target_n = target_node > 0 ? target_node : g->N;
     P.punct_s = g->punct_s; P.punct_e = g->punct_e; P.short_s = g->short_s; P.short_e = g->short_e;
     P.HW = (P.NZ + 31) / 32;
     fill_smem_layout(&P, d->packed);

@@ -145,7 +145,8 @@ __device__ __forceinline__ void copy_out(const KParams &P, const Ctx &c, const u
         const int f = item / P.HW, w = item - f * P.HW;
         if (!((mask[f >> 5] >> (f & 31)) & 1u)) continue;
         uint32_t outw = 0;
-        if ((onesm[f >> 5] >> (f & 31)) & 1u) {
+        // frames whose counted columns are clean still need the gather when parity columns are not counted
+        if (P.target_n < P.N || ((onesm[f >> 5] >> (f & 31)) & 1u)) {
             const int half = H2 ? (f & 1) : 0, fp = H2 ? (f >> 1) : f;
             const uint32_t *hb = nms_smem + P.off_hb + (hbuf * nh + half) * P.N * P.C;
             int k = 32 * w;
@@ -155,7 +156,9 @@ __device__ __forceinline__ void copy_out(const KParams &P, const Ctx &c, const u
                 outw |= ((hb[j * P.C + (qq >> 5)] >> (qq & 31)) & 1u) << b;
                 if (++a == P.z) { a = 0; ++j; }
             }
-            if (outw) atomicAdd(&misc[MISC_BITERR + f], (uint32_t)__popc(outw));
+            const int nb = min(32, max(0, P.target_n * P.z - 32 * w));   // bits of this word that count
+            const uint32_t cw = nb >= 32 ? outw : (outw & ((1u << nb) - 1u));
+            if (cw) atomicAdd(&misc[MISC_BITERR + f], (uint32_t)__popc(cw));
         }
         if (P.hard != nullptr) P.hard[(c.frame0 + f) * (long long)P.HW + w] = outw;
     }

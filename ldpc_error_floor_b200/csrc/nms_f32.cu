@@ -124,7 +124,7 @@ __device__ __forceinline__ F32Var f32_var(const KParams &P, const Ctx &c, int j,
     }
     const float hsrc = INIT ? v.xin : app;
     const bool hbit = hsrc >= 0.0f;                                  // Print_Functions.py:106
-    if (!INIT && hbit) ones |= 1u;
+    if (!INIT && hbit && j < P.target_n) ones |= 1u;
     const uint32_t b = __ballot_sync(0xffffffffu, c.act && hbit);
     if (c.lane == 0) nms_smem[P.off_hb + ((INIT ? 1 : (t & 1)) * P.N + j) * P.C + c.chunk] = b;
     if (!INIT && P.app != nullptr) app_store(P, c, j, t, c.f0, app);

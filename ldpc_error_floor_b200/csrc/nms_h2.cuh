@@ -252,7 +252,7 @@ __device__ __forceinline__ bool h2_var(const KParams &P, const Ctx &c, const H2C
     for (int k = 0; k < NC; ++k) {
         const __half2 hsrc = INIT ? v[k].xin : app[k];   // iteration 0 takes the syndrome of xin_0 (:181-182)
         v[k].hbw = (~h2u(hsrc) >> 15) & LSB2;            // bit = (value >= 0); a zero here is always +0
-        if (!INIT) ones |= v[k].hbw;
+        if (!INIT && j[k] < P.target_n) ones |= v[k].hbw;
     }
     if (cold) {
 #pragma unroll

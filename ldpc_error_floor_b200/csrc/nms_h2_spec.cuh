@@ -108,7 +108,9 @@ struct H2SpecPolicy {
         // hard bit = (value >= 0): of xin_0 before iteration 0 (:181-182), of the APP afterwards (a zero is +0)
         const __half2 hsrc = INIT ? xin : __hadd2(xqh, S);
         const uint32_t hbw = ~(h2u(hsrc) >> 15) & LSB2;
-        if constexpr (!INIT) ones |= hbw;
+        if constexpr (!INIT) {
+            if (J < P.target_n) ones |= hbw;   // uniform: only the first target_node columns count (systematic)
+        }
         if constexpr (HB) {
             const bool act = !PAD || h.amask != 0u;
             const uint32_t lo = __ballot_sync(0xffffffffu, act && (hbw & 1u));

@@ -81,10 +81,19 @@ class NMSDecoder:
     weight file (base rows followed by post rows)."""
 
     def __init__(self, graph: BaseGraph, weights: WeightSet, iters: Optional[int] = None, decoding_type: int = 2,
-                 q_bit: int = 5, clip_llr: float = 20.0, device: Optional[int] = None):
+                 q_bit: int = 5, clip_llr: float = 20.0, device: Optional[int] = None, systematic: int = 0,
+                 fixed_iter: int = 0):
+        """systematic = 1 (main_Base.py:29): the error metrics cover the first N - M proto columns only.
+        fixed_iter: for temporal sharing (code 4) given as its fixed_iter + 1 variables."""
         self.graph = graph
-        self.sharing = [int(s) for s in weights.sharing]
         T = weights.iterations if iters is None else int(iters)
+        if any(int(c) in (4, 5) for c in weights.sharing):
+            from .formats import expand_temporal
+            if iters is None:
+                raise ValueError("temporal sharing needs the iteration count (iters=...)")
+            weights = expand_temporal(weights, T, int(fixed_iter))
+        self.target_node = graph.N - graph.M if systematic else 0
+        self.sharing = [int(s) for s in weights.sharing]
         if T <= 0:
             raise ValueError("a decoder needs at least one iteration (all-zero sharing carries no rows: pass iters)")
         self.T = T
@@ -107,9 +116,9 @@ class NMSDecoder:
         lib = _lib.load()
         sh = (ctypes.c_int32 * 3)(*self.sharing)
         self._h = ctypes.c_void_p()
-        _lib.check(lib.ldpc_decoder_create(
+        _lib.check(lib.ldpc_decoder_create2(
             graph._h, sh, T, *[b.ctypes.data if b is not None else None for b in blocks],
-            self.decoding_type, self.q_bit, self.clip_llr, self.device_index, ctypes.byref(self._h)))
+            self.decoding_type, self.q_bit, self.clip_llr, self.device_index, self.target_node, ctypes.byref(self._h)))
         self.packed = bool(lib.ldpc_decoder_uses_packed_kernel(self._h))
         self.kernel_name = lib.ldpc_decoder_kernel_name(self._h).decode()
         fb, cps, thr, smem = (ctypes.c_int32() for _ in range(4))

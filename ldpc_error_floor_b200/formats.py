@@ -85,6 +85,30 @@ class WeightSet:
         return WeightSet(list(self.sharing), {i: b[start:stop].copy() for i, b in self.blocks.items()})
 
 
+def expand_temporal(ws: "WeightSet", T: int, fixed_iter: int) -> "WeightSet":
+    """Temporal sharing (codes 4 / 5, main_Base.py:24): iterations t >= fixed_iter reuse the variables of
+    iteration fixed_iter (Main_Functions.py:170-174, 299-304), so only fixed_iter + 1 rows exist
+    (weight_init :411-414).  Returns the equivalent per-iteration set: code 4 -> 1 (per edge) with T rows;
+    a UCN block of code 4 is dropped because build_neural_network has no UCN branch for it (:299-304).
+    Files written by print_weight already hold the T expanded rows (Print_Functions.py:87-94) and pass through."""
+    sharing, blocks = list(ws.sharing), {}
+    for i, code in enumerate(ws.sharing):
+        if code <= 0:
+            continue
+        b = np.asarray(ws.blocks[i], dtype=np.float32)
+        if code in (4, 5):
+            if i == 1:
+                sharing[1] = 0
+                continue
+            if b.shape[0] < T:
+                if b.shape[0] < fixed_iter + 1:
+                    raise ValueError(f"temporal block {i}: {b.shape[0]} rows < fixed_iter + 1 = {fixed_iter + 1}")
+                b = b[np.minimum(np.arange(T), fixed_iter)]
+            sharing[i] = 1 if code == 4 else 2
+        blocks[i] = b
+    return WeightSet(sharing, blocks)
+
+
 def read_weights(path: str) -> WeightSet:
     """Header "s0 s1 s2", blank line, then one blank-line-terminated block of T lines per
     non-zero sharing code (tab-separated float32 reprs).  The reference addresses the same

@@ -47,7 +47,7 @@ class ReferenceDecoder:
     but eagerly (numpy arrays instead of TF tensors)."""
 
     def __init__(self, code_proto, z, sharing, weights, T, decoding_type=2, q_bit=5,
-                 clip_llr=20.0, punct=(0, 0), short=(0, 0), snr_db=(0.0,)):
+                 clip_llr=20.0, punct=(0, 0), short=(0, 0), snr_db=(0.0,), target_node=None, fixed_iter=0):
         self.mf, self.pf = load_reference()
         self.code_proto = np.asarray(code_proto, dtype=int)
         self.z = int(z)
@@ -62,6 +62,8 @@ class ReferenceDecoder:
          self.snr_sigma) = self.mf.init_parameter(self.code_proto, np.asarray(snr_db, dtype=float),
                                                   self.z, punct[0], punct[1], short[0], short[1])
         self.E = int(self.E)
+        self.target_node = self.N if target_node is None else int(target_node)   # main_Base.py:83-86 (systematic)
+        self.fixed_iter = int(fixed_iter)                                        # temporal sharing (code 4)
         self.mats = self.mf.init_connecting_matrix(self.code_proto, self.code_base, self.N, self.M,
                                                    self.E, self.z, self.vn_deg, self.cn_deg,
                                                    punct[0], punct[1])
@@ -70,7 +72,8 @@ class ReferenceDecoder:
         for i, code in enumerate(self.sharing):
             if code > 0:
                 w = np.asarray(weights[i], dtype=np.float32)
-                for t in range(self.T):
+                rows = self.T if code in (1, 2, 3) else self.fixed_iter + 1       # weight_init :411-414
+                for t in range(rows):
                     self.vars[f"var_{i}_{t}"] = np.ascontiguousarray(w[t]).reshape(-1)
 
     def decode(self, xa, ya=None):
@@ -86,7 +89,7 @@ class ReferenceDecoder:
         net["LLRa0"] = np.zeros((B, self.z, self.E), dtype=np.float32)  # main_Base.py:126
         for t in range(self.T):
             net = self.mf.build_neural_network(
-                net, self.sharing, self.decoding_type, 2, 2, self.N, t, self.T, 0, 0, 0, self.T,
+                net, self.sharing, self.decoding_type, 2, 2, self.target_node, t, self.T, self.fixed_iter, 0, 0, self.T,
                 self.N, self.M, self.E, self.z, B, *self.mats, self.q_bit, self.clip_llr)
         app = np.stack([net[f"ya_output{t}"] for t in range(self.T)], axis=0)
         c2v = np.stack([net[f"LLRa{t + 1}"] for t in range(self.T)], axis=0)

@@ -29,6 +29,17 @@ def load_case(name):
         "q_bit": int(d["q_bit"]), "clip": float(d["clip"]), "xa": d["xa"], "app": d["app"],
         "weights": {i: d[f"w{i}"] for i in range(3) if f"w{i}" in d},
     }
+    case["raw_sharing"], case["raw_weights"] = list(case["sharing"]), dict(case["weights"])
+    case["fixed_iter"] = int(d["fixed_iter"]) if "fixed_iter" in d else 0
+    if any(c in (4, 5) for c in case["sharing"]):
+        # temporal sharing: the reference ran with fixed_iter + 1 variables; everything on our side takes the
+        # equivalent per-iteration table (formats.expand_temporal)
+        from ldpc_error_floor_b200 import formats
+        ws = formats.expand_temporal(formats.WeightSet(case["sharing"], case["weights"]), case["T"], case["fixed_iter"])
+        case["sharing"], case["weights"] = ws.sharing, ws.blocks
+    if "target_node" in d:
+        case.update(target_node=int(d["target_node"]), ya_output_all=d["ya_output_all"], uncor_flag=d["uncor_flag"],
+                    error_num=d["error_num"], metrics=d["metrics"])
     return case
 
 

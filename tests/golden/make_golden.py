@@ -53,6 +53,9 @@ WEIGHTS = {
 }
 
 
+ONLY = []
+
+
 def graph_meta(key):
     stem, z, punct, short = GRAPHS[key]
     path = os.path.join(REF, "BaseGraph", stem + ".txt")
@@ -100,10 +103,12 @@ def ref_llrs(pf, sigmas, B, N, z, decoding_type, punct, short, q_bit, clip, seed
 
 
 def make_decode_case(name, gkey, sharing, weights, T, decoding_type, q_bit, B, snr_db, seed=2, clip=20.0,
-                     raw_llr=False):
+                     raw_llr=False, target_node=None, fixed_iter=0):
+    if ONLY and not any(o in name for o in ONLY):
+        return
     stem, proto, z, punct, short = graph_meta(gkey)
     rd = ref_runner.ReferenceDecoder(proto.astype(int), z, sharing, weights, T, decoding_type, q_bit, clip,
-                                     punct, short, snr_db)
+                                     punct, short, snr_db, target_node=target_node, fixed_iter=fixed_iter)
     # raw_llr: feed UNQUANTISED channel LLRs to the quantised decoder (legal in the reference: the
     # graph quantises its input itself, Main_Functions.py:176-177, 321-322)
     X = ref_llrs(rd.pf, rd.snr_sigma, B, rd.N, z, 1 if raw_llr else decoding_type, punct, short, q_bit, clip, seed)
@@ -115,6 +120,17 @@ def make_decode_case(name, gkey, sharing, weights, T, decoding_type, q_bit, B, s
     for i in range(3):
         if sharing[i] > 0:
             out[f"w{i}"] = np.asarray(weights[i], dtype=np.float32)[:T]
+    if target_node is not None:
+        # systematic = 1 (main_Base.py:83-84): ya_output_all holds the first target_node columns only and
+        # calc_ber_fer (Print_Functions.py:100-118) counts over those
+        ya_all = res["ya_output_all"]
+        Y = np.zeros((B, rd.N * z), dtype=np.int64)
+        ber_last, fer_last, fer, uncor, error_num = rd.pf.calc_ber_fer(ya_all, T, Y, B)
+        out.update(target_node=np.array(target_node), ya_output_all=ya_all.astype(np.float32),
+                   uncor_flag=np.asarray(uncor), error_num=np.asarray(error_num),
+                   metrics=np.array([ber_last, fer_last, fer]))
+    if fixed_iter:
+        out["fixed_iter"] = np.array(fixed_iter)
     np.savez_compressed(os.path.join(OUT, f"decode_{name}.npz"), **out)
     hard_fail = ((res["app"][-1] >= 0).sum(axis=1) > 0).sum()
     print(f"decode_{name}.npz  B={B} T={T}  frames still wrong at the end: {hard_fail}")
@@ -193,6 +209,19 @@ def make_decode_cases():
         make_decode_case(f"wimax_qms_q{qb}_323_t6".replace("-", "m"), "wimax", [3, 3, 3],
                          const_weights([3, 3, 3], 6, M, N, E, rng=rng), 6, 2, qb, 4, [3.0, 3.5])
     make_decode_case("wimax_qms_000_t5", "wimax", [0, 0, 0], {}, 5, 2, 5, 4, [3.0, 3.5])
+    # "next" row N3: temporal sharing (code 4: per-edge CN weights, rows >= fixed_iter reuse row fixed_iter,
+    # Main_Functions.py:299-304) and the systematic metric (target_node = N - M, main_Base.py:83-84)
+    stem, proto, z, punct, short = graph_meta("wimax")
+    M, N = proto.shape
+    E = int((proto != -1).sum())
+    rng = np.random.RandomState(11)
+    w4 = const_weights([1, 0, 2], 4, M, N, E, rng=rng)          # var_0_0..var_0_3 (fixed_iter = 3), var_2_t for t < 8
+    w4[2] = const_weights([1, 0, 2], 8, M, N, E, rng=rng)[2]
+    make_decode_case("wimax_qms_402_t8_fixed3", "wimax", [4, 0, 2], w4, 8, 2, 5, 6, [3.0, 3.5], fixed_iter=3)
+    sh, w = shipped("5g_r050_z64_boost50")
+    stem, proto, z, punct, short = graph_meta("5g_r050_z64")
+    M, N = proto.shape
+    make_decode_case("5g_r050_z64_qms_222_t12_sys", "5g_r050_z64", sh, w, 12, 2, 5, 12, [0.5, 1.5, 2.5], target_node=N - M)
 
 
 def make_mc():
@@ -222,7 +251,9 @@ def make_mc():
 if __name__ == "__main__":
     if not ref_runner.reference_available():
         raise SystemExit("needs /root/reference (development container only)")
-    what = sys.argv[1:] or ["codes", "decode", "mc"]
+    # `make_golden.py decode only=sys,fixed` re-mints just the decode cases whose name contains one of the keys
+    ONLY[:] = [k for a in sys.argv[1:] if a.startswith("only=") for k in a[5:].split(",")]
+    what = [a for a in sys.argv[1:] if not a.startswith("only=")] or ["codes", "decode", "mc"]
     if "codes" in what:
         make_codes()
     if "decode" in what:

@@ -158,3 +158,51 @@ def test_q8_words_decode_like_float_words(name):
         assert np.array_equal(h["flags"], a.flags.cpu().numpy()) and np.array_equal(h["iters"], a.iters.cpu().numpy())
         c = cnt.cpu().numpy()
         assert c[0] == 1500 and c[3] == int(a.biterr.sum().item()) and c[2] == int(((a.flags & 2) != 0).sum().item())
+
+
+def test_systematic_metrics_match_reference():
+    """systematic = 1 (main_Base.py:29, 83-86): ya_output_all and calc_ber_fer only see the first N - M columns.
+    Golden: the reference's own calc_ber_fer on its ya_output_all (decode_5g_r050_z64_qms_222_t12_sys.npz)."""
+    import torch
+    import ldpc_error_floor_b200 as L
+    case = load_case("5g_r050_z64_qms_222_t12_sys")
+    g = L.BaseGraph(case["proto"], case["z"], case["punct"], case["short"])
+    ws = L.WeightSet(case["sharing"], dict(case["weights"]))
+    dec = L.NMSDecoder(g, ws, iters=case["T"], decoding_type=2, q_bit=5, clip_llr=case["clip"], systematic=1)
+    assert dec.target_node == case["target_node"] == g.N - g.M
+    xa = torch.from_numpy(case["xa"]).cuda()
+    r = dec.decode(xa, app="all", unpack=True)
+    B, tz = xa.shape[0], case["target_node"] * case["z"]
+    # ya_output_all = per-iteration APPs truncated to the target columns, iterations stacked on axis 0 (:329-335, 380-383)
+    ya = r.app[:, :, :tz].reshape(-1, tz).cpu().numpy()
+    assert np.array_equal(ya, case["ya_output_all"])
+    assert np.array_equal(r.uncor_any.cpu().numpy(), case["uncor_flag"] > 0)
+    assert np.array_equal(r.biterr.cpu().numpy(), case["error_num"])
+    full = L.NMSDecoder(g, ws, iters=case["T"], decoding_type=2, q_bit=5, clip_llr=case["clip"]).decode(xa, unpack=True)
+    assert torch.equal(full.hard, r.hard) and torch.equal(full.iters, r.iters)       # outputs cover the whole word
+    assert int(full.biterr.sum()) >= int(r.biterr.sum()) and int(full.uncor_any.sum()) >= int(r.uncor_any.sum())
+    assert np.array_equal(r.hard[:, :tz].sum(dim=1).cpu().numpy(), case["error_num"])
+    # same through the fused Monte-Carlo counters and with early termination on device buffers
+    cnt = torch.zeros(8, dtype=torch.int64, device="cuda")
+    dec.decode_q8(torch.round(torch.clamp(xa.reshape(B, -1), -7.5, 7.5) * 2).to(torch.int8), counters=cnt)
+    c = cnt.cpu().numpy()
+    assert c[0] == B and c[2] == int((case["uncor_flag"] > 0).sum()) and c[3] == int(case["error_num"].sum())
+    ber_last, fer_last, fer = case["metrics"]
+    assert c[1] / B == pytest.approx(fer_last) and c[2] / B == pytest.approx(fer)
+    assert c[3] / (B * g.NZ) == pytest.approx(ber_last)          # the reference divides by the FULL length (:113)
+
+
+def test_temporal_sharing_matches_reference():
+    """sharing code 4: fixed_iter + 1 per-edge variables, iterations >= fixed_iter reuse the last one
+    (Main_Functions.py:299-304).  Golden: the reference run with sharing [4,0,2], fixed_iter = 3, T = 8."""
+    import torch
+    import ldpc_error_floor_b200 as L
+    case = load_case("wimax_qms_402_t8_fixed3")
+    assert case["raw_sharing"] == [4, 0, 2] and case["raw_weights"][0].shape[0] == 4 and case["sharing"] == [1, 0, 2]
+    g = L.BaseGraph(case["proto"], case["z"])
+    raw = L.WeightSet(case["raw_sharing"], dict(case["raw_weights"]))
+    with pytest.raises(ValueError):
+        L.NMSDecoder(g, raw)                                       # iteration count is not in the variables
+    dec = L.NMSDecoder(g, raw, iters=8, fixed_iter=3, decoding_type=2, q_bit=5)
+    r = dec.decode(torch.from_numpy(case["xa"]).cuda(), app="all")
+    assert np.array_equal(r.app.cpu().numpy(), case["app"])

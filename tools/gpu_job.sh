@@ -1,3 +1,3 @@
 mkdir -p gpurun_out
-python -m pytest tests -m gpu -x -q 2>&1 | tail -5
-python bench.py > gpurun_out/bench_cur.json 2> gpurun_out/bench_cur.err; echo rc=$?; tail -3 gpurun_out/bench_cur.err
+python -m pytest tests -m gpu -x -q 2>&1 | tail -12
+SWEEP_SNR=1.0 python tools/geom_sweep.py wimax "0,0" 2>&1 | tail -1
