@@ -248,15 +248,73 @@ def make_mc():
     print("mc_wimax.npz", np.stack(results, axis=1))
 
 
+def make_grad_case(name, gkey, sharing, weights, T, t_lo, loss_type, etha, decoding_type, B, snr_db, seed=7,
+                   q_bit=5, clip=20.0, target_node=None):
+    """One training batch through the reference's own loss (Main_Functions.py:337-378), differentiated by
+    torch.autograd (oracle/ref_grad.py): the golden for the CUDA backward ("next" row N1)."""
+    from oracle import ref_grad
+    if ONLY and not any(o in name for o in ONLY):
+        return
+    stem, proto, z, punct, short = graph_meta(gkey)
+    rd = ref_runner.ReferenceDecoder(proto.astype(int), z, sharing, weights, T, decoding_type, q_bit, clip, punct,
+                                     short, snr_db)
+    X = ref_llrs(rd.pf, rd.snr_sigma, B, rd.N, z, decoding_type, punct, short, q_bit, clip, seed)
+    r = ref_grad.loss_and_grads(proto.astype(int), z, sharing, weights, X, T, iter_start=t_lo, loss_type=loss_type,
+                                etha=etha, decoding_type=decoding_type, q_bit=q_bit, clip_llr=clip, punct=punct,
+                                short=short, target_node=target_node)
+    out = {"proto": proto.astype(np.int16), "meta": np.array([z, punct[0], punct[1], short[0], short[1]]),
+           "sharing": np.array(sharing), "T": np.array(T), "t_lo": np.array(t_lo), "loss_type": np.array(loss_type),
+           "etha": np.array(etha, dtype=np.float64), "decoding_type": np.array(decoding_type), "q_bit": np.array(q_bit),
+           "clip": np.array(clip, dtype=np.float32), "xa": X, "loss": np.array(r["loss"], dtype=np.float64),
+           "target_node": np.array(-1 if target_node is None else target_node)}
+    for i in range(3):
+        if sharing[i] > 0:
+            w = np.asarray(weights[i], dtype=np.float32)[:T]
+            out[f"w{i}"] = w
+            gr = np.zeros_like(w.reshape(T, -1))
+            for t in range(t_lo, T):
+                gr[t] = r["grads"][(i, t)]
+            out[f"g{i}"] = gr
+    np.savez_compressed(os.path.join(OUT, f"grad_{name}.npz"), **out)
+    print(f"grad_{name}.npz  loss {r['loss']:.6g}  max|g| {max(np.abs(out[k]).max() for k in out if k[0] == 'g' and k[1:].isdigit()):.4g}")
+
+
+def make_grad_cases():
+    sh, w = shipped("wimax_base20")
+    make_grad_case("wimax_qms_333_fer_t6", "wimax", sh, w, 6, 0, 2, 0.0, 2, 6, [2.0, 2.5])
+    make_grad_case("wimax_qms_333_bce_eta_t6", "wimax", sh, w, 6, 2, 0, 0.5, 2, 6, [2.0, 2.5])
+    make_grad_case("wimax_float_333_sber_t5", "wimax", sh, w, 5, 0, 1, 1.0, 1, 4, [2.0])
+    sh5, w5 = shipped("5g_r073_z32_boost50")
+    make_grad_case("5g_r073_z32_qms_222_fer_t8", "5g_r073_z32", sh5, w5, 8, 3, 2, 0.7, 2, 4, [1.0, 2.0])
+    stem, proto, z, punct, short = graph_meta("5g_r073_z32")
+    M, N = proto.shape
+    make_grad_case("5g_r073_z32_qms_222_bce_sys_t6", "5g_r073_z32", sh5, w5, 6, 0, 0, 1.0, 2, 4, [1.0, 2.0],
+                   target_node=N - M)
+    stem, proto, z, punct, short = graph_meta("wimax")
+    M, N = proto.shape
+    E = int((proto != -1).sum())
+    rng = np.random.RandomState(5)
+    make_grad_case("wimax_qms_112_fer_t4", "wimax", [1, 1, 2], const_weights([1, 1, 2], 4, M, N, E, rng=rng), 4, 0, 2, 0.0,
+                   2, 4, [2.0])
+    make_grad_case("wimax_qms_303_bce_t4", "wimax", [3, 0, 3], {0: w[0], 2: w[2]}, 4, 1, 0, 0.0, 2, 4, [2.5])
+    stem, proto, z, punct, short = graph_meta("mackay")
+    M, N = proto.shape
+    E = int((proto != -1).sum())
+    make_grad_case("mackay_float_300_bce_t5", "mackay", [3, 0, 0], const_weights([3, 0, 0], 5, M, N, E), 5, 0, 0, 1.0, 1,
+                   16, [2.0, 3.0])
+
+
 if __name__ == "__main__":
     if not ref_runner.reference_available():
         raise SystemExit("needs /root/reference (development container only)")
     # `make_golden.py decode only=sys,fixed` re-mints just the decode cases whose name contains one of the keys
     ONLY[:] = [k for a in sys.argv[1:] if a.startswith("only=") for k in a[5:].split(",")]
-    what = [a for a in sys.argv[1:] if not a.startswith("only=")] or ["codes", "decode", "mc"]
+    what = [a for a in sys.argv[1:] if not a.startswith("only=")] or ["codes", "decode", "mc", "grad"]
     if "codes" in what:
         make_codes()
     if "decode" in what:
         make_decode_cases()
     if "mc" in what:
         make_mc()
+    if "grad" in what:
+        make_grad_cases()
