@@ -207,6 +207,26 @@ int ldpc_post_decode(const ldpc_decoder_t *post, const float *uncor_dev, int64_t
                      int32_t iters, int32_t early_term, uint64_t *counters_dev, uint32_t *hard_dev,
                      int32_t *iters_dev, uint8_t *flags_dev, void *stream);
 
+/* ---- training step ("next" row N1 of SURVEY.md 8f) ------------------------------------------
+ * ldpc_decoder_set_weights replaces the decoder's weights (same shapes as at creation): the one mutable part
+ * of a handle; it synchronises the device first, and the caller must not launch from other threads meanwhile.
+ * It stands for the variable update of tf.train.AdamOptimizer.minimize (Main_Functions.py:377-378); the
+ * optimiser arithmetic itself lives on the host (trainer.py) -- there are at most a few hundred weights.
+ *
+ * ldpc_train_grad runs the reference's training batch (main_Base.py:160-162) for the all-zero codeword:
+ * `iters` iterations forward, loss over iterations [iter_lo, iters) weighted by pow(etha, iters-1-t) and
+ * normalised (Main_Functions.py:339-357; loss_type 0 = sigmoid cross entropy, 1 = soft BER, 2 = FER with the
+ * straight-through sign), and its gradient with respect to the weights of iterations [iter_lo, iters)
+ * (var_list, :360-375; iter_lo = max(training_iter_start - fixed_init, fixed_iter)).  Gradient rules are
+ * TensorFlow's for the reference graph: straight-through quantisers (:475-494), tie-split reduce_min, no
+ * gradient through signs / comparisons.  Outputs on the HOST: *loss_host; g_*_host f32 [T, width] (T = the
+ * decoder's iteration count; rows outside [iter_lo, iters) are zero; NULL for absent blocks); optional
+ * app_dev f32 [iters, B, N*z] (= ya_output{t}).  Synchronous; the error metrics' target_node applies. */
+int ldpc_decoder_set_weights(ldpc_decoder_t *d, const float *w_cn, const float *w_ucn, const float *w_vn);
+int ldpc_train_grad(const ldpc_decoder_t *d, const float *llr_dev, int64_t B, int32_t iters, int32_t iter_lo,
+                    int32_t loss_type, double etha, double *loss_host, float *g_cn_host, float *g_ucn_host,
+                    float *g_vn_host, float *app_dev);
+
 /* kernels launched by this library since load (for bench.py's gpu_launches) */
 uint64_t ldpc_launch_count(void);
 

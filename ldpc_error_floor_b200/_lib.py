@@ -66,6 +66,9 @@ SYMBOLS = {
     "ldpc_mc_run_host": (ctypes.c_int, [_P, ctypes.c_double, _I64, _U64, _U64, _I32, _I32, _I32, _P, _P, _U32,
                                         ctypes.POINTER(_U32)]),
     "ldpc_post_decode": (ctypes.c_int, [_P, _P, _I64, _I32, _I32, _P, _P, _P, _P, _P]),
+    "ldpc_decoder_set_weights": (ctypes.c_int, [_P, _P, _P, _P]),
+    "ldpc_train_grad": (ctypes.c_int, [_P, _P, _I64, _I32, _I32, _I32, ctypes.c_double, ctypes.POINTER(ctypes.c_double),
+                                       _P, _P, _P, _P]),
     "ldpc_launch_count": (ctypes.c_uint64, []),
 }
 

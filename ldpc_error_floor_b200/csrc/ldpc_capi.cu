@@ -6,6 +6,7 @@
 // list, pre-scaled for the lane-interleaved layout of the kernels (nms_common.cuh).
 #include "../../include/ldpc_b200.h"
 #include "nms_common.cuh"
+#include "nms_train.cuh"
 
 #include <algorithm>
 #include <cmath>
@@ -110,6 +111,15 @@ struct ldpc_decoder {
     LaunchGeom geom{};
     KParams base{};
     float *d_w = nullptr;
+    // training step (nms_train.cu): the weights as given ([T*wc | T*wu | T*wv], no "effective" rows), graph tables,
+    // per-call workspace -- all created on first use
+    int wc_raw = 0, wu_raw = 0, wv_raw = 0;
+    bool ones_cn = false;
+    std::vector<float> w_raw;
+    float *d_w_raw = nullptr;
+    int *d_tab = nullptr;
+    float *d_hist = nullptr; size_t hist_cap = 0;
+    float *d_coef = nullptr; float *d_grad = nullptr; double *d_loss = nullptr;
     std::mutex mu;
     HostScratch hs;
 };
@@ -399,6 +409,11 @@ extern "C" int ldpc_decoder_create2(const ldpc_graph_t *g, const int32_t sharing
     if (d->packed && (int)wh.size() > NMS_WSTAGE_MAX_WORDS) d->packed = false;   // weights must fit in shared memory
     if (!d->packed && ones_cn) { wc = 0; wh.erase(wh.begin(), wh.begin() + T); }
     const int w_words = (int)wh.size();
+    d->wc_raw = weight_width(sharing[0], 0, g->M, g->N, g->E); d->wu_raw = wu; d->wv_raw = wv;
+    d->ones_cn = d->packed && sharing[0] == 0;
+    if (d->wc_raw) d->w_raw.assign(w_cn, w_cn + (size_t)T * d->wc_raw);
+    if (wu) d->w_raw.insert(d->w_raw.end(), w_ucn, w_ucn + (size_t)T * wu);
+    if (wv) d->w_raw.insert(d->w_raw.end(), w_vn, w_vn + (size_t)T * wv);
     // a graph known at build time gets its specialised kernel (gen_spec.py); anything else the generic buckets
     int rc = LDPC_E_LIMIT;
     d->func = nullptr;
@@ -512,7 +527,8 @@ extern "C" int ldpc_decoder_destroy(ldpc_decoder_t *d) {
     {
         DeviceGuard guard(d->device);
         free_scratch(d->hs);
-        cudaFree(d->d_w);
+        cudaFree(d->d_w); cudaFree(d->d_w_raw); cudaFree(d->d_tab); cudaFree(d->d_hist); cudaFree(d->d_coef);
+        cudaFree(d->d_grad); cudaFree(d->d_loss);
     }
     delete d;
     return LDPC_OK;
@@ -789,6 +805,100 @@ extern "C" int ldpc_post_decode(const ldpc_decoder_t *post, const float *uncor_d
     P.counters = (unsigned long long *)counters_dev;
     P.hard = hard_dev; P.iters = iters_dev; P.flags = flags_dev;
     return launch(post, P, (cudaStream_t)stream);
+}
+
+// --------------------------------------------------------------------------- training step
+extern "C" int ldpc_decoder_set_weights(ldpc_decoder_t *d, const float *w_cn, const float *w_ucn, const float *w_vn) {
+    if (!d) return fail(LDPC_E_INVALID, "set_weights: null decoder");
+    if ((d->wc_raw && !w_cn) || (d->wu_raw && !w_ucn) || (d->wv_raw && !w_vn))
+        return fail(LDPC_E_INVALID, "set_weights: missing weight block");
+    DeviceGuard guard(d->device);
+    if (!guard.ok) return fail(LDPC_E_CUDA, "cudaSetDevice(%d) failed", d->device);
+    std::lock_guard<std::mutex> lock(d->mu);
+    const size_t T = (size_t)d->T;
+    std::vector<float> raw, eff;
+    if (d->wc_raw) raw.assign(w_cn, w_cn + T * d->wc_raw);
+    if (d->wu_raw) raw.insert(raw.end(), w_ucn, w_ucn + T * d->wu_raw);
+    if (d->wv_raw) raw.insert(raw.end(), w_vn, w_vn + T * d->wv_raw);
+    if (d->ones_cn) eff.assign(T, 1.0f);            // same "effective" layout ldpc_decoder_create2 built
+    eff.insert(eff.end(), raw.begin(), raw.end());
+    if ((int)eff.size() != d->base.w_words) return fail(LDPC_E_INVALID, "internal: weight block size changed");
+    CUDA_TRY(cudaDeviceSynchronize());               // no launch may still be reading the old block
+    if (!eff.empty()) CUDA_TRY(cudaMemcpy(d->d_w, eff.data(), eff.size() * sizeof(float), cudaMemcpyHostToDevice));
+    d->w_raw = raw;
+    if (d->d_w_raw && !raw.empty())
+        CUDA_TRY(cudaMemcpy(d->d_w_raw, raw.data(), raw.size() * sizeof(float), cudaMemcpyHostToDevice));
+    return LDPC_OK;
+}
+
+extern "C" int ldpc_train_grad(const ldpc_decoder_t *dc, const float *llr_dev, int64_t B, int32_t iters, int32_t iter_lo,
+                               int32_t loss_type, double etha, double *loss_host, float *g_cn_host, float *g_ucn_host,
+                               float *g_vn_host, float *app_dev) {
+    ldpc_decoder *d = const_cast<ldpc_decoder *>(dc);
+    if (!d || !llr_dev || B <= 0 || !loss_host) return fail(LDPC_E_INVALID, "train_grad: bad arguments");
+    const int T = iters == 0 ? d->T : iters;
+    if (T < 1 || T > d->T || iter_lo < 0 || iter_lo >= T) return fail(LDPC_E_INVALID, "train_grad: iterations [%d, %d) outside 0..%d", iter_lo, T, d->T);
+    if (loss_type < 0 || loss_type > 2) return fail(LDPC_E_INVALID, "train_grad: loss_type %d (0 BCE, 1 soft BER, 2 FER)", loss_type);
+    if (d->g.info.max_dc > 64) return fail(LDPC_E_LIMIT, "train_grad: row degree %d > 64", d->g.info.max_dc);
+    DeviceGuard guard(d->device);
+    if (!guard.ok) return fail(LDPC_E_CUDA, "cudaSetDevice(%d) failed", d->device);
+    std::lock_guard<std::mutex> lock(d->mu);
+    const ldpc_graph &g = d->g;
+    const int E = g.E, M = g.M, N = g.N;
+    if (!d->d_tab) {
+        std::vector<int> tab;
+        tab.insert(tab.end(), g.row.begin(), g.row.end());
+        tab.insert(tab.end(), g.col.begin(), g.col.end());
+        tab.insert(tab.end(), g.shift.begin(), g.shift.end());
+        tab.insert(tab.end(), g.row_ptr.begin(), g.row_ptr.end());
+        tab.insert(tab.end(), g.col_ptr.begin(), g.col_ptr.end());
+        tab.insert(tab.end(), g.col_edge.begin(), g.col_edge.end());
+        CUDA_TRY(cudaMalloc(&d->d_tab, tab.size() * sizeof(int)));
+        CUDA_TRY(cudaMemcpy(d->d_tab, tab.data(), tab.size() * sizeof(int), cudaMemcpyHostToDevice));
+        const size_t nw = std::max<size_t>(d->w_raw.size(), 1);
+        CUDA_TRY(cudaMalloc(&d->d_w_raw, nw * sizeof(float)));
+        if (!d->w_raw.empty())
+            CUDA_TRY(cudaMemcpy(d->d_w_raw, d->w_raw.data(), d->w_raw.size() * sizeof(float), cudaMemcpyHostToDevice));
+        CUDA_TRY(cudaMalloc(&d->d_grad, nw * sizeof(float)));
+        CUDA_TRY(cudaMalloc(&d->d_coef, LDPC_MAX_T * sizeof(float)));
+        CUDA_TRY(cudaMalloc(&d->d_loss, sizeof(double)));
+    }
+    TrainParams P{};
+    P.M = M; P.N = N; P.E = E; P.z = g.z; P.NZ = N * g.z; P.EZ = E * g.z; P.MZ = M * g.z;
+    P.row = d->d_tab; P.col = P.row + E; P.shift = P.col + E; P.row_ptr = P.shift + E; P.col_ptr = P.row_ptr + M + 1;
+    P.col_edge = P.col_ptr + N + 1;
+    P.qms = d->decoding_type == 2; P.qmagic = d->base.qmagic; P.qmax = d->base.qmax; P.clip = d->clip;
+    P.sharing0 = d->sharing[0]; P.sharing1 = d->sharing[1]; P.sharing2 = d->sharing[2];
+    P.wc = d->wc_raw; P.wu = d->wu_raw; P.wv = d->wv_raw;
+    P.w = d->d_w_raw; P.off_cn = 0; P.off_ucn = d->T * P.wc; P.off_vn = d->T * (P.wc + P.wu);
+    P.T = T; P.t_lo = iter_lo; P.loss_type = loss_type; P.target_nz = d->base.target_n * g.z; P.B = (int)B;
+    P.llr = llr_dev; P.app_out = app_dev;
+    const size_t need = (size_t)B * (T + 1) * P.EZ;
+    if (d->hist_cap < need) {
+        cudaFree(d->d_hist); d->d_hist = nullptr; d->hist_cap = 0;
+        CUDA_TRY(cudaMalloc(&d->d_hist, need * sizeof(float)));
+        d->hist_cap = need;
+    }
+    P.hist = d->d_hist; P.loss = d->d_loss; P.grad = d->d_grad; P.coef = d->d_coef;
+    if (nms_train_smem_bytes(P) > 227 * 1024) return fail(LDPC_E_LIMIT, "train_grad: graph needs %zu bytes of shared memory", nms_train_smem_bytes(P));
+    // loss coefficients pow(etha, T-1-t) / sum (Main_Functions.py:342-354); pow(0, 0) = 1
+    std::vector<float> coef(LDPC_MAX_T, 0.0f);
+    double norm = 0.0;
+    for (int t = iter_lo; t < T; ++t) norm += std::pow(etha, (double)(T - 1 - t));
+    for (int t = iter_lo; t < T; ++t) coef[t] = (float)(std::pow(etha, (double)(T - 1 - t)) / norm);
+    CUDA_TRY(cudaMemcpy(d->d_coef, coef.data(), coef.size() * sizeof(float), cudaMemcpyHostToDevice));
+    const size_t nw = std::max<size_t>(d->w_raw.size(), 1);
+    CUDA_TRY(cudaMemset(d->d_grad, 0, nw * sizeof(float)));
+    CUDA_TRY(cudaMemset(d->d_loss, 0, sizeof(double)));
+    CUDA_TRY(nms_launch_train(P, nullptr));
+    CUDA_TRY(cudaMemcpy(loss_host, d->d_loss, sizeof(double), cudaMemcpyDeviceToHost));
+    std::vector<float> gh(nw);
+    CUDA_TRY(cudaMemcpy(gh.data(), d->d_grad, nw * sizeof(float), cudaMemcpyDeviceToHost));
+    const size_t Tw = (size_t)d->T;
+    if (g_cn_host && P.wc) std::memcpy(g_cn_host, gh.data(), Tw * P.wc * sizeof(float));
+    if (g_ucn_host && P.wu) std::memcpy(g_ucn_host, gh.data() + Tw * P.wc, Tw * P.wu * sizeof(float));
+    if (g_vn_host && P.wv) std::memcpy(g_vn_host, gh.data() + Tw * (P.wc + P.wu), Tw * P.wv * sizeof(float));
+    return LDPC_OK;
 }
 
 extern "C" uint64_t ldpc_launch_count(void) { return nms_launch_count(); }

@@ -211,6 +211,42 @@ class NMSDecoder:
             it.ctypes.data, fl.ctypes.data, be.ctypes.data))
         return {"hard_packed": hard, "iters": it, "flags": fl, "biterr": be, "app": app_a}
 
+    # ------------------------------------------------------------------ training step (N1)
+    def set_weights(self, weights: WeightSet) -> None:
+        """Replace the weights (same sharing codes and shapes): the variable update of a training step."""
+        if [int(c) for c in weights.sharing] != self.sharing:
+            raise ValueError(f"set_weights: sharing {weights.sharing} != {self.sharing}")
+        blocks = [None, None, None]
+        for i, code in enumerate(self.sharing):
+            if code > 0:
+                w = np.ascontiguousarray(np.asarray(weights.blocks[i], dtype=np.float32).reshape(-1, self._blocks[i].shape[1])[:self.T])
+                if w.shape != self._blocks[i].shape:
+                    raise ValueError(f"set_weights: block {i} has shape {w.shape}, need {self._blocks[i].shape}")
+                blocks[i] = w
+        _lib.check(_lib.load().ldpc_decoder_set_weights(self._h, *[b.ctypes.data if b is not None else None for b in blocks]))
+        self._blocks = blocks
+
+    def train_grad(self, llr: torch.Tensor, iter_lo: int = 0, loss_type: int = 2, etha: float = 0.0, iters: int = 0,
+                   want_app: bool = False):
+        """One training batch of the reference (main_Base.py:160-162): returns (loss, {i: grad f32 [T, width]}, app).
+        llr: CUDA float32 [B, N, z] / [B, N*z]; loss over iterations [iter_lo, iters), gradient for their weights."""
+        g = self.graph
+        if not llr.is_cuda or llr.dtype != torch.float32:
+            raise ValueError("train_grad: llr must be a CUDA float32 tensor")
+        B = llr.shape[0]
+        if llr.numel() != B * g.NZ:
+            raise ValueError(f"train_grad: llr has {llr.numel()} elements, expected {B}x{g.NZ}")
+        llr = llr.contiguous()
+        T_run = self.T if iters == 0 else int(iters)
+        grads = [np.zeros_like(b) if b is not None else None for b in self._blocks]
+        app = torch.empty((T_run, B, g.NZ), dtype=torch.float32, device=self.device) if want_app else None
+        loss = ctypes.c_double(0.0)
+        torch.cuda.current_stream(self.device).synchronize()
+        _lib.check(_lib.load().ldpc_train_grad(self._h, _ptr(llr), B, int(iters), int(iter_lo), int(loss_type), float(etha),
+                                               ctypes.byref(loss), *[x.ctypes.data if x is not None else None for x in grads],
+                                               _ptr(app)))
+        return loss.value, {i: x for i, x in enumerate(grads) if x is not None}, app
+
     # -------------------------------------------------------------- compact int8 words (N2)
     @property
     def q8_step(self) -> float:
