@@ -1,13 +1,9 @@
+# one GPU session: parity tests, plain bench, launch list, one full ncu capture of the top kernel
+set -x
 mkdir -p gpurun_out
-timeout 600 python -m pytest tests/test_gpu_train.py -x -q -k short_training 2>&1 | tail -30
-python - <<'PY'
-import sys, os, numpy as np, time
-sys.path.insert(0, 'tools'); sys.path.insert(0, '.')
-import materialize_files
-from ldpc_error_floor_b200 import drivers, trainer
-root='gpurun_out/train_demo'; materialize_files.materialize(root)
-cfg = drivers.RunConfig(root=root, sharing=[3,0,3], decoding_type=2, loss_type=2, etha_start=0.0, iters_max=10, iter_step=10,
-                        batch_size=20, training_num=2000, valid_num=100000, SNR_Matrix=np.array([2.0,2.5,3.0,3.5,4.0]))
-t=time.time(); res = trainer.train_block(cfg, 0, 10, epochs=3, log=None); print('shipped-style config (QMS, FER loss, batch 20): 3 epochs x 100 batches in', round(time.time()-t,1),'s')
-print('losses', res.losses); print('valid FER_last per epoch', [r[1].round(4).tolist() for r in res.valid])
-PY
+python -m pytest tests -m gpu -x -q 2>&1 | tail -3
+python bench.py > gpurun_out/bench_cur.json 2> gpurun_out/bench_cur.err; echo rc=$?
+python bench.py --impl reference --steps 3 --warmup 1 > gpurun_out/bench_ref.json 2>/dev/null
+ncu --metrics gpu__time_duration.sum --clock-control none -c 80 --csv --log-file gpurun_out/launches_cur.csv python bench.py --steps 2 --warmup 3 --frames 262144 --e2e-frames 32768 --skip-cpu > gpurun_out/ncu_l.log 2>&1
+ncu --set full --clock-control none --import-source on -k regex:nms_h2 -s 6 -c 1 -o gpurun_out/prof_cur -f python bench.py --steps 2 --warmup 3 --frames 262144 --e2e-frames 32768 --skip-cpu > gpurun_out/ncu_f.log 2>&1
+python -c "import __graft_entry__ as g; g.smoke()"
