@@ -101,17 +101,26 @@ def cpu_baseline(proto, z, sharing, blocks, words, budget_s=15.0):
     """The C port of the reference arithmetic (oracle/nms_oracle.c) on the box's host cores,
     all threads, on a bounded sample of the SAME workload."""
     from oracle import c_oracle
-    cores = c_oracle.max_threads()
+    cores = host_threads()
     probe = np.ascontiguousarray(np.resize(words, (256,) + words.shape[1:]))
     t0 = time.time()
-    c_oracle.decode(proto, z, probe, sharing, blocks, 20, 2, 5, 20.0, want_all=False)
+    c_oracle.decode(proto, z, probe, sharing, blocks, 20, 2, 5, 20.0, want_all=False, nthreads=cores)
     dt = max(time.time() - t0, 1e-3)
     n = int(min(max(256, 256 * budget_s / dt), 200000))
     sample = np.ascontiguousarray(np.resize(words, (n,) + words.shape[1:]))
     t0 = time.time()
-    c_oracle.decode(proto, z, sample, sharing, blocks, 20, 2, 5, 20.0, want_all=False)
+    c_oracle.decode(proto, z, sample, sharing, blocks, 20, 2, 5, 20.0, want_all=False, nthreads=cores)
     dt = time.time() - t0
     return n / dt, cores, n, dt
+
+
+def host_threads():
+    """All the host threads this process may use -- torchrun exports OMP_NUM_THREADS=1, which would otherwise
+    pin the CPU arm to one core."""
+    try:
+        return max(1, len(os.sched_getaffinity(0)))
+    except AttributeError:
+        return max(1, os.cpu_count() or 1)
 
 
 def synth_words_cpu(n, N, z, seed=1):
@@ -136,10 +145,10 @@ def run_reference(args, rank, emit=print):
     from oracle import c_oracle
     sample = np.ascontiguousarray(np.resize(words, (n,) + words.shape[1:]))
     for _ in range(args.warmup):
-        c_oracle.decode(proto, z, sample[:max(256, n // 8)], sharing, blocks, 20, 2, 5, 20.0, want_all=False)
+        c_oracle.decode(proto, z, sample[:max(256, n // 8)], sharing, blocks, 20, 2, 5, 20.0, want_all=False, nthreads=cores)
     t0 = time.time()
     for _ in range(args.steps):
-        c_oracle.decode(proto, z, sample, sharing, blocks, 20, 2, 5, 20.0, want_all=False)
+        c_oracle.decode(proto, z, sample, sharing, blocks, 20, 2, 5, 20.0, want_all=False, nthreads=cores)
     dt = time.time() - t0
     fps = args.steps * n / dt
     val = fps * k_info / 1e9

@@ -89,6 +89,8 @@ def main(argv=None) -> int:
     ap.add_argument("--min-errors", type=int, default=None)
     ap.add_argument("--no-early-term", action="store_true")
     ap.add_argument("--true-rate", action="store_true", help="sigma from k/n without the reference's +1 quirk")
+    ap.add_argument("--systematic", action="store_true",
+                    help="count errors over the N - M information columns only (main_Base.py:29 systematic = 1)")
     ap.add_argument("--seed", type=int, default=2044)
     ap.add_argument("--chunk", type=int, default=1 << 21)
     ap.add_argument("--harvest", default=None, help="append never-corrected words to this file (Inputs/[Uncor] format)")
@@ -116,12 +118,13 @@ def main(argv=None) -> int:
         ws = formats.read_weights(args.weights)
     else:
         ws = formats.WeightSet([3, 0, 0], {0: np.full((args.iters, 1), args.ms_weight, dtype=np.float32)})
-    dec = NMSDecoder(g, ws, iters=args.iters, decoding_type=args.decoding_type, q_bit=args.q_bit, device=local_rank)
+    dec = NMSDecoder(g, ws, iters=args.iters, decoding_type=args.decoding_type, q_bit=args.q_bit, device=local_rank,
+                     systematic=1 if args.systematic else 0)
     post = None
     if args.post_weights:
         pws = formats.read_weights(args.post_weights)
         post = NMSDecoder(g, pws, iters=args.post_iters or None, decoding_type=args.decoding_type, q_bit=args.q_bit,
-                          device=local_rank)
+                          device=local_rank, systematic=1 if args.systematic else 0)
     if rank == 0:
         print(f"# {g.name or args.graph}: M={g.M} N={g.N} z={g.z} E={g.E} k={g.k_true} n={g.n_true}  kernel {dec.kernel_name}  "
               f"{world} GPU(s)", flush=True)
