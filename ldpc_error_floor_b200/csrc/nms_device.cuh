@@ -105,9 +105,12 @@ __device__ __forceinline__ void gen_llr4(const KParams &P, unsigned long long F,
     for (int h = 0; h < 2; ++h) {
         const float u1 = fmaf((float)r[2 * h], 2.3283064365386963e-10f, 1.1641532182693481e-10f);   // (r+0.5)/2^32
         const float u2 = (float)r[2 * h + 1] * 2.3283064365386963e-10f;
-        const float rad = sqrtf(-2.0f * logf(u1));
+        // hardware log2 / rsqrt / sin / cos (MUFU): ~1e-6 absolute on the normals, far below the quantiser step and
+        // the Monte-Carlo noise; ldpc_llr_generate and the fused loop share this code, so they stay identical
+        const float x = -2.0f * __logf(u1);
+        const float rad = x > 0.0f ? x * rsqrtf(x) : 0.0f;
         float sn, cs;
-        sincospif(2.0f * u2, &sn, &cs);
+        __sincosf(6.283185307179586f * u2, &sn, &cs);
         n[2 * h] = rad * cs;
         n[2 * h + 1] = rad * sn;
     }
@@ -125,6 +128,12 @@ __device__ __forceinline__ void gen_llr4(const KParams &P, unsigned long long F,
 template <bool H2>
 __device__ __forceinline__ void store_xa(const KParams &P, int f, int k, float v) {
     const int j = k / P.z, a = k - j * P.z;
+    if (P.qms) v = fminf(fmaxf(v, -XA_BOUND), XA_BOUND);
+    if (H2) smem_f(P.off_xa + (j * P.LP + a * P.Fp + (f >> 1)) * 2 + (f & 1)) = v;
+    else smem_f(P.off_xa + j * P.LP + a * P.Fp + f) = v;
+}
+template <bool H2>
+__device__ __forceinline__ void store_xa_ja(const KParams &P, int f, int j, int a, float v) {   // bit k = j*z + a
     if (P.qms) v = fminf(fmaxf(v, -XA_BOUND), XA_BOUND);
     if (H2) smem_f(P.off_xa + (j * P.LP + a * P.Fp + (f >> 1)) * 2 + (f & 1)) = v;
     else smem_f(P.off_xa + j * P.LP + a * P.Fp + f) = v;
@@ -238,14 +247,19 @@ __device__ __forceinline__ void nms_decode_body(const KParams &P) {
                 store_xa<H2>(P, f, k, v);
             }
         } else {
-            const int nquads = (P.NZ + 3) >> 2, tot = P.FB * nquads;
-            for (int idx = tid; idx < tot; idx += blockDim.x) {
-                const int f = idx / nquads, quad = idx - f * nquads;
+            const int nquads = (P.NZ + 3) >> 2;
+            int f = tid / nquads, quad = tid - f * nquads;   // (frame, quad) advance incrementally: no division per item
+            while (f < P.FB) {
                 float v[4] = {0.0f, 0.0f, 0.0f, 0.0f};
                 if (f < c.nvalid) gen_llr4(P, P.frame_offset + (unsigned long long)(c.frame0 + f), quad, v);
+                int k = 4 * quad, j = k / P.z, a = k - j * P.z;
 #pragma unroll
-                for (int k4 = 0; k4 < 4; ++k4)
-                    if (4 * quad + k4 < P.NZ) store_xa<H2>(P, f, 4 * quad + k4, v[k4]);
+                for (int k4 = 0; k4 < 4; ++k4, ++k) {
+                    if (k < P.NZ) store_xa_ja<H2>(P, f, j, a, v[k4]);
+                    if (++a == P.z) { a = 0; ++j; }
+                }
+                quad += blockDim.x;
+                while (quad >= nquads) { quad -= nquads; ++f; }
             }
         }
         for (int idx = tid; idx < NMS_MISC_WORDS; idx += blockDim.x) misc[idx] = 0;
@@ -278,7 +292,11 @@ __device__ __forceinline__ void nms_decode_body(const KParams &P) {
             uint32_t bad = 0;
             Policy::cn_phase(P, c, t, bad);
             if (t >= 1) publish(P, c, MISC_SYND + (t & 1) * 2, bad, H2);
-            __syncthreads();   // A
+            // A.  With early termination the barrier also tells whether ANY frame of the CTA still violates a check:
+            // if none does, every running frame stops here and the VN phase of this iteration is not needed
+            bool all_clean = false;
+            if (P.early_term && t >= 1) all_clean = __syncthreads_or(c.act && (bad & (H2 ? LSB2 : 1u)) != 0u) == 0;
+            else __syncthreads();
             // ======== per-frame bookkeeping for APP_{t-1} (threads 0..63), concurrent with the VN phase
             if (tid < 64) {
                 bool newly = false;
@@ -309,6 +327,14 @@ __device__ __forceinline__ void nms_decode_body(const KParams &P) {
                         ctrl[CTRL_FROZEN + (t & 1) * 2 + c.warp] = fm;
                     }
                 }
+            }
+            if (all_clean) {
+                __syncthreads();   // the bookkeeping's control words
+                const uint32_t nm[2] = {ctrl[CTRL_NEWLY], ctrl[CTRL_NEWLY + 1]};
+                const uint32_t no[2] = {ctrl[CTRL_NEWONES], ctrl[CTRL_NEWONES + 1]};
+                if (nm[0] | nm[1]) copy_out<H2>(P, c, nm, no, (t + 1) & 1);   // hard bits of APP_{t-1}
+                alldone = true;
+                break;
             }
             // ======== VN phase (hard-decision ballots only when a copy-out can follow)
             uint32_t ones = 0;
