@@ -35,6 +35,11 @@ GEOMETRIES = {
     "mackay": [(32, 8)],
     "bch": [(32, 4)],
 }
+# float32 kernels (one frame per lane): same lanes as the packed choice
+GEOMETRIES_F32 = {
+    "wimax": [(4, 2)], "wifi": [(7, 2)], "5g_r073_z72": [(3, 2)], "5g_r050_z64": [(2, 2)], "5g_r050_z32": [(4, 2)],
+    "5g_r033_z32": [(4, 2)], "5g_r073_z32": [(4, 2)],
+}   # the z = 1 codes (MacKay, BCH) stay on the generic float kernels: unrolling 48-96 nodes costs minutes of compile time
 SKIP = {"polar"}   # row degree 64 > 32: generic two-pass kernel
 
 
@@ -94,7 +99,7 @@ def arr(name, vals, ty="short"):
     return f"    static constexpr {ty} {name}[{max(len(vals), 1)}] = {{{', '.join(str(int(v)) for v in vals) or '0'}}};"
 
 
-def emit(key, proto, z, Fp, R, outdir):
+def emit(key, proto, z, Fp, R, outdir, f32=False):
     M, N = proto.shape
     row, col, shift, row_ptr = [], [], [], [0]
     for i in range(M):
@@ -125,9 +130,41 @@ def emit(key, proto, z, Fp, R, outdir):
     vn_rot = [(L - shift[col_edge[k]] * Fp) % L for k in range(E)]
     threads = C * R * 32
     smem = layout(E, N, LP, C, 256)[-1] * 4
+    if f32:   # msg + xa + xq (one word each) + ballots + weights + misc
+        smem = (E * LP + 2 * N * LP + 2 * N * C + 256 + MISC_WORDS) * 4
     # resident CTAs the kernel is compiled for: shared memory, threads, and >= 56 registers per thread
     minb = max(1, min(MAX_SMEM // (smem + 1024), 2048 // threads, 65536 // (threads * 56)))
     name = f"{key}_fp{Fp}_r{R}"
+    e_sF = [shift[e] * Fp for e in range(E)]
+    if f32:
+        src = f"""// GENERATED by gen_spec.py -- do not edit.  Graph "{key}": {M}x{N}, z={z}, E={E}; float32 geometry Fp={Fp} R={R}.
+#include "../nms_f32_spec.cuh"
+
+namespace nms {{
+struct GF_{name} {{
+    static constexpr int M = {M}, N = {N}, E = {E}, z = {z}, Fp = {Fp}, L = {L}, LP = {LP}, C = {C}, R = {R};
+{arr('row_ptr', row_ptr)}
+{arr('col_ptr', col_ptr)}
+{arr('cn_order', cn_order)}
+{arr('vn_order', vn_order)}
+{arr('vn_e', vn_e)}
+{arr('vn_rot', vn_rot)}
+{arr('e_col', col)}
+{arr('e_sF', e_sF)}
+}};
+
+__global__ void __launch_bounds__({threads}, {minb}) nms_f32_spec_{name}(const __grid_constant__ KParams P) {{
+    nms_decode_body<F32SpecPolicy<GF_{name}>>(P);
+}}
+}}   // namespace nms
+
+extern "C" const void *nms_spec_f32_func_{name}() {{ return (const void *)nms::nms_f32_spec_{name}; }}
+"""
+        path = os.path.join(outdir, f"spec_f32_{name}.cu")
+        old = open(path).read() if os.path.exists(path) else None
+        if old != src:
+            open(path, "w").write(src)
+        return dict(name=name, hash=fnv1a(M, N, z, proto), M=M, N=N, z=z, E=E, Fp=Fp, R=R, path=path)
     h = fnv1a(M, N, z, proto)
     src = f"""// GENERATED by gen_spec.py -- do not edit.  Graph "{key}": {M}x{N}, z={z}, E={E}; geometry Fp={Fp} R={R}.
 #include "../nms_h2_spec.cuh"
@@ -177,7 +214,24 @@ def main():
             e = emit(key, proto, z, Fp, R, outdir)
             if e:
                 entries.append(e)
+    entries32 = []
+    for key in keys:
+        if key in SKIP or key not in GEOMETRIES_F32:
+            continue
+        proto = d[f"graph/{key}/proto"].astype(np.int64)
+        z = int(d[f"graph/{key}/meta"][0])
+        for Fp, R in GEOMETRIES_F32[key]:
+            e = emit(key, proto, z, Fp, R, outdir, f32=True)
+            if e:
+                entries32.append(e)
     reg = ["// GENERATED by gen_spec.py -- do not edit.", '#include "../nms_common.cuh"', ""]
+    reg += [f'extern "C" const void *nms_spec_f32_func_{e["name"]}();' for e in entries32]
+    reg += ["", "static const NmsSpecEntry g_spec_f32[] = {"]
+    reg += [f'    {{"{e["name"]}", 0x{e["hash"]:016x}ull, {e["M"]}, {e["N"]}, {e["z"]}, {e["E"]}, {e["Fp"]}, {e["R"]}, '
+            f'nms_spec_f32_func_{e["name"]}}},' for e in entries32]
+    reg += ["    {nullptr, 0ull, 0, 0, 0, 0, 0, 0, nullptr}", "};", "",
+            'extern "C" const NmsSpecEntry *nms_spec_f32_table(int *count) {',
+            f"    if (count) *count = {len(entries32)};", "    return g_spec_f32;", "}", ""]
     reg += [f'extern "C" const void *nms_spec_func_{e["name"]}();' for e in entries]
     reg += ["", "static const NmsSpecEntry g_spec[] = {"]
     reg += [f'    {{"{e["name"]}", 0x{e["hash"]:016x}ull, {e["M"]}, {e["N"]}, {e["z"]}, {e["E"]}, {e["Fp"]}, {e["R"]}, '
@@ -189,7 +243,7 @@ def main():
     txt = "\n".join(reg)
     if not os.path.exists(rpath) or open(rpath).read() != txt:
         open(rpath, "w").write(txt)
-    for e in entries:
+    for e in entries + entries32:
         print(os.path.basename(e["path"]))
     print("spec_registry.cu")
 

@@ -434,6 +434,20 @@ extern "C" int ldpc_decoder_create2(const ldpc_graph_t *g, const int32_t sharing
             }
         }
     }
+    if (!d->packed && !env_on("LDPC_B200_NO_SPEC")) {   // graph-specialised float32 kernel
+        int n = 0;
+        const NmsSpecEntry *tab = nms_spec_f32_table(&n);
+        const unsigned long long h = graph_hash(d->g);
+        for (int k = 0; k < n; ++k) {
+            if (tab[k].graph_hash != h || tab[k].M != g->M || tab[k].N != g->N || tab[k].z != g->z) continue;
+            const void *f = tab[k].func();
+            LaunchGeom geo{};
+            if (choose_geometry(d->g, false, qms, w_words, f, tab[k].Fp, tab[k].R, 32, &geo) == LDPC_OK) {
+                d->func = f; d->geom = geo; d->spec_name = tab[k].name; rc = LDPC_OK;
+                break;
+            }
+        }
+    }
     if (d->func == nullptr) {
         d->func = pick_kernel(d->packed, g->info.max_dc, g->info.max_dv, &d->dcb, &d->dvb);
         rc = choose_geometry(d->g, d->packed, qms, w_words, d->func, 0, 0, 16, &d->geom);   // generic kernels: __launch_bounds__(512)
@@ -445,6 +459,7 @@ extern "C" int ldpc_decoder_create2(const ldpc_graph_t *g, const int32_t sharing
     P.M = g->M; P.N = g->N; P.E = g->E; P.z = g->z; P.NZ = g->N * g->z;
     P.Fp = d->geom.Fp; P.FB = d->geom.FB; P.L = d->geom.L; P.LP = d->geom.LP; P.C = d->geom.C; P.R = d->geom.R;
     P.qms = qms; P.qmagic = 12582912.0f / qk; P.qmax = qmax; P.clip = clip_llr;
+    P.sat_magic = qms ? P.qmagic : 0.0f; P.sat_bound = qms ? qmax : clip_llr;
     P.sharing0 = sharing[0]; P.sharing1 = sharing[1]; P.sharing2 = sharing[2];
     P.wc = wc; P.wu = wu; P.wv = wv;
     P.w_words = (int)wh.size(); P.w_staged = P.w_words > 0 && P.w_words <= NMS_WSTAGE_MAX_WORDS;
@@ -539,7 +554,7 @@ extern "C" int ldpc_decoder_uses_packed_kernel(const ldpc_decoder_t *d) { return
 extern "C" const char *ldpc_decoder_kernel_name(const ldpc_decoder_t *d) {
     static thread_local char buf[96];
     if (!d) return "";
-    if (d->spec_name) snprintf(buf, sizeof buf, "nms_h2_spec_%s", d->spec_name);
+    if (d->spec_name) snprintf(buf, sizeof buf, "nms_%s_spec_%s", d->packed ? "h2" : "f32", d->spec_name);
     else snprintf(buf, sizeof buf, "nms_%s_kernel_%d_%d", d->packed ? "h2" : "f32", d->dcb, d->dvb);
     return buf;
 }

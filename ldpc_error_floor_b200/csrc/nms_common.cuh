@@ -35,6 +35,9 @@ struct KParams {
     float qmagic;      // 1.5*2^23/qk: (x + qmagic) - qmagic rounds x half-to-even to the quantiser step 1/qk
     float qmax;        // Q(x) = clamp(round_to_step(x), +-qmax)            (Main_Functions.py:483-492)
     float clip;        // clip_LLR (main_Base.py:69)
+    // message saturation without a mode branch: sat(x) = clamp((x + sat_magic) - sat_magic, +-sat_bound) is Q(x) on the
+    // quantised path (qmagic, qmax) and clip(x, +-clip_LLR) on the float path (0, clip)
+    float sat_magic, sat_bound;
     int sharing0, sharing1, sharing2;
     int wc, wu, wv;    // weight row widths
     const float *w_all;   // device [T*wc | T*wu | T*wv]
@@ -88,6 +91,7 @@ struct NmsSpecEntry {
     const void *(*func)();
 };
 extern "C" const NmsSpecEntry *nms_spec_table(int *count);
+extern "C" const NmsSpecEntry *nms_spec_f32_table(int *count);
 
 // ---- Philox4x32-10 (Salmon et al., SC'11), written out so the host tests can restate it
 __host__ __device__ __forceinline__ void philox4x32_10(uint32_t c0, uint32_t c1, uint32_t c2, uint32_t c3,
