@@ -37,7 +37,7 @@ GEOMETRIES = {
 }
 # float32 kernels (one frame per lane): same lanes as the packed choice
 GEOMETRIES_F32 = {
-    "wimax": [(4, 2)], "wifi": [(7, 2)], "5g_r073_z72": [(3, 2)], "5g_r050_z64": [(2, 2)], "5g_r050_z32": [(4, 2)],
+    "wimax": [(4, 2), (4, 3), (4, 1), (8, 2), (8, 1), (2, 4)], "wifi": [(7, 2)], "5g_r073_z72": [(3, 2), (4, 2), (4, 1)], "5g_r050_z64": [(2, 2), (4, 1), (4, 2)], "5g_r050_z32": [(4, 2)],
     "5g_r033_z32": [(4, 2)], "5g_r073_z32": [(4, 2)],
 }   # the z = 1 codes (MacKay, BCH) stay on the generic float kernels: unrolling 48-96 nodes costs minutes of compile time
 SKIP = {"polar"}   # row degree 64 > 32: generic two-pass kernel
@@ -130,13 +130,11 @@ def emit(key, proto, z, Fp, R, outdir, f32=False):
     vn_rot = [(L - shift[col_edge[k]] * Fp) % L for k in range(E)]
     threads = C * R * 32
     smem = layout(E, N, LP, C, 256)[-1] * 4
-    if f32:   # msg + xa + xq (one word each) + ballots + weights + misc
-        smem = (E * LP + 2 * N * LP + 2 * N * C + 256 + MISC_WORDS) * 4
-    # resident CTAs the kernel is compiled for: shared memory, threads, and >= 56 registers per thread
-    minb = max(1, min(MAX_SMEM // (smem + 1024), 2048 // threads, 65536 // (threads * 56)))
     name = f"{key}_fp{Fp}_r{R}"
-    e_sF = [shift[e] * Fp for e in range(E)]
     if f32:
+        # float path: msg + xa + ballots + weights + misc; the quantised twin adds the xq array
+        words = E * LP + N * LP + 2 * N * C + E + 1 + 256 + MISC_WORDS
+        mb = [max(1, min(MAX_SMEM // (w * 4 + 1024), 2048 // threads, 65536 // (threads * 56))) for w in (words, words + N * LP)]
         src = f"""// GENERATED by gen_spec.py -- do not edit.  Graph "{key}": {M}x{N}, z={z}, E={E}; float32 geometry Fp={Fp} R={R}.
 #include "../nms_f32_spec.cuh"
 
@@ -149,22 +147,28 @@ struct GF_{name} {{
 {arr('vn_order', vn_order)}
 {arr('vn_e', vn_e)}
 {arr('vn_rot', vn_rot)}
-{arr('e_col', col)}
-{arr('e_sF', e_sF)}
+    static constexpr int NDEG = {len(sorted(set(dc)))}, DVMAX = {max(dv)};
+{arr('cn_degs', sorted(set(dc)))}
 }};
 
-__global__ void __launch_bounds__({threads}, {minb}) nms_f32_spec_{name}(const __grid_constant__ KParams P) {{
-    nms_decode_body<F32SpecPolicy<GF_{name}>>(P);
+__global__ void __launch_bounds__({threads}, {mb[0]}) nms_f32_spec_{name}(const __grid_constant__ KParams P) {{
+    nms_decode_body<F32SpecPolicy<GF_{name}, 0>>(P);
+}}
+__global__ void __launch_bounds__({threads}, {mb[1]}) nms_f32q_spec_{name}(const __grid_constant__ KParams P) {{
+    nms_decode_body<F32SpecPolicy<GF_{name}, 1>>(P);
 }}
 }}   // namespace nms
 
 extern "C" const void *nms_spec_f32_func_{name}() {{ return (const void *)nms::nms_f32_spec_{name}; }}
+extern "C" const void *nms_spec_f32q_func_{name}() {{ return (const void *)nms::nms_f32q_spec_{name}; }}
 """
         path = os.path.join(outdir, f"spec_f32_{name}.cu")
         old = open(path).read() if os.path.exists(path) else None
         if old != src:
             open(path, "w").write(src)
         return dict(name=name, hash=fnv1a(M, N, z, proto), M=M, N=N, z=z, E=E, Fp=Fp, R=R, path=path)
+    # resident CTAs the kernel is compiled for: shared memory, threads, and >= 56 registers per thread
+    minb = max(1, min(MAX_SMEM // (smem + 1024), 2048 // threads, 65536 // (threads * 56)))
     h = fnv1a(M, N, z, proto)
     src = f"""// GENERATED by gen_spec.py -- do not edit.  Graph "{key}": {M}x{N}, z={z}, E={E}; geometry Fp={Fp} R={R}.
 #include "../nms_h2_spec.cuh"
@@ -225,13 +229,14 @@ def main():
             if e:
                 entries32.append(e)
     reg = ["// GENERATED by gen_spec.py -- do not edit.", '#include "../nms_common.cuh"', ""]
-    reg += [f'extern "C" const void *nms_spec_f32_func_{e["name"]}();' for e in entries32]
-    reg += ["", "static const NmsSpecEntry g_spec_f32[] = {"]
-    reg += [f'    {{"{e["name"]}", 0x{e["hash"]:016x}ull, {e["M"]}, {e["N"]}, {e["z"]}, {e["E"]}, {e["Fp"]}, {e["R"]}, '
-            f'nms_spec_f32_func_{e["name"]}}},' for e in entries32]
-    reg += ["    {nullptr, 0ull, 0, 0, 0, 0, 0, 0, nullptr}", "};", "",
-            'extern "C" const NmsSpecEntry *nms_spec_f32_table(int *count) {',
-            f"    if (count) *count = {len(entries32)};", "    return g_spec_f32;", "}", ""]
+    for tag in ("f32", "f32q"):
+        reg += [f'extern "C" const void *nms_spec_{tag}_func_{e["name"]}();' for e in entries32]
+        reg += ["", f"static const NmsSpecEntry g_spec_{tag}[] = {{"]
+        reg += [f'    {{"{e["name"]}", 0x{e["hash"]:016x}ull, {e["M"]}, {e["N"]}, {e["z"]}, {e["E"]}, {e["Fp"]}, {e["R"]}, '
+                f'nms_spec_{tag}_func_{e["name"]}}},' for e in entries32]
+        reg += ["    {nullptr, 0ull, 0, 0, 0, 0, 0, 0, nullptr}", "};", "",
+                f'extern "C" const NmsSpecEntry *nms_spec_{tag}_table(int *count) {{',
+                f"    if (count) *count = {len(entries32)};", f"    return g_spec_{tag};", "}", ""]
     reg += [f'extern "C" const void *nms_spec_func_{e["name"]}();' for e in entries]
     reg += ["", "static const NmsSpecEntry g_spec[] = {"]
     reg += [f'    {{"{e["name"]}", 0x{e["hash"]:016x}ull, {e["M"]}, {e["N"]}, {e["z"]}, {e["E"]}, {e["Fp"]}, {e["R"]}, '

@@ -258,6 +258,7 @@ void fill_smem_layout(KParams *P, bool packed) {
     P->off_xa = off; off += P->N * P->LP * (packed ? 2 : 1);
     P->off_xq = off; off += (packed || P->qms) ? P->N * P->LP : 0;
     P->off_hb = off; off += 2 * (packed ? 2 : 1) * P->N * P->C;
+    P->off_et = off; off += packed ? 0 : P->E + 1;
     P->off_w = off; off += P->w_staged ? P->w_words : 0;
     P->off_misc = off; off += NMS_MISC_WORDS;
     P->smem_words = off;
@@ -434,12 +435,16 @@ extern "C" int ldpc_decoder_create2(const ldpc_graph_t *g, const int32_t sharing
             }
         }
     }
-    if (!d->packed && !env_on("LDPC_B200_NO_SPEC")) {   // graph-specialised float32 kernel
+    // graph-specialised float32 kernel (float / quantised twin); it reads its weights from shared memory
+    if (!d->packed && w_words <= NMS_WSTAGE_MAX_WORDS && !env_on("LDPC_B200_NO_SPEC")) {
         int n = 0;
-        const NmsSpecEntry *tab = nms_spec_f32_table(&n);
+        const NmsSpecEntry *tab = qms ? nms_spec_f32q_table(&n) : nms_spec_f32_table(&n);
         const unsigned long long h = graph_hash(d->g);
+        const int want_fp = getenv("LDPC_B200_FP") ? atoi(getenv("LDPC_B200_FP")) : 0;
+        const int want_r = getenv("LDPC_B200_R") ? atoi(getenv("LDPC_B200_R")) : 0;
         for (int k = 0; k < n; ++k) {
             if (tab[k].graph_hash != h || tab[k].M != g->M || tab[k].N != g->N || tab[k].z != g->z) continue;
+            if ((want_fp && tab[k].Fp != want_fp) || (want_r && tab[k].R != want_r)) continue;   // tuning override
             const void *f = tab[k].func();
             LaunchGeom geo{};
             if (choose_geometry(d->g, false, qms, w_words, f, tab[k].Fp, tab[k].R, 32, &geo) == LDPC_OK) {
@@ -506,10 +511,9 @@ extern "C" int ldpc_decoder_create2(const ldpc_graph_t *g, const int32_t sharing
     }
     for (int k = 0; k < g->E; ++k) {
         const int e = g->col_edge[k];
-        // variable lane q -> check lane (q - s*Fp) mod L; packed kernels address shared memory in bytes
-        const int unit = d->packed ? 4 : 1;
-        P.vn_edge[k].x = e * P.LP * unit;
-        P.vn_edge[k].y = ((P.L - g->shift[e] * P.Fp) % P.L) * unit;
+        // variable lane q -> check lane (q - s*Fp) mod L, as byte offsets into shared memory
+        P.vn_edge[k].x = e * P.LP * 4;
+        P.vn_edge[k].y = ((P.L - g->shift[e] * P.Fp) % P.L) * 4;
     }
     if (!wh.empty()) {
         if (cudaMalloc(&d->d_w, wh.size() * sizeof(float)) != cudaSuccess ||
@@ -554,7 +558,7 @@ extern "C" int ldpc_decoder_uses_packed_kernel(const ldpc_decoder_t *d) { return
 extern "C" const char *ldpc_decoder_kernel_name(const ldpc_decoder_t *d) {
     static thread_local char buf[96];
     if (!d) return "";
-    if (d->spec_name) snprintf(buf, sizeof buf, "nms_%s_spec_%s", d->packed ? "h2" : "f32", d->spec_name);
+    if (d->spec_name) snprintf(buf, sizeof buf, "nms_%s_spec_%s", d->packed ? "h2" : (d->decoding_type == 2 ? "f32q" : "f32"), d->spec_name);
     else snprintf(buf, sizeof buf, "nms_%s_kernel_%d_%d", d->packed ? "h2" : "f32", d->dcb, d->dvb);
     return buf;
 }

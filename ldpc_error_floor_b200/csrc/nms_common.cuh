@@ -65,7 +65,7 @@ struct KParams {
     unsigned long long *counters;
     float *uncor_buf; unsigned int *uncor_count; unsigned int uncor_cap; int harvest_mode;
     // shared-memory carve-up (word offsets; the message array always starts at word 0)
-    int off_xa, off_xq, off_hb, off_w, off_misc, smem_words;
+    int off_xa, off_xq, off_hb, off_et, off_w, off_misc, smem_words;   // off_et: float kernels only (E words)
     // tables
     unsigned short row_ptr[LDPC_MAX_M + 1];   // E(C) edges of proto row i: [row_ptr[i], row_ptr[i+1])
     unsigned short col_ptr[LDPC_MAX_N + 1];   // CSR by proto column into vn_edge
@@ -76,7 +76,7 @@ struct KParams {
     uint2 cn_task[LDPC_MAX_M];                // slot-major row list: [slot * ceil(M/R) + n] = {e0*LP*4, dc | row << 16}; dc 0 = none
     unsigned short e_col[LDPC_MAX_E];         // proto column of E(C) edge e
     unsigned short e_sF[LDPC_MAX_E];          // s_e*Fp: check lane q -> variable lane (q + sF) mod L
-    int2 vn_edge[LDPC_MAX_E];                 // column-sorted: {e*LP, (L - s_e*Fp) mod L} in words (float kernel) / bytes (packed)
+    int2 vn_edge[LDPC_MAX_E];                 // column-sorted: {e*LP*4, ((L - s_e*Fp) mod L)*4}: byte offsets
 };
 
 struct LaunchGeom {
@@ -91,7 +91,8 @@ struct NmsSpecEntry {
     const void *(*func)();
 };
 extern "C" const NmsSpecEntry *nms_spec_table(int *count);
-extern "C" const NmsSpecEntry *nms_spec_f32_table(int *count);
+extern "C" const NmsSpecEntry *nms_spec_f32_table(int *count);    // float path (decoding_type 1)
+extern "C" const NmsSpecEntry *nms_spec_f32q_table(int *count);   // quantised twin (q_bit 6, per-edge weights)
 
 // ---- Philox4x32-10 (Salmon et al., SC'11), written out so the host tests can restate it
 __host__ __device__ __forceinline__ void philox4x32_10(uint32_t c0, uint32_t c1, uint32_t c2, uint32_t c3,

@@ -74,13 +74,6 @@ struct Ctx {
     int nvalid;
 };
 
-// variable lane q -> word index of the message of CSR entry `ve` (rotation into the check lane frame)
-__device__ __forceinline__ int vn_addr(const Ctx &c, int2 ve, int L) {
-    int qq = c.q + ve.y * c.act;
-    qq = (qq >= c.Lthr) ? qq - L : qq;
-    return ve.x + qq;
-}
-
 // is frame f frozen as far as the VN phase of iteration t can tell?  (only used for the optional APP output)
 __device__ __forceinline__ bool app_frozen(const KParams &P, int t, int f) {
     const uint32_t *misc = nms_smem + P.off_misc;
@@ -130,13 +123,13 @@ __device__ __forceinline__ void store_xa(const KParams &P, int f, int k, float v
     const int j = k / P.z, a = k - j * P.z;
     if (P.qms) v = fminf(fmaxf(v, -XA_BOUND), XA_BOUND);
     if (H2) smem_f(P.off_xa + (j * P.LP + a * P.Fp + (f >> 1)) * 2 + (f & 1)) = v;
-    else smem_f(P.off_xa + j * P.LP + a * P.Fp + f) = v;
+    else smem_f(P.off_xa + j * P.LP + a * P.Fp + f) = __fadd_rn(v, 0.0f);   // float kernels: never -0.0 (nms_f32.cuh)
 }
 template <bool H2>
 __device__ __forceinline__ void store_xa_ja(const KParams &P, int f, int j, int a, float v) {   // bit k = j*z + a
     if (P.qms) v = fminf(fmaxf(v, -XA_BOUND), XA_BOUND);
     if (H2) smem_f(P.off_xa + (j * P.LP + a * P.Fp + (f >> 1)) * 2 + (f & 1)) = v;
-    else smem_f(P.off_xa + j * P.LP + a * P.Fp + f) = v;
+    else smem_f(P.off_xa + j * P.LP + a * P.Fp + f) = __fadd_rn(v, 0.0f);
 }
 template <bool H2>
 __device__ __forceinline__ float load_xa(const KParams &P, int f, int k) {
@@ -225,6 +218,12 @@ __device__ __forceinline__ void nms_decode_body(const KParams &P) {
     // padding lanes read their own (otherwise unused) words: give those defined contents once
     if (P.LP != P.L) {
         for (int idx = tid; idx < P.off_hb; idx += blockDim.x) nms_smem[idx] = 0u;
+    }
+    // float kernels: per-edge table of the syndrome pass {column * C | s_e*Fp << 16} (nms_f32.cuh)
+    // followed by one word holding 1.0f (the "no weight" row of the specialised float kernels)
+    if constexpr (!H2) {
+        for (int e = tid; e < P.E; e += blockDim.x) nms_smem[P.off_et + e] = (uint32_t)(P.e_col[e] * P.C) | ((uint32_t)P.e_sF[e] << 16);
+        if (tid == 0) nms_smem[P.off_et + P.E] = __float_as_uint(1.0f);
     }
 
     for (long long batch = blockIdx.x; batch < nbatches; batch += gridDim.x) {
@@ -338,7 +337,7 @@ __device__ __forceinline__ void nms_decode_body(const KParams &P) {
             }
             // ======== VN phase (hard-decision ballots only when a copy-out can follow)
             uint32_t ones = 0;
-            const bool need_hb = !H2 || P.early_term || t == P.T_run - 1;
+            const bool need_hb = !H2 || P.early_term || t == P.T_run - 1;   // float kernels: always (their syndrome reads the ballots)
             Policy::template vn_phase<false>(P, c, t, need_hb, ones);
             publish(P, c, MISC_ONES + (t & 1) * 2, ones, H2);
             __syncthreads();   // B

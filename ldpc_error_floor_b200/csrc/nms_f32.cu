@@ -1,12 +1,9 @@
-// nms_f32.cu -- float32 arithmetic back-end (one frame per 32-bit word): every reference mode.
+// nms_f32.cu -- float32 arithmetic back-end (one frame per 32-bit word), generic kernels: any base graph.
 //
-// Compiled once per degree bucket like nms_h2.cu (-DNMS_DCB / -DNMS_DVB, 0/0 = any degree).
-// Serves decoding_type 1 (min-sum, clip +-clip_LLR) and every quantised configuration the
-// packed kernel does not take (q_bit 6, per-edge weights).  Operation order follows the TF
-// graph: direct extrinsic V->C sums in ascending E(C) order (Main_Functions.py:213-215), the
-// 1e-4 zero / minimum rules (:230, :250), |.|*w -> ReLU -> clip/quantise -> sign (:267-316),
-// APP = clip(xq + sum) (:317-325).  Hard decisions are kept as ballot words per (column, lane
-// chunk) so the CN phase can form the syndrome of the previous iteration exactly.
+// Compiled once per degree bucket like nms_h2.cu (-DNMS_DCB / -DNMS_DVB, 0/0 = any degree).  Serves decoding_type 1
+// (min-sum, clip +-clip_LLR) and every quantised configuration the packed kernel does not take (q_bit 6, per-edge
+// weights) for graphs without a specialised kernel (nms_f32_spec.cuh); the arithmetic is the shared code of
+// nms_f32.cuh, so both kernel families give identical results.
 #include "nms_f32.cuh"
 
 #ifndef NMS_DCB
@@ -24,16 +21,25 @@ struct F32Policy {
     static constexpr bool FUSED_LOAD = false;
 
     static __device__ __forceinline__ void cn_phase(const KParams &P, const Ctx &c, int t, uint32_t &bad) {
+        const F32Ctx h = f32_ctx(P, c);
+        const uint32_t a00 = h.sb + h.q4, stride4 = (uint32_t)P.LP * 4u;
+        const uint32_t hb4 = h.sb + (uint32_t)(P.off_hb + ((t + 1) & 1) * P.N * P.C) * 4u;   // hard bits of APP_{t-1} (init pass: buffer 1)
+        const bool pad = P.L != P.LP;
         for (int n = c.slot; n < P.M; n += P.R) {
             const int i = P.cn_order[n];
-            if constexpr (DCB == 0) {
-                cn_row_f32_generic(P, c, i, t, bad);
+            const int e0 = P.row_ptr[i], dc = P.row_ptr[i + 1] - e0;
+            const uint32_t a0 = a00 + (uint32_t)e0 * stride4;
+            const uint32_t par = pad ? f32_row_syndrome<true>(P, h, hb4, e0, dc) : f32_row_syndrome<false>(P, h, hb4, e0, dc);
+            bad |= par;
+            if (DCB == 0 || P.sharing0 == 1) {
+                cn_row_f32_generic<2>(P, a0, stride4, dc, t, i, e0, par);
             } else {
-                const int dc = P.row_ptr[i + 1] - P.row_ptr[i];
+                float w0, w1;
+                f32_row_weights(P, t, i, w0, w1);
                 switch (dc) {
-#define X(p)                                                        \
-    case (p) + 1:                                                   \
-        if constexpr ((p) < DCB) cn_row_f32<(p) + 1>(P, c, i, t, bad); \
+#define X(p)                                                                       \
+    case (p) + 1:                                                                  \
+        if constexpr ((p) < DCB) cn_row_f32<(p) + 1, 2>(P, a0, stride4, w0, w1, par); \
         break;
                     NMS_REP_DESC(X)
 #undef X
@@ -45,36 +51,11 @@ struct F32Policy {
 
     template <bool INIT>
     static __device__ __forceinline__ void vn_phase(const KParams &P, const Ctx &c, int t, bool need_hb, uint32_t &ones) {
-        for (int n = c.slot; n < P.N; n += P.R) {
-            const int j = P.vn_order[n];
-            if constexpr (DVB == 0) {
-                vn_col_f32_generic<INIT>(P, c, j, t, ones);
-            } else {
-                const int dv = P.col_ptr[j + 1] - P.col_ptr[j];
-                switch (dv) {
-#define X(p)                                                                 \
-    case (p) + 1:                                                            \
-        if constexpr ((p) < DVB) vn_col_f32<(p) + 1, INIT>(P, c, j, t, ones); \
-        break;
-                    NMS_REP_DESC(X)
-#undef X
-                default: break;
-                }
-            }
-        }
+        const F32Ctx h = f32_ctx(P, c);
+        f32_vn_phase_tab<DVB, INIT, 2>(P, c, h, t, need_hb, ones);
     }
 
-    static __device__ __forceinline__ uint32_t synd_phase(const KParams &P, const Ctx &c, int tl) {
-        uint32_t bad = 0;
-        for (int n = c.slot; n < P.M; n += P.R) {
-            const int i = P.cn_order[n];
-            const int e0 = P.row_ptr[i], dc = P.row_ptr[i + 1] - e0;
-            uint32_t par = 0;
-            for (int p = 0; p < dc; ++p) par ^= f32_hbit(P, c, (tl + 1) & 1, e0 + p);
-            bad |= par;
-        }
-        return bad;
-    }
+    static __device__ __forceinline__ uint32_t synd_phase(const KParams &P, const Ctx &c, int tl) { return f32_synd_phase(P, c, (tl + 1) & 1); }
 };
 
 #define NMS_CAT2(a, b, c, d) a##b##c##d

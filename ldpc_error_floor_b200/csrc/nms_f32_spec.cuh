@@ -1,144 +1,137 @@
-// nms_f32_spec.cuh -- graph-specialised float32 kernels (one frame per 32-bit lane): the float min-sum path
-// (decoding_type 1) and the quantised modes the packed kernels do not take (q_bit 6, per-edge weights), for the base
-// graphs known at build time.  Same structure as nms_h2_spec.cuh: every row / column offset, degree and circulant
-// rotation is an immediate, the VN phase is unrolled per column, the prologue takes the channel LLRs straight from
-// global memory.  The arithmetic is the reference-ordered code of nms_f32.cu (direct extrinsic sums in ascending
-// E(C) order, the 1e-4 rules, |.|*w -> ReLU -> saturate -> sign), so results equal the generic float kernels bit for
-// bit.  Hard decisions travel as ballot words per (column, lane chunk); the previous syndrome a check needs for its
-// unsatisfied-check weight is the parity of those bits at the rotated lanes.
+// nms_f32_spec.cuh -- graph-specialised float32 kernels (one frame per 32-bit lane) for the base graphs known at
+// build time: the float min-sum path (decoding_type 1; QM = 0) and the quantised modes the packed kernels do not take
+// (q_bit 6, per-edge weights; QM = 1).  Same structure as nms_h2_spec.cuh:
+//   * VN phase unrolled per column, every message row offset and circulant rotation an immediate, no branches; the
+//     same column code serves the iteration loop (with or without hard-decision ballots), and the fused "channel
+//     LLRs from global memory -> first V->C messages" prologue;
+//   * CN phase: one body per distinct row degree, rows from the host-built task table -- the iteration loop stays
+//     inside the 32 KB instruction cache (a fully unrolled CN phase stalled 58 % of the issue slots on fetch);
+//   * final syndrome pass unrolled per row.
+// The arithmetic is the shared code of nms_f32.cuh, so results equal the generic float kernels bit for bit.
 #pragma once
 #include "nms_f32.cuh"
 
 namespace nms {
 
-template <class G>
+template <class G, int ROT>
+__device__ __forceinline__ uint32_t f32_spec_rot(const F32Ctx &h) {
+    if constexpr (ROT == 0) {
+        return h.q4;
+    } else if constexpr (G::L == G::LP) {
+        if constexpr ((G::L & (G::L - 1)) == 0) return (h.q4 + ROT * 4u) & (G::L * 4u - 1u);
+        else return f32_rot<false>(h, ROT * 4u, G::L * 4u);
+    } else {
+        return f32_rot<true>(h, ROT * 4u, G::L * 4u);
+    }
+}
+
+template <class G, int QM>
 struct F32SpecPolicy {
     static constexpr bool H2 = false;
     static constexpr bool FUSED_LOAD = true;
+    static constexpr uint32_t LP4 = G::LP * 4u;
     static constexpr bool PAD = G::L != G::LP;
-
-    // lane q -> (q + ROT) mod L in words; padding lanes stay put
-    template <int ROT>
-    static __device__ __forceinline__ int rot(const Ctx &c) {
-        if constexpr (ROT == 0) return c.q;
-        int qq = c.q + (PAD ? ROT * c.act : ROT);
-        return qq >= (PAD ? c.Lthr : G::L) ? qq - G::L : qq;
-    }
+    enum { F_ITER = 0, F_INIT_SMEM = 1, F_INIT_GLOBAL = 2 };
 
     // ------------------------------------------------------------------------------ CN phase
-    static __device__ __forceinline__ float sat(const KParams &P, float x) {   // Q() or clip, no mode branch
-        return fminf(fmaxf(__fsub_rn(__fadd_rn(x, P.sat_magic), P.sat_magic), -P.sat_bound), P.sat_bound);
-    }
-    // weighted, saturated output magnitude for a minimum m of the other edges (the arithmetic of f32_cn_emit, done once
-    // per row for min1 and min2 instead of once per edge): returns the bits of the value with sign(m_fixed) folded in
-    static __device__ __forceinline__ uint32_t row_mag(const KParams &P, float m, float w) {
-        m = m > 0.0001f ? m : __fadd_rn(m, -0.0001f);                 // :250
-        const float x1 = __fmul_rn(fabsf(m), w);                      // :267-298
-        const float x2 = sat(P, x1 > 0.0f ? x1 : 0.0f);               // :308-313
-        return __float_as_uint(x2) ^ (__float_as_uint(m) & 0x80000000u);
-    }
-
-    template <int I>
-    static __device__ __forceinline__ void cn_row(const KParams &P, const Ctx &c, int t, uint32_t &bad) {
-        constexpr int E0 = G::row_ptr[I], DC = G::row_ptr[I + 1] - E0;
-        const int off = E0 * G::LP + c.q;
-        float raw[DC];
-#pragma unroll
-        for (int p = 0; p < DC; ++p) raw[p] = smem_f(off + p * G::LP);
-        // syndrome of the previous hard decision: its bits sit in hb[buf][column][chunk] at the variable's lane
-        uint32_t par = 0;
-        const uint32_t *hb = nms_smem + P.off_hb + ((t + 1) & 1) * G::N * G::C;
-        static_for<0, DC>([&](auto p) {
-            constexpr int E = E0 + decltype(p)::v;
-            const int qv = rot<G::e_sF[E]>(c);
-            par ^= hb[G::e_col[E] * G::C + (qv >> 5)] >> (qv & 31);
-        });
-        par &= 1u;
-        bad |= par;
-        float m1 = 10000.0f, m2 = 10000.0f;   // all-masked row -> 10000 (:248)
-        uint32_t sx = 0;                       // XOR of the inputs: bit 31 = parity of the negative ones
-#pragma unroll
-        for (int p = 0; p < DC; ++p) {
-            const float a = fabsf(raw[p]);
-            const float tmx = fmaxf(m1, a);
-            m1 = fminf(m1, a);
-            m2 = fminf(m2, tmx);
-            sx ^= __float_as_uint(raw[p]);
-        }
-        // C->V of edge p: magnitude from the minimum of the OTHER edges, negative iff (number of positive others) is even
-        // (:251-254; an input is never 0 here, :230).  With P = parity of all positive inputs and s = sign bit of the edge's
-        // own input: sign bit of the output = sign(m_fixed) ^ P ^ s.
-        const uint32_t Pbit = ((sx >> 31) ^ (uint32_t)(DC & 1)) << 31;
-        const bool ucn = P.sharing1 != 0 && par;
-        if (P.sharing0 == 1) {     // per-edge weights: nothing to hoist
-#pragma unroll
-            for (int p = 0; p < DC; ++p) {
-                const float w = ucn ? ucn_weight(P, t, I, E0 + p) : cn_weight(P, t, I, E0 + p);
-                const uint32_t v = row_mag(P, fabsf(raw[p]) > m1 ? m1 : m2, w);
-                smem_f(off + p * G::LP) = __uint_as_float(v ^ Pbit ^ (__float_as_uint(raw[p]) & 0x80000000u));
-            }
-        } else {
-            const float w = f32_edge_w(P, ucn, t, I, E0);   // one weight per row (or none)
-            const uint32_t A = row_mag(P, m1, w) ^ Pbit, B = row_mag(P, m2, w) ^ Pbit;
-#pragma unroll
-            for (int p = 0; p < DC; ++p) {
-                const uint32_t v = fabsf(raw[p]) > m1 ? A : B;
-                smem_f(off + p * G::LP) = __uint_as_float(v ^ (__float_as_uint(raw[p]) & 0x80000000u));
-            }
-        }
-    }
-
     static __device__ __forceinline__ void cn_phase(const KParams &P, const Ctx &c, int t, uint32_t &bad) {
-        static_for<0, G::R>([&](auto s) {
-            constexpr int SLOT = decltype(s)::v;
-            constexpr int NT = (G::M - SLOT + G::R - 1) / G::R;
-            if (c.slot == SLOT) {
-                static_for<0, NT>([&](auto n) { cn_row<G::cn_order[SLOT + decltype(n)::v * G::R]>(P, c, t, bad); });
+        const F32Ctx h = f32_ctx(P, c);
+        const uint32_t a00 = h.sb + h.q4;
+        const uint32_t hb4 = h.sb + (uint32_t)(P.off_hb + ((t + 1) & 1) * G::N * G::C) * 4u;   // hard bits of APP_{t-1}
+        // weight rows of iteration t, branch-free (the host only picks these kernels when the weights are staged in shared
+        // memory): "no CN weight" reads the 1.0f parked behind the syndrome table, "no UCN weight" aliases the CN row
+        const uint32_t one4 = h.et4 + (uint32_t)G::E * 4u;
+        const uint32_t w0row = P.sharing0 != 0 ? h.sb + (uint32_t)(P.off_w + P.w_off_cn + t * P.wc) * 4u : one4;
+        const int m0 = (P.sharing0 != 0 && P.wc > 1) ? -1 : 0;
+        const uint32_t w1row = P.sharing1 != 0 ? h.sb + (uint32_t)(P.off_w + P.w_off_ucn + t * P.wu) * 4u : w0row;
+        const int m1 = P.sharing1 != 0 ? (P.wu > 1 ? -1 : 0) : m0;
+        constexpr int NT = (G::M + G::R - 1) / G::R;
+        const uint2 *task = P.cn_task + c.slot * NT;   // host-built: {row offset in bytes, degree | row index << 16}
+#pragma unroll 1
+        for (int n = 0; n < NT; ++n) {
+            const uint2 tk = task[n];
+            const int dc = (int)(tk.y & 0xffffu), i = (int)(tk.y >> 16);
+            if (dc == 0) break;
+            const uint32_t a0 = a00 + tk.x;
+            const uint32_t par = f32_row_syndrome<PAD>(P, h, hb4, (int)(tk.x / LP4), dc);
+            bad |= par;
+            if (P.sharing0 == 1) {   // per-edge weights: the compact two-pass code
+                cn_row_f32_generic<QM>(P, a0, LP4, dc, t, i, (int)(tk.x / LP4), par);
+                continue;
             }
-        });
+            const float w0 = ldsf(w0row + (uint32_t)((i & m0) * 4)), w1 = ldsf(w1row + (uint32_t)((i & m1) * 4));
+            static_for<0, G::NDEG>([&](auto k) {
+                constexpr int DC = G::cn_degs[decltype(k)::v];
+                if (dc == DC) cn_row_f32<DC, QM>(P, a0, LP4, w0, w1, par);
+            });
+        }
     }
 
     // ------------------------------------------------------------------------------ VN phase
-    // MODE 0: iteration t;  1: pass before iteration 0, xa in shared memory;  2: same, xa = `xg` from global memory
-    template <int J, int MODE>
-    static __device__ __forceinline__ void vn_col(const KParams &P, const Ctx &c, int t, float xg, uint32_t &ones) {
+    // One column, everything constant-folded.  MODE F_ITER: iteration t;  F_INIT_GLOBAL: pass before iteration 0 with the
+    // channel value `xg` just loaded from global memory (also fills the xa / xq arrays).
+    // VNW: VN weights present (wvrow = the next iteration's row).  The hard decisions of the column go out as one
+    // ballot word per chunk (hbrow) and are OR-ed into `onesw` (bit l = lane l's decision has a one so far).
+    template <int J, int MODE, bool VNW>
+    static __device__ __forceinline__ void vn_col(const KParams &P, const F32Ctx &h, uint32_t wvrow, int wvmask, uint32_t hbrow,
+                                                  float xg, uint32_t &onesw) {
         constexpr int C0 = G::col_ptr[J], DV = G::col_ptr[J + 1] - C0;
-        constexpr bool INIT = MODE != 0;
-        int addr[DV];
-        float cv[DV];
+        constexpr bool INIT = MODE != F_ITER;
+        constexpr uint32_t XJ4 = (uint32_t)(J * G::LP) * 4u;
+        uint32_t addr[DV];
+        float cv[DV], ext[DV];
         static_for<0, DV>([&](auto u) {
             constexpr int U = decltype(u)::v;
-            addr[U] = G::vn_e[C0 + U] * G::LP + rot<G::vn_rot[C0 + U]>(c);
-            cv[U] = INIT ? 0.0f : smem_f(addr[U]);
+            constexpr uint32_t X4 = (uint32_t)G::vn_e[C0 + U] * LP4;
+            addr[U] = h.sb + f32_spec_rot<G, G::vn_rot[C0 + U]>(h) + X4;
+            if constexpr (!INIT) cv[U] = ldsf(addr[U]);
         });
         float S = 0.0f;
-#pragma unroll
-        for (int u = 0; u < DV; ++u) S = __fadd_rn(S, cv[u]);            // ascending E(C), like the GEMM column (:317)
-        if constexpr (MODE == 2) {
-            if (P.qms) xg = fminf(fmaxf(xg, -XA_BOUND), XA_BOUND);
-            smem_f(P.off_xa + J * G::LP + c.q) = xg;
-        }
-        const F32Var v = f32_var<INIT>(P, c, J, t, S, ones);
-        if (v.has_next) {
-#pragma unroll
-            for (int u = 0; u < DV; ++u) {
-                float acc = 0.0f;                                        // direct extrinsic sum (:214), ascending
-#pragma unroll
-                for (int u2 = 0; u2 < DV; ++u2)
-                    if (u2 != u) acc = __fadd_rn(acc, cv[u2]);
-                const float m = sat(P, __fadd_rn(v.xin, acc));           // :215, :223-226
-                smem_f(addr[u]) = m == 0.0f ? 0.0001f : m;               // :230
+        if constexpr (!INIT) S = f32_extrinsic<DV>(cv, ext);
+        float xa = xg, xqv;
+        if constexpr (INIT) {
+            if constexpr (QM == 1) {
+                xa = fminf(fmaxf(xa, -XA_BOUND), XA_BOUND);
+                xqv = qf(P, xa);                                     // :321-322
+                sts32(h.xq4 + XJ4, __float_as_uint(xqv));
+            } else {
+                xa = f32_pos_zero(xa);   // -0.0 (it occurs in [Uncor] files) -> +0.0: same value everywhere it is used
+                xqv = xa;
+            }
+            sts32(h.xa4 + XJ4, __float_as_uint(xa));
+        } else {
+            if constexpr (QM == 1) {
+                xqv = ldsf(h.xq4 + XJ4);
+                if constexpr (VNW) xa = ldsf(h.xa4 + XJ4);
+            } else {
+                xa = ldsf(h.xa4 + XJ4);
+                xqv = xa;
             }
         }
+        float xin = QM == 1 ? xqv : xa;
+        if constexpr (VNW) {
+            xin = __fmul_rn(xa, ldsf(wvrow + (uint32_t)((J & wvmask) * 4)));   // :168-169
+            xin = QM == 1 ? qf(P, xin) : f32_pos_zero(xin);                    // :176-177
+        }
+        const float hsrc = INIT ? xin : __fadd_rn(xqv, S);          // :181-182 / :324 (clip_LLR never changes the sign)
+        const bool hb = hsrc >= 0.0f;
+        const uint32_t b = __ballot_sync(0xffffffffu, (!PAD || h.amask != 0u) && hb);   // hard decisions of this column / chunk
+        if constexpr (!INIT) {
+            if (J < P.target_n) onesw |= b;   // uniform: only the first target_node columns count (systematic)
+        }
+        if ((threadIdx.x & 31) == 0) sts32(hbrow + (uint32_t)(J * G::C) * 4u, b);
+#pragma unroll
+        for (int u = 0; u < DV; ++u) sts32(addr[u], f32_v2c<QM>(P, xin, INIT ? 0.0f : ext[u]));
     }
 
-    template <int SLOT, int MODE>
-    static __device__ __forceinline__ void vn_slot(const KParams &P, const Ctx &c, int t, uint32_t &ones) {
+    template <int SLOT, int MODE, bool VNW>
+    static __device__ __forceinline__ void vn_slot(const KParams &P, const Ctx &c, const F32Ctx &h, uint32_t wvrow, int wvmask,
+                                                   uint32_t hbrow, uint32_t &onesw) {
         constexpr int NT = (G::N - SLOT + G::R - 1) / G::R;
-        if constexpr (MODE == 2) {
+        if constexpr (MODE == F_INIT_GLOBAL) {
             const bool ok = c.act && c.f0 < c.nvalid;
             const long long o = (c.frame0 + (ok ? c.f0 : 0)) * (long long)P.NZ + c.a_lane;
-            float x[NT];
+            float x[NT];   // all of the slot's loads are issued before the first use
             if (P.llr != nullptr) {
                 const float *p0 = P.llr + o;
                 static_for<0, NT>([&](auto n) {
@@ -153,51 +146,68 @@ struct F32SpecPolicy {
                 });
             }
             static_for<0, NT>([&](auto n) {
-                vn_col<G::vn_order[SLOT + decltype(n)::v * G::R], MODE>(P, c, t, x[decltype(n)::v], ones);
+                vn_col<G::vn_order[SLOT + decltype(n)::v * G::R], MODE, VNW>(P, h, wvrow, wvmask, hbrow, x[decltype(n)::v], onesw);
             });
         } else {
-            static_for<0, NT>([&](auto n) { vn_col<G::vn_order[SLOT + decltype(n)::v * G::R], MODE>(P, c, t, 0.0f, ones); });
+            static_for<0, NT>([&](auto n) {
+                vn_col<G::vn_order[SLOT + decltype(n)::v * G::R], MODE, VNW>(P, h, wvrow, wvmask, hbrow, 0.0f, onesw);
+            });
         }
     }
 
     template <int MODE>
-    static __device__ __forceinline__ void vn_dispatch(const KParams &P, const Ctx &c, int t, uint32_t &ones) {
-        static_for<0, G::R>([&](auto s) {
-            if (c.slot == decltype(s)::v) vn_slot<decltype(s)::v, MODE>(P, c, t, ones);
-        });
+    static __device__ __forceinline__ void vn_dispatch(const KParams &P, const Ctx &c, const F32Ctx &h, int trow, int tbuf,
+                                                       uint32_t &ones) {
+        const uint32_t hbrow = h.sb + (uint32_t)(P.off_hb + tbuf * G::N * G::C + c.chunk) * 4u;   // hb[buf][j][chunk]
+        uint32_t onesw = 0;
+        if (P.sharing2 != 0) {
+            const uint32_t wvrow = h.sb + (uint32_t)(P.off_w + P.w_off_vn + trow * P.wv) * 4u;
+            const int wvmask = P.wv > 1 ? -1 : 0;
+            static_for<0, G::R>([&](auto s) {
+                if (c.slot == decltype(s)::v) vn_slot<decltype(s)::v, MODE, true>(P, c, h, wvrow, wvmask, hbrow, onesw);
+            });
+        } else {
+            static_for<0, G::R>([&](auto s) {
+                if (c.slot == decltype(s)::v) vn_slot<decltype(s)::v, MODE, false>(P, c, h, 0u, 0, hbrow, onesw);
+            });
+        }
+        ones |= (onesw >> c.lane) & 1u;
     }
+
+    static __device__ __forceinline__ bool unrolled_ok(const KParams &P) { return P.app == nullptr; }   // APP output: table code
 
     template <bool INIT>
     static __device__ __forceinline__ void vn_phase(const KParams &P, const Ctx &c, int t, bool need_hb, uint32_t &ones) {
-        if constexpr (INIT) vn_dispatch<1>(P, c, t, ones);
-        else vn_dispatch<0>(P, c, t, ones);
+        const F32Ctx h = f32_ctx(P, c);
+        if (INIT || !unrolled_ok(P)) {   // channel values already in shared memory (generator), or APP output wanted
+            f32_vn_phase_tab<G::DVMAX, INIT, QM, PAD ? 1 : 0>(P, c, h, t, need_hb, ones);
+            return;
+        }
+        const int trow = min(t + 1, P.T_run - 1);
+        vn_dispatch<F_ITER>(P, c, h, trow, t & 1, ones);
     }
 
+    // channel LLRs straight from global memory into the first V->C messages (replaces load + init pass)
     static __device__ __forceinline__ void load_init(const KParams &P, const Ctx &c) {
+        const F32Ctx h = f32_ctx(P, c);
         uint32_t dummy = 0;
-        vn_dispatch<2>(P, c, -1, dummy);
+        vn_dispatch<F_INIT_GLOBAL>(P, c, h, 0, 1, dummy);   // hard bits of xin_0 -> ballot buffer 1
     }
 
+    // ------------------------------------------------------------------ final syndrome pass
     static __device__ __forceinline__ uint32_t synd_phase(const KParams &P, const Ctx &c, int tl) {
+        const F32Ctx h = f32_ctx(P, c);
+        const uint32_t hb4 = h.sb + (uint32_t)(P.off_hb + ((tl + 1) & 1) * G::N * G::C) * 4u;
+        constexpr int NT = (G::M + G::R - 1) / G::R;
+        const uint2 *task = P.cn_task + c.slot * NT;
         uint32_t bad = 0;
-        const uint32_t *hb = nms_smem + P.off_hb + ((tl + 1) & 1) * G::N * G::C;
-        static_for<0, G::R>([&](auto s) {
-            constexpr int SLOT = decltype(s)::v;
-            constexpr int NT = (G::M - SLOT + G::R - 1) / G::R;
-            if (c.slot == SLOT) {
-                static_for<0, NT>([&](auto n) {
-                    constexpr int I = G::cn_order[SLOT + decltype(n)::v * G::R];
-                    constexpr int E0 = G::row_ptr[I], DC = G::row_ptr[I + 1] - E0;
-                    uint32_t par = 0;
-                    static_for<0, DC>([&](auto p) {
-                        constexpr int E = E0 + decltype(p)::v;
-                        const int qv = rot<G::e_sF[E]>(c);
-                        par ^= hb[G::e_col[E] * G::C + (qv >> 5)] >> (qv & 31);
-                    });
-                    bad |= par & 1u;
-                });
-            }
-        });
+#pragma unroll 1
+        for (int n = 0; n < NT; ++n) {
+            const uint2 tk = task[n];
+            const int dc = (int)(tk.y & 0xffffu);
+            if (dc == 0) break;
+            bad |= f32_row_syndrome<PAD>(P, h, hb4, (int)(tk.x / LP4), dc);
+        }
         return bad;
     }
 };

@@ -63,6 +63,33 @@ def test_golden_decode(name):
     assert np.array_equal(dec.ya_output_all(xa).cpu().numpy(), app.reshape(-1, app.shape[-1]))
 
 
+@pytest.mark.parametrize("name", all_cases())
+def test_golden_fast_path(name):
+    """Without APP output the graph-specialised kernels run their unrolled code (with it, the table-driven code): the hard
+    decisions, flags, first zero-syndrome iteration and bit-error counts of that path against the reference, with and
+    without early termination."""
+    import torch
+    case = load_case(name)
+    g, dec = build_decoder(case)
+    xa = torch.from_numpy(case["xa"]).cuda()
+    hard_ref, synd_ok, any_one, uncor_any, iters = oracle_flags(g, case["app"])
+    T = case["T"]
+    r = dec.decode(xa, app=None, unpack=True)
+    assert np.array_equal(r.hard.cpu().numpy().astype(bool), hard_ref[T - 1])
+    flags = r.flags.cpu().numpy()
+    assert np.array_equal((flags & 1) != 0, synd_ok[T - 1])
+    assert np.array_equal((flags & 2) != 0, uncor_any)
+    assert np.array_equal((flags & 4) != 0, any_one[T - 1])
+    assert np.array_equal(r.iters.cpu().numpy(), iters)
+    assert np.array_equal(r.biterr.cpu().numpy(), hard_ref[T - 1].sum(axis=1))
+    e = dec.decode(xa, early_term=True, app=None, unpack=True)
+    stop = iters - 1
+    B = hard_ref.shape[1]
+    assert np.array_equal(e.iters.cpu().numpy(), iters)
+    assert np.array_equal(e.hard.cpu().numpy().astype(bool), np.stack([hard_ref[stop[b], b] for b in range(B)]))
+    assert np.array_equal((e.flags.cpu().numpy() & 1) != 0, np.array([synd_ok[stop[b], b] for b in range(B)]))
+
+
 @pytest.mark.parametrize("name", ["wimax_qms_333_t20", "5g_r073_z32_qms_222_t50", "wimax_float_333_t20",
                                   "mackay_qms_300_t20"])
 def test_golden_early_termination(name):
