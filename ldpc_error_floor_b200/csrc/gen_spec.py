@@ -37,7 +37,7 @@ GEOMETRIES = {
 }
 # float32 kernels (one frame per lane): same lanes as the packed choice
 GEOMETRIES_F32 = {
-    "wimax": [(4, 2), (4, 3), (4, 1), (8, 2), (8, 1), (2, 4)], "wifi": [(7, 2)], "5g_r073_z72": [(3, 2), (4, 2), (4, 1)], "5g_r050_z64": [(2, 2), (4, 1), (4, 2)], "5g_r050_z32": [(4, 2)],
+    "wimax": [(4, 2), (8, 2)], "wifi": [(7, 2)], "5g_r073_z72": [(4, 2), (3, 2)], "5g_r050_z64": [(2, 2)], "5g_r050_z32": [(4, 2)],
     "5g_r033_z32": [(4, 2)], "5g_r073_z32": [(4, 2)],
 }   # the z = 1 codes (MacKay, BCH) stay on the generic float kernels: unrolling 48-96 nodes costs minutes of compile time
 SKIP = {"polar"}   # row degree 64 > 32: generic two-pass kernel
@@ -133,7 +133,7 @@ def emit(key, proto, z, Fp, R, outdir, f32=False):
     name = f"{key}_fp{Fp}_r{R}"
     if f32:
         # float path: msg + xa + ballots + weights + misc; the quantised twin adds the xq array
-        words = E * LP + N * LP + 2 * N * C + E + 1 + 256 + MISC_WORDS
+        words = E * LP + N * LP + 2 * N * C + E + 1 + E * C * (2 if L != LP else 1) + 256 + MISC_WORDS
         mb = [max(1, min(MAX_SMEM // (w * 4 + 1024), 2048 // threads, 65536 // (threads * 56))) for w in (words, words + N * LP)]
         src = f"""// GENERATED by gen_spec.py -- do not edit.  Graph "{key}": {M}x{N}, z={z}, E={E}; float32 geometry Fp={Fp} R={R}.
 #include "../nms_f32_spec.cuh"

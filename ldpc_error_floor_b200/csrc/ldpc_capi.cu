@@ -252,13 +252,15 @@ const void *pick_kernel(bool packed, int max_dc, int max_dv, int *dcb, int *dvb)
     return nms_f32_func_0_0();
 }
 
-void fill_smem_layout(KParams *P, bool packed) {
+// spec_f32: graph-specialised float kernel (adds the per-(edge, chunk) syndrome table, nms_f32_spec.cuh)
+void fill_smem_layout(KParams *P, bool packed, bool spec_f32 = false) {
     int off = P->E * P->LP;                 // message array at word 0
     off = (off + 3) & ~3;
     P->off_xa = off; off += P->N * P->LP * (packed ? 2 : 1);
     P->off_xq = off; off += (packed || P->qms) ? P->N * P->LP : 0;
     P->off_hb = off; off += 2 * (packed ? 2 : 1) * P->N * P->C;
     P->off_et = off; off += packed ? 0 : P->E + 1;
+    P->off_et2 = off; off += spec_f32 ? P->E * P->C * (P->L != P->LP ? 2 : 1) : 0;
     P->off_w = off; off += P->w_staged ? P->w_words : 0;
     P->off_misc = off; off += NMS_MISC_WORDS;
     P->smem_words = off;
@@ -277,7 +279,7 @@ unsigned long long graph_hash(const ldpc_graph &g) {   // FNV-1a over (M, N, z, 
 
 // pick (Fp, R): lane efficiency x task balance x achievable warps/SM (from the real occupancy calculator)
 int choose_geometry(const ldpc_graph &g, bool packed, bool qms, int w_words, const void *func, int force_fp,
-                    int force_r, int max_warps, LaunchGeom *out) {
+                    int force_r, int max_warps, LaunchGeom *out, bool spec_f32 = false) {
     const int max_smem = 227 * 1024;
     double best = -1.0;
     int forced_fp = force_fp, forced_r = force_r;
@@ -292,9 +294,9 @@ int choose_geometry(const ldpc_graph &g, bool packed, bool qms, int w_words, con
         const int L = g.z * Fp, LP = (L + 31) & ~31, C = LP / 32;
         if (C > 16) break;
         KParams tmp{};
-        tmp.E = g.E; tmp.N = g.N; tmp.LP = LP; tmp.C = C; tmp.qms = qms;
+        tmp.E = g.E; tmp.N = g.N; tmp.L = L; tmp.LP = LP; tmp.C = C; tmp.qms = qms;
         tmp.w_words = w_words; tmp.w_staged = w_words > 0 && w_words <= NMS_WSTAGE_MAX_WORDS;
-        fill_smem_layout(&tmp, packed);
+        fill_smem_layout(&tmp, packed, spec_f32);
         const int smem = tmp.smem_words * 4;
         if (smem > max_smem) break;
         for (int R = 1; R * C <= max_warps; ++R) {
@@ -447,7 +449,7 @@ extern "C" int ldpc_decoder_create2(const ldpc_graph_t *g, const int32_t sharing
             if ((want_fp && tab[k].Fp != want_fp) || (want_r && tab[k].R != want_r)) continue;   // tuning override
             const void *f = tab[k].func();
             LaunchGeom geo{};
-            if (choose_geometry(d->g, false, qms, w_words, f, tab[k].Fp, tab[k].R, 32, &geo) == LDPC_OK) {
+            if (choose_geometry(d->g, false, qms, w_words, f, tab[k].Fp, tab[k].R, 32, &geo, true) == LDPC_OK) {
                 d->func = f; d->geom = geo; d->spec_name = tab[k].name; rc = LDPC_OK;
                 break;
             }
@@ -473,7 +475,7 @@ extern "C" int ldpc_decoder_create2(const ldpc_graph_t *g, const int32_t sharing
     P.target_n = target_node > 0 ? target_node : g->N;
     P.punct_s = g->punct_s; P.punct_e = g->punct_e; P.short_s = g->short_s; P.short_e = g->short_e;
     P.HW = (P.NZ + 31) / 32;
-    fill_smem_layout(&P, d->packed);
+    fill_smem_layout(&P, d->packed, !d->packed && d->spec_name != nullptr);
     if (d->packed) {
         P.h2w_c = P.off_w + P.w_off_cn; P.h2_wc = wc; P.h2_mc = wc > 1 ? -1 : 0;
         if (wu) { P.h2w_u = P.off_w + P.w_off_ucn; P.h2_wu = wu; P.h2_mu = wu > 1 ? -1 : 0; }

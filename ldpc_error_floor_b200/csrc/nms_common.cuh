@@ -65,7 +65,7 @@ struct KParams {
     unsigned long long *counters;
     float *uncor_buf; unsigned int *uncor_count; unsigned int uncor_cap; int harvest_mode;
     // shared-memory carve-up (word offsets; the message array always starts at word 0)
-    int off_xa, off_xq, off_hb, off_et, off_w, off_misc, smem_words;   // off_et: float kernels only (E words)
+    int off_xa, off_xq, off_hb, off_et, off_et2, off_w, off_misc, smem_words;   // off_et (E + 1 words) / off_et2: float kernels only
     // tables
     unsigned short row_ptr[LDPC_MAX_M + 1];   // E(C) edges of proto row i: [row_ptr[i], row_ptr[i+1])
     unsigned short col_ptr[LDPC_MAX_N + 1];   // CSR by proto column into vn_edge

@@ -6,7 +6,7 @@
 // HBM sees LLRs in and bits/flags out; every edge message lives in shared memory / registers.
 // The arithmetic back-end is a Policy (nms_h2.cuh / nms_f32.cu / generated graph-specialised
 // policies) providing
-//   cn_phase(P,c,t,bad)   vn_phase<INIT>(P,c,t,need_hb,ones)   synd_phase(P,c,tl) -> bad
+//   setup(P,tid)   cn_phase(P,c,t,bad)   vn_phase<INIT>(P,c,t,need_hb,ones)   synd_phase(P,c,tl) -> bad
 //
 // Shared memory is ONE array `nms_smem` addressed by word offsets (message array at word 0), so
 // every access compiles to LDS/STS [reg + immediate]; inactive padding lanes (q >= L) work on
@@ -225,6 +225,7 @@ __device__ __forceinline__ void nms_decode_body(const KParams &P) {
         for (int e = tid; e < P.E; e += blockDim.x) nms_smem[P.off_et + e] = (uint32_t)(P.e_col[e] * P.C) | ((uint32_t)P.e_sF[e] << 16);
         if (tid == 0) nms_smem[P.off_et + P.E] = __float_as_uint(1.0f);
     }
+    Policy::setup(P, tid);   // policy-owned tables (visible after the first barrier of the batch loop)
 
     for (long long batch = blockIdx.x; batch < nbatches; batch += gridDim.x) {
         c.frame0 = batch * P.FB;

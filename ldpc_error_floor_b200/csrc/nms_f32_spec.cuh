@@ -32,12 +32,47 @@ struct F32SpecPolicy {
     static constexpr uint32_t LP4 = G::LP * 4u;
     static constexpr bool PAD = G::L != G::LP;
     enum { F_ITER = 0, F_INIT_SMEM = 1, F_INIT_GLOBAL = 2 };
+    static constexpr int ETW = PAD ? 2 : 1;   // words per (edge, chunk) entry of the syndrome table
+
+    // Syndrome table, built once per CTA: entry (e, chunk) tells the lane that serves edge e which two ballot words hold
+    // the 32 hard bits the chunk's check lanes see through that edge, and how far to funnel-shift them:
+    //   word 0 = lo | hi << 11 | r << 22   (word indices into hb[buf][.], r = first bit)
+    //   word 1 (L not a multiple of 32) = column's first word | thr << 16: lanes >= thr wrap to variable lane l - thr
+    static __device__ __forceinline__ void setup(const KParams &P, int tid) {
+        for (int idx = tid; idx < G::E * G::C; idx += blockDim.x) {
+            const int e = idx / G::C, ch = idx - e * G::C;
+            const int colC = P.e_col[e] * G::C;
+            int s = ch * 32 + P.e_sF[e];
+            s = s >= G::L ? s - G::L : s;
+            const int w = s >> 5, r = s & 31;
+            const int w1 = PAD ? min(w + 1, G::C - 1) : (w + 1 == G::C ? 0 : w + 1);
+            nms_smem[P.off_et2 + idx * ETW] = (uint32_t)(colC + w) | ((uint32_t)(colC + w1) << 11) | ((uint32_t)r << 22);
+            if constexpr (PAD) nms_smem[P.off_et2 + idx * ETW + 1] = (uint32_t)colC | ((uint32_t)min(G::L - s, 32) << 16);
+        }
+    }
+
+    // syndrome bit of this lane's check in row [e0, e0 + dc): lane p serves edge p, one XOR reduction (see nms_f32.cuh)
+    static __device__ __forceinline__ uint32_t row_syndrome(uint32_t et2c, uint32_t hb4, int e0, int dc) {
+        const int lane = threadIdx.x & 31;
+        uint32_t f = 0;
+        if (lane < dc) {   // dc <= 32 for the graphs that get a specialised kernel
+            const uint32_t ea = et2c + (uint32_t)((e0 + lane) * (G::C * ETW * 4));
+            const uint32_t tb = lds32(ea);
+            f = __funnelshift_r(lds32(hb4 + (tb & 0x7ffu) * 4u), lds32(hb4 + ((tb >> 11) & 0x7ffu) * 4u), tb >> 22);
+            if constexpr (PAD) {
+                const uint32_t t2 = lds32(ea + 4u), thr = t2 >> 16;
+                if (thr < 32u) f = (f & ((1u << thr) - 1u)) | (lds32(hb4 + (t2 & 0xffffu) * 4u) << thr);
+            }
+        }
+        return (__reduce_xor_sync(0xffffffffu, f) >> lane) & 1u;
+    }
 
     // ------------------------------------------------------------------------------ CN phase
     static __device__ __forceinline__ void cn_phase(const KParams &P, const Ctx &c, int t, uint32_t &bad) {
         const F32Ctx h = f32_ctx(P, c);
         const uint32_t a00 = h.sb + h.q4;
         const uint32_t hb4 = h.sb + (uint32_t)(P.off_hb + ((t + 1) & 1) * G::N * G::C) * 4u;   // hard bits of APP_{t-1}
+        const uint32_t et2c = h.sb + (uint32_t)(P.off_et2 + c.chunk * ETW) * 4u;
         // weight rows of iteration t, branch-free (the host only picks these kernels when the weights are staged in shared
         // memory): "no CN weight" reads the 1.0f parked behind the syndrome table, "no UCN weight" aliases the CN row
         const uint32_t one4 = h.et4 + (uint32_t)G::E * 4u;
@@ -53,7 +88,7 @@ struct F32SpecPolicy {
             const int dc = (int)(tk.y & 0xffffu), i = (int)(tk.y >> 16);
             if (dc == 0) break;
             const uint32_t a0 = a00 + tk.x;
-            const uint32_t par = f32_row_syndrome<PAD>(P, h, hb4, (int)(tk.x / LP4), dc);
+            const uint32_t par = row_syndrome(et2c, hb4, (int)(tk.x / LP4), dc);
             bad |= par;
             if (P.sharing0 == 1) {   // per-edge weights: the compact two-pass code
                 cn_row_f32_generic<QM>(P, a0, LP4, dc, t, i, (int)(tk.x / LP4), par);
@@ -72,7 +107,8 @@ struct F32SpecPolicy {
     // channel value `xg` just loaded from global memory (also fills the xa / xq arrays).
     // VNW: VN weights present (wvrow = the next iteration's row).  The hard decisions of the column go out as one
     // ballot word per chunk (hbrow) and are OR-ed into `onesw` (bit l = lane l's decision has a one so far).
-    template <int J, int MODE, bool VNW>
+    // TALL: every column counts in the error metrics (target_node = N), so the "has a one" word needs no column test.
+    template <int J, int MODE, bool VNW, bool TALL>
     static __device__ __forceinline__ void vn_col(const KParams &P, const F32Ctx &h, uint32_t wvrow, int wvmask, uint32_t hbrow,
                                                   float xg, uint32_t &onesw) {
         constexpr int C0 = G::col_ptr[J], DV = G::col_ptr[J + 1] - C0;
@@ -117,14 +153,14 @@ struct F32SpecPolicy {
         const bool hb = hsrc >= 0.0f;
         const uint32_t b = __ballot_sync(0xffffffffu, (!PAD || h.amask != 0u) && hb);   // hard decisions of this column / chunk
         if constexpr (!INIT) {
-            if (J < P.target_n) onesw |= b;   // uniform: only the first target_node columns count (systematic)
+            if (TALL || J < P.target_n) onesw |= b;   // uniform: only the first target_node columns count (systematic)
         }
-        if ((threadIdx.x & 31) == 0) sts32(hbrow + (uint32_t)(J * G::C) * 4u, b);
+        sts32(hbrow + (uint32_t)(J * G::C) * 4u, b);   // every lane stores the same word: no lane-0 branch
 #pragma unroll
         for (int u = 0; u < DV; ++u) sts32(addr[u], f32_v2c<QM>(P, xin, INIT ? 0.0f : ext[u]));
     }
 
-    template <int SLOT, int MODE, bool VNW>
+    template <int SLOT, int MODE, bool VNW, bool TALL>
     static __device__ __forceinline__ void vn_slot(const KParams &P, const Ctx &c, const F32Ctx &h, uint32_t wvrow, int wvmask,
                                                    uint32_t hbrow, uint32_t &onesw) {
         constexpr int NT = (G::N - SLOT + G::R - 1) / G::R;
@@ -146,11 +182,11 @@ struct F32SpecPolicy {
                 });
             }
             static_for<0, NT>([&](auto n) {
-                vn_col<G::vn_order[SLOT + decltype(n)::v * G::R], MODE, VNW>(P, h, wvrow, wvmask, hbrow, x[decltype(n)::v], onesw);
+                vn_col<G::vn_order[SLOT + decltype(n)::v * G::R], MODE, VNW, TALL>(P, h, wvrow, wvmask, hbrow, x[decltype(n)::v], onesw);
             });
         } else {
             static_for<0, NT>([&](auto n) {
-                vn_col<G::vn_order[SLOT + decltype(n)::v * G::R], MODE, VNW>(P, h, wvrow, wvmask, hbrow, 0.0f, onesw);
+                vn_col<G::vn_order[SLOT + decltype(n)::v * G::R], MODE, VNW, TALL>(P, h, wvrow, wvmask, hbrow, 0.0f, onesw);
             });
         }
     }
@@ -160,17 +196,21 @@ struct F32SpecPolicy {
                                                        uint32_t &ones) {
         const uint32_t hbrow = h.sb + (uint32_t)(P.off_hb + tbuf * G::N * G::C + c.chunk) * 4u;   // hb[buf][j][chunk]
         uint32_t onesw = 0;
-        if (P.sharing2 != 0) {
-            const uint32_t wvrow = h.sb + (uint32_t)(P.off_w + P.w_off_vn + trow * P.wv) * 4u;
-            const int wvmask = P.wv > 1 ? -1 : 0;
-            static_for<0, G::R>([&](auto s) {
-                if (c.slot == decltype(s)::v) vn_slot<decltype(s)::v, MODE, true>(P, c, h, wvrow, wvmask, hbrow, onesw);
-            });
-        } else {
-            static_for<0, G::R>([&](auto s) {
-                if (c.slot == decltype(s)::v) vn_slot<decltype(s)::v, MODE, false>(P, c, h, 0u, 0, hbrow, onesw);
-            });
-        }
+        const uint32_t wvrow = h.sb + (uint32_t)(P.off_w + P.w_off_vn + trow * P.wv) * 4u;
+        const int wvmask = P.wv > 1 ? -1 : 0;
+        const bool tall = MODE != F_ITER || P.target_n >= G::N;
+        static_for<0, G::R>([&](auto s) {
+            constexpr int S = decltype(s)::v;
+            if (c.slot == S) {
+                if (P.sharing2 != 0) {
+                    if (tall) vn_slot<S, MODE, true, true>(P, c, h, wvrow, wvmask, hbrow, onesw);
+                    else vn_slot<S, MODE, true, false>(P, c, h, wvrow, wvmask, hbrow, onesw);
+                } else {
+                    if (tall) vn_slot<S, MODE, false, true>(P, c, h, 0u, 0, hbrow, onesw);
+                    else vn_slot<S, MODE, false, false>(P, c, h, 0u, 0, hbrow, onesw);
+                }
+            }
+        });
         ones |= (onesw >> c.lane) & 1u;
     }
 
@@ -198,6 +238,7 @@ struct F32SpecPolicy {
     static __device__ __forceinline__ uint32_t synd_phase(const KParams &P, const Ctx &c, int tl) {
         const F32Ctx h = f32_ctx(P, c);
         const uint32_t hb4 = h.sb + (uint32_t)(P.off_hb + ((tl + 1) & 1) * G::N * G::C) * 4u;
+        const uint32_t et2c = h.sb + (uint32_t)(P.off_et2 + c.chunk * ETW) * 4u;
         constexpr int NT = (G::M + G::R - 1) / G::R;
         const uint2 *task = P.cn_task + c.slot * NT;
         uint32_t bad = 0;
@@ -206,7 +247,7 @@ struct F32SpecPolicy {
             const uint2 tk = task[n];
             const int dc = (int)(tk.y & 0xffffu);
             if (dc == 0) break;
-            bad |= f32_row_syndrome<PAD>(P, h, hb4, (int)(tk.x / LP4), dc);
+            bad |= row_syndrome(et2c, hb4, (int)(tk.x / LP4), dc);
         }
         return bad;
     }

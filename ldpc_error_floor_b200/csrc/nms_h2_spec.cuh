@@ -38,6 +38,7 @@ struct H2SpecPolicy {
     static constexpr bool FUSED_LOAD = true;
     static constexpr uint32_t LP4 = G::LP * 4u;
     static constexpr bool PAD = G::L != G::LP;
+    static __device__ __forceinline__ void setup(const KParams &, int) {}
 
     // ------------------------------------------------------------------------------ CN phase
     // rows of one degree share a body; the row's base offset and weights are the only per-row values
@@ -115,10 +116,8 @@ struct H2SpecPolicy {
             const bool act = !PAD || h.amask != 0u;
             const uint32_t lo = __ballot_sync(0xffffffffu, act && (hbw & 1u));
             const uint32_t hi = __ballot_sync(0xffffffffu, act && (hbw >> 16));
-            if ((threadIdx.x & 31) == 0) {
-                sts32(hbrow + (uint32_t)(J * G::C) * 4u, lo);
-                sts32(hbrow + (uint32_t)((G::N + J) * G::C) * 4u, hi);
-            }
+            sts32(hbrow + (uint32_t)(J * G::C) * 4u, lo);   // every lane stores the same word: no lane-0 branch
+            sts32(hbrow + (uint32_t)((G::N + J) * G::C) * 4u, hi);
         }
         if constexpr (INIT) {
 #pragma unroll
