@@ -29,6 +29,7 @@ ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 
 OPS_PER_EDGE_UPDATE_QMS = 26     # algorithmic ALU lane-ops per edge update, quantised NMS
+OPS_PER_EDGE_UPDATE_FLOAT = 20   # same table, float min-sum (no quantisers)
 SM_COUNT, LANES_PER_SM = 148, 128
 HARVEST_SNR_DB = 3.5
 HARVEST_SEED = 20261018
@@ -348,6 +349,22 @@ def main():
             dist.destroy_process_group()
         return
 
+    # ---- secondary (rank 0): the float min-sum path (decoding_type 1, SURVEY.md 8d "and also decoding_type=1") on the
+    # same words and weights -- one frame per 32-bit lane instead of two, reference-ordered float32 arithmetic
+    fdec = L.NMSDecoder(g, L.WeightSet(sharing, blocks), decoding_type=1, q_bit=5, clip_llr=20.0, device=local_rank)
+    Bf = min(B, 1 << 19)
+    fcnt = torch.zeros(_lib.NUM_COUNTERS, dtype=torch.int64, device=dev)
+    for _ in range(2):
+        fdec.post_decode(llr[:Bf], counters=fcnt)
+    torch.cuda.synchronize()
+    f0, f1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    f0.record()
+    for _ in range(5):
+        fdec.post_decode(llr[:Bf], counters=fcnt)
+    f1.record()
+    torch.cuda.synchronize()
+    f_ms = f0.elapsed_time(f1) / 5
+
     pk, pk_src = peaks()
     sm_max = float(clocks.get("sm_max_mhz") or pk.get("sm_max_mhz", 1965.0))
     alu_peak = SM_COUNT * LANES_PER_SM * sm_max * 1e6 / 1e12          # T lane-ops/s at max clock
@@ -405,6 +422,12 @@ def main():
                "note": f"fused Philox generate+decode+count at {HARVEST_SNR_DB} dB (ldpc_mc_run), 20 iterations fixed / "
                        f"with per-frame early termination",
                "fer_any": float(mcnt[2].item()) / float(mcnt[0].item())},
+        "float_min_sum": {"kernel": fdec.kernel_name, "frames_per_launch": Bf, "kernel_ms": f_ms,
+                          "frames_per_s": Bf / (f_ms / 1e3), "value": Bf / (f_ms / 1e3) * k_info / 1e9, "unit": "Gbit/s",
+                          "edge_updates_per_s": Bf / (f_ms / 1e3) * E * z * T, "ops_per_edge_update": OPS_PER_EDGE_UPDATE_FLOAT,
+                          "roofline_frac": Bf / (f_ms / 1e3) * E * z * T * OPS_PER_EDGE_UPDATE_FLOAT / 1e12 / alu_peak,
+                          "note": "decoding_type 1 (float32 messages, clip +-20), same words / weights / 20 iterations, "
+                                  "no early stop; HBM-resident inputs, kernel-only timing"},
         "geometry": {"packed_fp16x2": dec.packed, "frames_per_cta": dec.frames_per_cta, "ctas_per_sm": dec.ctas_per_sm,
                      "threads_per_cta": dec.threads_per_cta, "smem_bytes": dec.smem_bytes},
     }

@@ -76,7 +76,7 @@ def heuristic(M, N, E, z):
         C = LP // 32
         if C > 16:
             break
-        smem = layout(E, N, LP, C, 256)[-1] * 4
+        smem = (layout(E, N, LP, C, 256)[-1] - N * LP) * 4   # without the xq array (decoders with VN weights drop it)
         if smem > MAX_SMEM:
             break
         R = 1
@@ -129,7 +129,7 @@ def emit(key, proto, z, Fp, R, outdir, f32=False):
     vn_e = [col_edge[k] for k in range(E)]
     vn_rot = [(L - shift[col_edge[k]] * Fp) % L for k in range(E)]
     threads = C * R * 32
-    smem = layout(E, N, LP, C, 256)[-1] * 4
+    smem = (layout(E, N, LP, C, 256)[-1] - N * LP) * 4   # without the xq array (decoders with VN weights drop it)
     name = f"{key}_fp{Fp}_r{R}"
     if f32:
         # float path: msg + xa + ballots + weights + misc; the quantised twin adds the xq array

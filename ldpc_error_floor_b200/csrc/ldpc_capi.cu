@@ -257,7 +257,8 @@ void fill_smem_layout(KParams *P, bool packed, bool spec_f32 = false) {
     int off = P->E * P->LP;                 // message array at word 0
     off = (off + 3) & ~3;
     P->off_xa = off; off += P->N * P->LP * (packed ? 2 : 1);
-    P->off_xq = off; off += (packed || P->qms) ? P->N * P->LP : 0;
+    const bool drop_xq = P->no_xq && !env_on("LDPC_B200_KEEP_XQ");   // the env switch keeps the (then unused) array: occupancy A/B
+    P->off_xq = off; off += ((packed && !drop_xq) || (!packed && P->qms)) ? P->N * P->LP : 0;
     P->off_hb = off; off += 2 * (packed ? 2 : 1) * P->N * P->C;
     P->off_et = off; off += packed ? 0 : P->E + 1;
     P->off_et2 = off; off += spec_f32 ? P->E * P->C * (P->L != P->LP ? 2 : 1) : 0;
@@ -279,7 +280,7 @@ unsigned long long graph_hash(const ldpc_graph &g) {   // FNV-1a over (M, N, z, 
 
 // pick (Fp, R): lane efficiency x task balance x achievable warps/SM (from the real occupancy calculator)
 int choose_geometry(const ldpc_graph &g, bool packed, bool qms, int w_words, const void *func, int force_fp,
-                    int force_r, int max_warps, LaunchGeom *out, bool spec_f32 = false) {
+                    int force_r, int max_warps, LaunchGeom *out, bool spec_f32 = false, bool no_xq = false) {
     const int max_smem = 227 * 1024;
     double best = -1.0;
     int forced_fp = force_fp, forced_r = force_r;
@@ -294,7 +295,7 @@ int choose_geometry(const ldpc_graph &g, bool packed, bool qms, int w_words, con
         const int L = g.z * Fp, LP = (L + 31) & ~31, C = LP / 32;
         if (C > 16) break;
         KParams tmp{};
-        tmp.E = g.E; tmp.N = g.N; tmp.L = L; tmp.LP = LP; tmp.C = C; tmp.qms = qms;
+        tmp.E = g.E; tmp.N = g.N; tmp.L = L; tmp.LP = LP; tmp.C = C; tmp.qms = qms; tmp.no_xq = no_xq;
         tmp.w_words = w_words; tmp.w_staged = w_words > 0 && w_words <= NMS_WSTAGE_MAX_WORDS;
         fill_smem_layout(&tmp, packed, spec_f32);
         const int smem = tmp.smem_words * 4;
@@ -418,6 +419,7 @@ extern "C" int ldpc_decoder_create2(const ldpc_graph_t *g, const int32_t sharing
     if (wu) d->w_raw.insert(d->w_raw.end(), w_ucn, w_ucn + (size_t)T * wu);
     if (wv) d->w_raw.insert(d->w_raw.end(), w_vn, w_vn + (size_t)T * wv);
     // a graph known at build time gets its specialised kernel (gen_spec.py); anything else the generic buckets
+    const bool no_xq = sharing[2] != 0;   // packed kernels: see KParams::no_xq
     int rc = LDPC_E_LIMIT;
     d->func = nullptr;
     if (d->packed && !env_on("LDPC_B200_NO_SPEC")) {
@@ -431,7 +433,7 @@ extern "C" int ldpc_decoder_create2(const ldpc_graph_t *g, const int32_t sharing
             if ((want_fp && tab[k].Fp != want_fp) || (want_r && tab[k].R != want_r)) continue;   // tuning override
             const void *f = tab[k].func();
             LaunchGeom geo{};
-            if (choose_geometry(d->g, true, qms, w_words, f, tab[k].Fp, tab[k].R, 32, &geo) == LDPC_OK) {
+            if (choose_geometry(d->g, true, qms, w_words, f, tab[k].Fp, tab[k].R, 32, &geo, false, no_xq) == LDPC_OK) {
                 d->func = f; d->geom = geo; d->spec_name = tab[k].name; rc = LDPC_OK;
                 break;
             }
@@ -457,7 +459,7 @@ extern "C" int ldpc_decoder_create2(const ldpc_graph_t *g, const int32_t sharing
     }
     if (d->func == nullptr) {
         d->func = pick_kernel(d->packed, g->info.max_dc, g->info.max_dv, &d->dcb, &d->dvb);
-        rc = choose_geometry(d->g, d->packed, qms, w_words, d->func, 0, 0, 16, &d->geom);   // generic kernels: __launch_bounds__(512)
+        rc = choose_geometry(d->g, d->packed, qms, w_words, d->func, 0, 0, 16, &d->geom, false, d->packed && no_xq);   // generic kernels: __launch_bounds__(512)
     }
     if (rc != LDPC_OK) { delete d; return rc; }
 
@@ -472,6 +474,7 @@ extern "C" int ldpc_decoder_create2(const ldpc_graph_t *g, const int32_t sharing
     P.w_words = (int)wh.size(); P.w_staged = P.w_words > 0 && P.w_words <= NMS_WSTAGE_MAX_WORDS;
     P.w_off_cn = 0; P.w_off_ucn = T * wc; P.w_off_vn = T * (wc + wu);
     P.T_run = T;
+    P.no_xq = d->packed && no_xq;
     P.target_n = target_node > 0 ? target_node : g->N;
     P.punct_s = g->punct_s; P.punct_e = g->punct_e; P.short_s = g->short_s; P.short_e = g->short_e;
     P.HW = (P.NZ + 31) / 32;

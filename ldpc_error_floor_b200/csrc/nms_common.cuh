@@ -48,6 +48,7 @@ struct KParams {
     // "no weight" is a staged row of 1.0f, "no UCN weight" aliases the CN block.
     int h2w_c, h2w_u, h2w_v, h2_wc, h2_wu, h2_wv, h2_mc, h2_mu, h2_mv;
     int T_run, early_term;
+    int no_xq;         // packed kernels with VN weights: no xq array, Q(xa) recomputed from xa
     int target_n;      // proto columns that count in the error metrics (systematic: N - M, main_Base.py:83-86; else N)
     // source: llr != nullptr -> global float32 LLRs; llr_q8 != nullptr -> global int8 LLRs in units of q8_step
     // (the compact form of on-grid words); else Philox generator

@@ -153,10 +153,14 @@ __device__ __forceinline__ void cn_row_h2(const KParams &P, uint32_t a0, uint32_
     }
     uint32_t A, B;
     h2_row_mags(P, w0, w1, (DC & 1) != 0, par, m1, m2, A, B);
+    // |v| > min1 -> the others' minimum is min1 (A), else min2 (B).  The select is done as B + g (A - B) with g in {0, 1}
+    // on the FMA pipe instead of a second LOP3: the integer / logic pipe runs at half the issue rate and is the busiest
+    // pipe of this kernel.  Exact: A, B are on-grid values of one sign, so A - B and the sum are representable.
+    const __half2 dAB = __hsub2(u2h(A), u2h(B));
 #pragma unroll
     for (int p = 0; p < DC; ++p) {
-        const uint32_t gt = __hgt2_mask(__habs2(u2h(raw[p])), m1);   // |v| > min1 -> others' min is min1, else min2
-        sts32(a0 + p * stride4, ((gt & A) | (~gt & B)) ^ (raw[p] & SIGN2));
+        const __half2 g = __hgt2(__habs2(u2h(raw[p])), m1);
+        sts32(a0 + p * stride4, h2u(__hfma2(g, dAB, u2h(B))) ^ (raw[p] & SIGN2));
     }
 }
 
@@ -226,9 +230,9 @@ __device__ __forceinline__ bool h2_var(const KParams &P, const Ctx &c, const H2C
     for (int k = 0; k < NC; ++k) x[k] = lds64f(h.xa8 + (uint32_t)jlp[k] * 8u);
 #pragma unroll
     for (int k = 0; k < NC; ++k) {
-        if (INIT) {
+        if (INIT || P.no_xq) {   // no_xq: Q(xa) is recomputed from xa instead of kept in its own array
             xqh[k] = q2(P, x[k].x, x[k].y);                       // Q(xa), :321-322
-            sts32(h.xq4 + (uint32_t)jlp[k] * 4u, h2u(xqh[k]));
+            if (!P.no_xq) sts32(h.xq4 + (uint32_t)jlp[k] * 4u, h2u(xqh[k]));
         } else {
             xqh[k] = u2h(lds32(h.xq4 + (uint32_t)jlp[k] * 4u));
         }

@@ -95,9 +95,11 @@ struct H2SpecPolicy {
             sts64f(h.xa8 + XA8, x);
         }
         if constexpr (MODE == VN_INIT_SMEM || (MODE == VN_ITER && VNW)) x = lds64f(h.xa8 + XA8);
-        if constexpr (INIT) {
+        // With VN weights xa is loaded anyway, so Q(xa) is recomputed (6 instructions) instead of kept in an array of its
+        // own: 9 KB less shared memory per CTA on WiMAX, i.e. a fourth resident CTA (KParams::no_xq, set by the host).
+        if constexpr (INIT || VNW) {
             xqh = q2(P, x.x, x.y);                       // Q(xa), :321-322
-            sts32(h.xq4 + XQ4, h2u(xqh));
+            if constexpr (!VNW) sts32(h.xq4 + XQ4, h2u(xqh));
         } else {
             xqh = u2h(lds32(h.xq4 + XQ4));
         }
