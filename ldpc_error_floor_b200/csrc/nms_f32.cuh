@@ -138,38 +138,34 @@ __device__ __forceinline__ void f32_row_weights(const KParams &P, int t, int i, 
     w1 = P.sharing1 != 0 ? ucn_weight(P, t, i, 0) : w0;
 }
 
-// (min1, min2) of |raw[.]|
-template <int DC>
-__device__ __forceinline__ void f32_min12(const uint32_t (&raw)[DC], float &m1, float &m2) {
-    m1 = 10000.0f; m2 = 10000.0f;   // all-masked row -> 10000 (:248)
-    if constexpr (DC >= 6) {        // two independent chains over even / odd edges: half the dependency depth
-        float n1 = 10000.0f, n2 = 10000.0f;
-#pragma unroll
-        for (int p = 0; p < DC; p += 2) {
-            const float a = fabsf(__uint_as_float(raw[p]));
-            const float tmx = fmaxf(m1, a);
-            m1 = fminf(m1, a);
-            m2 = fminf(m2, tmx);
-            if (p + 1 < DC) {
-                const float b = fabsf(__uint_as_float(raw[p + 1]));
-                const float tnx = fmaxf(n1, b);
-                n1 = fminf(n1, b);
-                n2 = fminf(n2, tnx);
-            }
-        }
-        const float hi = fmaxf(m1, n1);
-        m1 = fminf(m1, n1);
-        m2 = fminf(hi, fminf(m2, n2));
+// (min1, min2) of |raw[LO..HI)| as a tournament (see h2_min12): 35 operations for 15 edges instead of 45
+template <int DC, int LO, int HI>
+__device__ __forceinline__ void f32_min12t(const uint32_t (&raw)[DC], float &m1, float &m2) {
+    if constexpr (HI - LO == 1) {
+        m1 = fabsf(__uint_as_float(raw[LO]));
+        m2 = 10000.0f;   // all-masked row -> 10000 (:248)
+    } else if constexpr (HI - LO == 2) {
+        const float a = fabsf(__uint_as_float(raw[LO])), b = fabsf(__uint_as_float(raw[LO + 1]));
+        m1 = fminf(a, b);
+        m2 = fmaxf(a, b);
+    } else if constexpr (HI - LO == 3) {
+        f32_min12t<DC, LO, LO + 2>(raw, m1, m2);
+        const float a = fabsf(__uint_as_float(raw[LO + 2]));
+        const float t = fmaxf(m1, a);
+        m1 = fminf(m1, a);
+        m2 = fminf(m2, t);
     } else {
-#pragma unroll
-        for (int p = 0; p < DC; ++p) {
-            const float a = fabsf(__uint_as_float(raw[p]));
-            const float tmx = fmaxf(m1, a);
-            m1 = fminf(m1, a);
-            m2 = fminf(m2, tmx);
-        }
+        constexpr int MID = LO + (((HI - LO) / 2 + 1) & ~1);   // even-sized left half: its leaves are pairs
+        float a1, a2, b1, b2;
+        f32_min12t<DC, LO, MID>(raw, a1, a2);
+        f32_min12t<DC, MID, HI>(raw, b1, b2);
+        const float hi = fmaxf(a1, b1);
+        m1 = fminf(a1, b1);
+        m2 = fminf(fminf(hi, a2), b2);
     }
 }
+template <int DC>
+__device__ __forceinline__ void f32_min12(const uint32_t (&raw)[DC], float &m1, float &m2) { f32_min12t<DC, 0, DC>(raw, m1, m2); }
 
 // one check row held in registers, one weight per row.  a0: byte address of msg[e0][q]; stride4 = LP*4
 // par: this lane's syndrome bit of the previous hard decision (f32_row_syndrome)
