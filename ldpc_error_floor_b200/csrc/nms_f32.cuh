@@ -15,8 +15,9 @@
 //    instructions per row instead of 8 per edge, and the float messages stay untouched (the packed kernels' trick of
 //    parking the bit in the mantissa LSB would cost the float path one unit in the last place per message);
 //  * per-edge work moved to the check row where it commutes with the minimum: a V->C value only reaches the output
-//    through (min1, min2) and its sign, so the zero rule (:230; a V->C word is never -0.0 because xin never is) and,
-//    on the float path, the clip of :225-226 are applied to the two minima instead of to every edge.
+//    through (min1, min2) and its sign, so on the float path the clip of :225-226 is applied to the two minima instead
+//    of to every edge, and the zero rule (:230, "0 counts as +1e-4"; a V->C word is never -0.0 because xin never is)
+//    costs one compare per row: only a row whose smallest magnitude is 0 patches its zeros and redoes its minima.
 #pragma once
 #include "nms_h2.cuh"   // lds32 / ldsf / sts32
 
@@ -97,8 +98,7 @@ __device__ __forceinline__ uint32_t f32_row_mag(const KParams &P, uint32_t mb, f
     const float Z = 0.0001f;
     if constexpr (QM == 0 && CLAMP) m = fminf(m, P.clip);             // :225-226
     if constexpr (QM == 2 && CLAMP) m = fminf(m, P.sat_bound);        // same; a no-op after Q() on the quantised path
-    const float adj = m == 0.0f ? 0.0f : __fadd_rn(m, -Z);            // :230 then :250: 0 -> 1e-4 -> 0
-    m = m > Z ? m : adj;                                              // :250
+    m = m > Z ? m : __fadd_rn(m, -Z);                                 // :250 (a zero V->C arrives here as 1e-4, :230)
     const float x1 = __fmul_rn(fabsf(m), w);                          // :267-298
     const float x2 = f32_sat_pos<QM>(P, x1 > 0.0f ? x1 : 0.0f);       // :308-313
     return __float_as_uint(x2) ^ (__float_as_uint(m) & SIGN1);
@@ -180,6 +180,11 @@ __device__ __forceinline__ void cn_row_f32(const KParams &P, uint32_t a0, uint32
     for (int p = 0; p < DC; ++p) sx ^= raw[p];
     float m1, m2;
     f32_min12<DC>(raw, m1, m2);
+    if (m1 == 0.0f) {   // a zero V->C counts as +1e-4 (:230): rare, so patch the zeros and redo the minima
+#pragma unroll
+        for (int p = 0; p < DC; ++p) raw[p] = __uint_as_float(raw[p]) == 0.0f ? __float_as_uint(0.0001f) : raw[p];
+        f32_min12<DC>(raw, m1, m2);
+    }
     const float w = par ? w1 : w0;   // unsatisfied check -> UCN weight (:275,:285,:295)
     // C->V of edge p is negative iff the number of positive OTHER inputs is even (:251-254; an input is never 0, :230):
     // sign bit = sign(adjusted min) ^ (dc & 1) ^ parity(negative inputs) ^ own sign
@@ -193,6 +198,12 @@ __device__ __forceinline__ void cn_row_f32(const KParams &P, uint32_t a0, uint32
     }
 }
 
+// magnitude of a V->C word as the check sees it: a zero counts as +1e-4 (:230)
+__device__ __forceinline__ float f32_eff(uint32_t r) {
+    const float a = fabsf(__uint_as_float(r));
+    return a == 0.0f ? 0.0001f : a;
+}
+
 // any degree, any weight sharing (per-edge weights included): two passes over shared memory
 template <int QM>
 static __device__ __noinline__ void cn_row_f32_generic(const KParams &P, uint32_t a0, uint32_t stride4, int dc, int t, int i,
@@ -202,7 +213,7 @@ static __device__ __noinline__ void cn_row_f32_generic(const KParams &P, uint32_
     for (int p = 0; p < dc; ++p) {
         const uint32_t r = lds32(a0 + p * stride4);
         sx ^= r;
-        const float a = fabsf(__uint_as_float(r));
+        const float a = f32_eff(r);
         const float tmx = fmaxf(m1, a);
         m1 = fminf(m1, a);
         m2 = fminf(m2, tmx);
@@ -213,7 +224,7 @@ static __device__ __noinline__ void cn_row_f32_generic(const KParams &P, uint32_
         for (int p = 0; p < dc; ++p) {
             const uint32_t r = lds32(a0 + p * stride4);
             const float w = ucn ? ucn_weight(P, t, i, e0 + p) : cn_weight(P, t, i, e0 + p);
-            const bool ismin = !(fabsf(__uint_as_float(r)) > m1);
+            const bool ismin = !(f32_eff(r) > m1);
             const uint32_t v = (ismin && dc < 2) ? f32_row_mag<QM, false>(P, __float_as_uint(m2), w)
                                                  : f32_row_mag<QM, true>(P, __float_as_uint(ismin ? m2 : m1), w);
             sts32(a0 + p * stride4, v ^ Pbit ^ (r & SIGN1));
@@ -224,7 +235,7 @@ static __device__ __noinline__ void cn_row_f32_generic(const KParams &P, uint32_
         const uint32_t B = (dc >= 2 ? f32_row_mag<QM, true>(P, __float_as_uint(m2), w) : f32_row_mag<QM, false>(P, __float_as_uint(m2), w)) ^ Pbit;
         for (int p = 0; p < dc; ++p) {
             const uint32_t r = lds32(a0 + p * stride4);
-            sts32(a0 + p * stride4, (fabsf(__uint_as_float(r)) > m1 ? A : B) ^ (r & SIGN1));
+            sts32(a0 + p * stride4, (f32_eff(r) > m1 ? A : B) ^ (r & SIGN1));
         }
     }
 }
