@@ -180,7 +180,22 @@ def load_block_weights(cfg: RunConfig, graph: BaseGraph, training_iter_start: in
         if code <= 0:
             continue
         width = formats.weight_width(code, i, graph.M, graph.N, graph.E)
-        rows = np.full((training_iter_end, width), cfg.init_VN_weight if i == 2 else cfg.init_weight, dtype=np.float32)
+        para_init = cfg.init_VN_weight if i == 2 else cfg.init_weight
+        if para_init == -1:
+            # tf.truncated_normal_initializer(mean = (min + max) / 2, stddev = 0.1) (:427-428): normal draws, those beyond
+            # two standard deviations redrawn; TF's own generator is not reproduced, the seed is the run's noise seed
+            rng = np.random.RandomState(1074 + cfg.seed_in + 104729 * i)
+            draw = rng.normal(size=(training_iter_end, width))
+            while True:
+                bad = np.abs(draw) > 2.0
+                if not bad.any():
+                    break
+                draw[bad] = rng.normal(size=int(bad.sum()))
+            rows = ((cfg.Min_weight + cfg.Max_weight) / 2 + 0.1 * draw).astype(np.float32)
+            if code in (4, 5):   # temporal sharing: one variable serves every iteration >= fixed_iter (:411-414)
+                rows[cfg.fixed_iter:] = rows[min(cfg.fixed_iter, training_iter_end - 1)]
+        else:
+            rows = np.full((training_iter_end, width), para_init, dtype=np.float32)
         if prev is not None:
             rows[:training_iter_start] = prev.blocks[i][:training_iter_start]
         if init is not None:

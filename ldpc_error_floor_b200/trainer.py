@@ -5,6 +5,7 @@ validation is the fused Monte-Carlo / decode path; this module is the host loop 
 main_Base.py:108-202 (blocks of `iter_step` iterations, `epoch_input` epochs, evaluate-before-train at epoch 0,
 weight dump every epoch, best-on-validation copy), Adam as TF 1.x defines it, the [Min_weight, Max_weight] clip
 constraint of weight_init (Main_Functions.py:434), the eta / learning-rate discounts (:192-196).
+Temporal sharing (sharing code 4) ties the rows of the iterations >= fixed_iter; init_weight = -1 draws truncated normals.
 Samples: the reference draws numpy MT19937 normals; here the Philox generator of the library, cycling through the
 SNR list frame by frame like create_mix_epoch (Print_Functions.py:36).
 """
@@ -76,7 +77,11 @@ def train_block(cfg: drivers.RunConfig, training_iter_start: int, training_iter_
     g = BaseGraph(proto, c.z_value, (c.punct_start, c.punct_end), (c.short_start, c.short_end), name=c.filename)
     SNR_sigma = g.sigma(SNR_Matrix)
     T = training_iter_end
-    ws = drivers.load_block_weights(c, g, training_iter_start, T, init)
+    ws_file = drivers.load_block_weights(c, g, training_iter_start, T, init)   # blocks under cfg.sharing's codes, T rows each
+    tied = [i for i, code in enumerate(ws_file.sharing) if code in (4, 5)]
+    # temporal sharing: the decoder takes the equivalent per-iteration table (code 4 -> per-edge rows; its UCN twin has no
+    # branch in build_neural_network and is only carried through to the weight file)
+    ws = formats.expand_temporal(ws_file, T, c.fixed_iter) if tied else ws_file
     dec = NMSDecoder(g, ws, iters=T, decoding_type=c.decoding_type, q_bit=c.q_bit, clip_llr=c.clip_LLR, device=device,
                      systematic=c.systematic)
     t_lo = max(training_iter_start - c.fixed_init, c.fixed_iter)                      # Main_Functions.py:342, 368
@@ -104,6 +109,12 @@ def train_block(cfg: drivers.RunConfig, training_iter_start: int, training_iter_
                 else:
                     xa = make_batch(dec, SNR_sigma, c.batch_size, seed, ((epoch - 1) * nbatch + b) * c.batch_size * 16)
                 loss, grads, _ = dec.train_grad(xa, iter_lo=t_lo, loss_type=c.loss_type, etha=etha)
+                for i in tied:
+                    # temporal sharing (codes 4 / 5): ONE variable serves every iteration >= fixed_iter (weight_init
+                    # :411-414, build_neural_network :299-304), so its gradient is the sum over those iterations; the
+                    # rows start equal and see equal Adam updates, so they stay tied (print_weight writes them expanded)
+                    if i in grads and c.fixed_iter < T:
+                        grads[i][c.fixed_iter:] = grads[i][c.fixed_iter:].sum(axis=0, keepdims=True)
                 adam.step(params, grads, lr)
                 for i in params:                                                            # clip constraint (:434)
                     np.clip(params[i], c.Min_weight, c.Max_weight, out=params[i])
@@ -112,7 +123,10 @@ def train_block(cfg: drivers.RunConfig, training_iter_start: int, training_iter_
                 avg += loss / nbatch
         t_train = time.time() - t0
         cur = formats.WeightSet(list(ws.sharing), {i: p.astype(np.float32) for i, p in params.items()})
-        formats.write_weights(c.path(formats.weights_filename(c.out_filename, T)), cur)     # print_weight (:74-96)
+        # print_weight (:74-96): header = the run's sharing codes, temporal blocks written as their T expanded rows
+        out_ws = cur if not tied else formats.WeightSet(list(ws_file.sharing), {i: (params[i].astype(np.float32) if i in params
+                                                                                     else ws_file.blocks[i]) for i in ws_file.blocks})
+        formats.write_weights(c.path(formats.weights_filename(c.out_filename, T)), out_ws)
         txt = (f"* Training_iter_start: {training_iter_start} training_iter_end: {T} epoch: [{epoch}/{n_ep}]\n"
                f"Training loss: {drivers.FTE([avg])}\n")
         with open(c.perf_filename, "a") as fh:

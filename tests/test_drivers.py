@@ -122,3 +122,24 @@ def test_load_block_weights_rules(tmp_path, codes):
         assert np.all(ws.blocks[i][20:] == 1.0)
     base = drivers.load_block_weights(drivers.RunConfig(root=str(tmp_path)), g, 0, 20)
     assert base.sharing == [3, 0, 3] and set(base.blocks) == {0, 2} and np.all(base.blocks[0] == 1.0)
+
+
+def test_random_weight_init_and_temporal_tie(tmp_path):
+    """init_weight = -1 (Main_Functions.py:427-428): truncated normal around (Min + Max) / 2, stddev 0.1, nothing beyond
+    two standard deviations; with temporal sharing (code 4) the rows of iterations >= fixed_iter are ONE variable."""
+    from ldpc_error_floor_b200 import drivers
+    from ldpc_error_floor_b200.graph import BaseGraph
+    d = dict(np.load(os.path.join(os.path.dirname(__file__), "golden", "codes.npz")))
+    g = BaseGraph(d["graph/wimax/proto"].astype(np.int32), 24)
+    cfg = drivers.RunConfig(root=str(tmp_path), sharing=[1, 0, 2], init_weight=-1, init_VN_weight=-1, iters_max=8, iter_step=8)
+    ws = drivers.load_block_weights(cfg, g, 0, 8)
+    assert ws.blocks[0].shape == (8, g.E) and ws.blocks[2].shape == (8, g.N)
+    for b in (ws.blocks[0], ws.blocks[2]):
+        assert np.all(np.abs(b - 1.0) <= 0.2 + 1e-6) and 0.07 < b.std() < 0.1 and abs(b.mean() - 1.0) < 0.02
+    assert not np.array_equal(ws.blocks[0][0], ws.blocks[0][1])
+    again = drivers.load_block_weights(cfg, g, 0, 8)
+    assert np.array_equal(again.blocks[0], ws.blocks[0])            # seeded by the run's seed_in
+    cfg4 = drivers.RunConfig(root=str(tmp_path), sharing=[4, 0, 2], init_weight=-1, iters_max=8, iter_step=5, fixed_iter=3)
+    w4 = drivers.load_block_weights(cfg4, g, 0, 8)
+    assert all(np.array_equal(w4.blocks[0][t], w4.blocks[0][3]) for t in range(3, 8))
+    assert not np.array_equal(w4.blocks[0][2], w4.blocks[0][3])

@@ -67,3 +67,29 @@ def test_set_weights_and_a_short_training_run(tmp_path):
     for i in range(3):
         assert np.array_equal(res2.weights.blocks[i][:6], best.blocks[i])
         assert not np.array_equal(res2.weights.blocks[i][6:], np.full_like(res2.weights.blocks[i][6:], 0.5))
+
+
+def test_temporal_sharing_training_keeps_the_shared_rows_tied(tmp_path):
+    """sharing code 4 (main_Base.py:24, weight_init :411-414): iterations >= fixed_iter share ONE per-edge variable.
+    After a few Adam steps the rows 3..5 are still equal to each other, have moved, rows 0..2 (below t_lo) have not, and
+    the weight file carries the run's header with the T expanded rows (print_weight :87-94)."""
+    import materialize_files
+    from ldpc_error_floor_b200 import drivers, formats, trainer
+    root = str(tmp_path)
+    materialize_files.materialize(root)
+    cfg = drivers.RunConfig(root=root, sharing=[4, 0, 2], decoding_type=2, q_bit=5, loss_type=0, etha_start=0.0, iters_max=6,
+                            fixed_iter=3, iter_step=3, batch_size=64, training_num=64 * 6, valid_num=2048, valid_flag=1,
+                            SNR_Matrix=np.array([2.5, 3.0]), learn_rate_start=0.02, init_weight=0.9, init_VN_weight=1.0)
+    E = 88
+    start = formats.WeightSet([4, 0, 2], {0: np.full((6, E), 0.9, np.float32), 2: np.ones((6, 24), np.float32)})
+    res = trainer.train_block(cfg, 3, 6, init=start, epochs=2, log=None)
+    w = res.weights
+    assert w.sharing[0] == 1 and w.blocks[0].shape == (6, E)          # the decoder's per-iteration form
+    assert np.array_equal(w.blocks[0][3], w.blocks[0][4]) and np.array_equal(w.blocks[0][3], w.blocks[0][5])
+    # the dump of the last epoch (res.weights is the best-on-validation copy, possibly the untrained epoch 0)
+    f = formats.read_weights(os.path.join(root, "Weights", "C0_wman_N0576_R34_z24_Weight_End6.txt"))
+    assert list(f.sharing) == [4, 0, 2] and f.blocks[0].shape == (6, E)
+    assert np.array_equal(f.blocks[0][3], f.blocks[0][4]) and np.array_equal(f.blocks[0][3], f.blocks[0][5])
+    assert np.abs(f.blocks[0][3] - 0.9).max() > 1e-3                  # the shared variable was trained ...
+    assert np.array_equal(f.blocks[0][:3], np.full((3, E), 0.9, np.float32))   # ... the iterations below t_lo were not
+    assert np.abs(f.blocks[2][3:] - 1.0).max() > 1e-4 and not np.array_equal(f.blocks[2][3], f.blocks[2][5])   # VN rows: untied
