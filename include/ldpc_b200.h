@@ -100,7 +100,8 @@ int ldpc_graph_sigma(const ldpc_graph_t *g, const double *snr_db, int32_t n, int
  * 2 per proto node, 3 one scalar per iteration); rules of check_params apply
  * (Main_Functions.py:515-521).  w_cn / w_ucn / w_vn: HOST float32 [T, width], width =
  * 1 / M (CN,UCN) or N (VN) / E by code (Main_Functions.py:397-405); NULL when the code is 0.
- * decoding_type 1 = min-sum (float32 messages, clip +-clip_llr), 2 = quantised min-sum
+ * decoding_type 0 = sum-product (tanh / atanh check update, Main_Functions.py:238-245; decode and Monte-Carlo only, no
+ * training kernel), 1 = min-sum (float32 messages, clip +-clip_llr), 2 = quantised min-sum
  * (q_bit in {5,6,-5,4,3}, Main_Functions.py:483-492).  Replaces weight_init
  * (Main_Functions.py:387-439) + the graph constants of build_neural_network. */
 int ldpc_decoder_create(const ldpc_graph_t *g, const int32_t sharing[3], int32_t T,

@@ -360,8 +360,10 @@ extern "C" int ldpc_decoder_create2(const ldpc_graph_t *g, const int32_t sharing
     // 87-94), which makes it per-edge sharing; its UCN twin has no branch in build_neural_network (:299-304)
     int32_t sharing[3] = {sharing_in[0], sharing_in[1], sharing_in[2]};
     if (sharing[0] == 4) { sharing[0] = 1; sharing[1] = 0; }
-    if (decoding_type != 1 && decoding_type != 2)
-        return fail(LDPC_E_UNSUPPORTED, "decoding_type %d (1 = min-sum, 2 = quantised min-sum)", decoding_type);
+    if (decoding_type < 0 || decoding_type > 2)
+        return fail(LDPC_E_UNSUPPORTED, "decoding_type %d (0 = sum-product, 1 = min-sum, 2 = quantised min-sum)", decoding_type);
+    if (decoding_type == 0 && g->info.max_dc > 64)
+        return fail(LDPC_E_LIMIT, "row degree > 64 in sum-product mode");
     float qk = 1.f, qmax = 0.f;
     if (decoding_type == 2) {
         switch (q_bit) {   // Main_Functions.py:483-492
@@ -467,7 +469,7 @@ extern "C" int ldpc_decoder_create2(const ldpc_graph_t *g, const int32_t sharing
     std::memset(&P, 0, sizeof P);
     P.M = g->M; P.N = g->N; P.E = g->E; P.z = g->z; P.NZ = g->N * g->z;
     P.Fp = d->geom.Fp; P.FB = d->geom.FB; P.L = d->geom.L; P.LP = d->geom.LP; P.C = d->geom.C; P.R = d->geom.R;
-    P.qms = qms; P.qmagic = 12582912.0f / qk; P.qmax = qmax; P.clip = clip_llr;
+    P.qms = qms; P.sp = decoding_type == 0; P.qmagic = 12582912.0f / qk; P.qmax = qmax; P.clip = clip_llr;
     P.sat_magic = qms ? P.qmagic : 0.0f; P.sat_bound = qms ? qmax : clip_llr;
     P.sharing0 = sharing[0]; P.sharing1 = sharing[1]; P.sharing2 = sharing[2];
     P.wc = wc; P.wu = wu; P.wv = wv;
@@ -864,6 +866,7 @@ extern "C" int ldpc_train_grad(const ldpc_decoder_t *dc, const float *llr_dev, i
     if (T < 1 || T > d->T || iter_lo < 0 || iter_lo >= T) return fail(LDPC_E_INVALID, "train_grad: iterations [%d, %d) outside 0..%d", iter_lo, T, d->T);
     if (loss_type < 0 || loss_type > 2) return fail(LDPC_E_INVALID, "train_grad: loss_type %d (0 BCE, 1 soft BER, 2 FER)", loss_type);
     if (d->g.info.max_dc > 64) return fail(LDPC_E_LIMIT, "train_grad: row degree %d > 64", d->g.info.max_dc);
+    if (d->decoding_type == 0) return fail(LDPC_E_UNSUPPORTED, "train_grad: sum-product (decoding_type 0) has no training kernel");
     DeviceGuard guard(d->device);
     if (!guard.ok) return fail(LDPC_E_CUDA, "cudaSetDevice(%d) failed", d->device);
     std::lock_guard<std::mutex> lock(d->mu);

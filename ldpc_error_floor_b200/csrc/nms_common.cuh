@@ -32,6 +32,7 @@ struct KParams {
     int R;    // task slots (warps per chunk); CTA = C*R warps
     // arithmetic
     int qms;           // 1: quantised min-sum
+    int sp;            // 1: sum-product check update (decoding_type 0, Main_Functions.py:238-245), float kernels only
     float qmagic;      // 1.5*2^23/qk: (x + qmagic) - qmagic rounds x half-to-even to the quantiser step 1/qk
     float qmax;        // Q(x) = clamp(round_to_step(x), +-qmax)            (Main_Functions.py:483-492)
     float clip;        // clip_LLR (main_Base.py:69)

@@ -112,7 +112,7 @@ __device__ __forceinline__ void gen_llr4(const KParams &P, unsigned long long F,
         const int k = 4 * quad + k4 + 1;   // 1-based bit index
         float llr = __fmul_rn(__fadd_rn(__fmul_rn(n[k4], P.sigma), -1.0f), P.two_over_s2);
         if (P.qms) llr = qf(P, llr);                                          // :49-50
-        if (P.punct_s > 0 && k >= P.punct_s && k <= P.punct_e) llr = 0.0f;    // :53-57
+        if (P.punct_s > 0 && k >= P.punct_s && k <= P.punct_e) llr = P.sp ? 0.001f : 0.0f;    // :53-57
         if (P.short_s > 0 && k >= P.short_s && k <= P.short_e) llr = -P.clip; // :59-60
         out[k4] = llr;
     }

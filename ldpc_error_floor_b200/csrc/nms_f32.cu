@@ -32,7 +32,9 @@ struct F32Policy {
             const uint32_t a0 = a00 + (uint32_t)e0 * stride4;
             const uint32_t par = pad ? f32_row_syndrome<true>(P, h, hb4, e0, dc) : f32_row_syndrome<false>(P, h, hb4, e0, dc);
             bad |= par;
-            if (DCB == 0 || P.sharing0 == 1) {
+            if (P.sp) {
+                cn_row_f32_sp(P, a0, stride4, dc, t, i, e0, par);
+            } else if (DCB == 0 || P.sharing0 == 1) {
                 cn_row_f32_generic<2>(P, a0, stride4, dc, t, i, e0, par);
             } else {
                 float w0, w1;

@@ -240,6 +240,34 @@ static __device__ __noinline__ void cn_row_f32_generic(const KParams &P, uint32_
     }
 }
 
+// sum-product check update (decoding_type 0, Main_Functions.py:238-245): t_p = tanh(-clip(v_p) / 2), a zero factor counts
+// as 1 (the reference cannot tell a zero message from a masked entry of its dense tile), product over the OTHER edges in
+// E(C) order, clipped at +-(1 - 1e-7) -- in float32 that is 1 - 2^-23 -- and x0 = -2 atanh(product); then the common
+// tail |x0| w -> ReLU -> clip -> sign (:267-316).  No zero rule on the inputs (:229 is min-sum only).  Any degree up to
+// 64; the factors are staged in the message words themselves.  Not a hot path: O(dc^2) products, libm tanhf / atanhf.
+static __device__ __noinline__ void cn_row_f32_sp(const KParams &P, uint32_t a0, uint32_t stride4, int dc, int t, int i, int e0,
+                                                  uint32_t par) {
+    const float lim = 1.0f - 1e-7f;
+    for (int p = 0; p < dc; ++p) {
+        const float v = fminf(fmaxf(__uint_as_float(lds32(a0 + p * stride4)), -P.clip), P.clip);   // :225-226
+        const float th = tanhf(__fmul_rn(-0.5f, v));
+        sts32(a0 + p * stride4, __float_as_uint(th == 0.0f ? 1.0f : th));
+    }
+    const bool ucn = P.sharing1 != 0 && par;
+    float outv[64];
+    for (int p = 0; p < dc; ++p) {
+        float prod = 1.0f;
+        for (int p2 = 0; p2 < dc; ++p2)
+            if (p2 != p) prod = __fmul_rn(prod, __uint_as_float(lds32(a0 + p2 * stride4)));
+        const float x0 = __fmul_rn(-2.0f, atanhf(fminf(fmaxf(prod, -lim), lim)));
+        const float w = P.sharing0 == 0 ? 1.0f : (ucn ? ucn_weight(P, t, i, e0 + p) : cn_weight(P, t, i, e0 + p));
+        const float x1 = __fmul_rn(fabsf(x0), w);
+        const float x2 = fminf(x1 > 0.0f ? x1 : 0.0f, P.clip);
+        outv[p] = x0 > 0.0f ? x2 : (x0 < 0.0f ? -x2 : 0.0f);                                           // :316
+    }
+    for (int p = 0; p < dc; ++p) sts32(a0 + p * stride4, __float_as_uint(outv[p]));
+}
+
 // extrinsic sums of a column held in registers, in the order of the reference restatement (oracle/nms_oracle.c): the
 // OTHER C->V values added one by one in ascending E(C) order.  The ascending sum that skips edge u starts with the
 // prefix c_0 + .. + c_{u-1}, which all edges share with the APP sum: dv (dv - 1) / 2 + dv additions instead of

@@ -90,6 +90,10 @@ struct F32SpecPolicy {
             const uint32_t a0 = a00 + tk.x;
             const uint32_t par = row_syndrome(et2c, hb4, (int)(tk.x / LP4), dc);
             bad |= par;
+            if (QM == 0 && P.sp) {   // sum-product check update (decoding_type 0)
+                cn_row_f32_sp(P, a0, LP4, dc, t, i, (int)(tk.x / LP4), par);
+                continue;
+            }
             if (P.sharing0 == 1) {   // per-edge weights: the compact two-pass code
                 cn_row_f32_generic<QM>(P, a0, LP4, dc, t, i, (int)(tk.x / LP4), par);
                 continue;

@@ -76,7 +76,7 @@ class NMSDecoder:
     """Flooding neural min-sum decoder for one (graph, weight set, arithmetic mode) on one GPU.
 
     weights: WeightSet (sharing codes + [T, width] blocks, format F2); `iters` defaults to the
-    number of weight rows.  decoding_type 1 = min-sum, 2 = quantised min-sum (q_bit as in
+    number of weight rows.  decoding_type 0 = sum-product, 1 = min-sum, 2 = quantised min-sum (q_bit as in
     Main_Functions.py:483-492).  A "post decoder" is simply an NMSDecoder built from the boosted
     weight file (base rows followed by post rows)."""
 

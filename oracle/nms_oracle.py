@@ -121,7 +121,7 @@ def decode(g: OracleGraph, xa, sharing, weights, T, decoding_type=2, q_bit=5, cl
     xa: f32 [B, N, z] (log p1/p0).  weights: {0: cn[T,w], 1: ucn[T,w], 2: vn[T,w]} for the
     non-zero sharing codes.  Returns dict(app [T,B,N*z] f32, synd [T,B] bool (any check
     unsatisfied by APP_t >= 0), ucn [T,B,M,z] bool (mask consumed at iteration t))."""
-    assert decoding_type in (1, 2)
+    assert decoding_type in (0, 1, 2)      # 0 = sum-product (:238-245), 1 = min-sum, 2 = quantised min-sum
     xa = np.ascontiguousarray(xa, dtype=F32)
     B = xa.shape[0]
     z, E, M, N = g.z, g.E, g.M, g.N
@@ -171,12 +171,27 @@ def decode(g: OracleGraph, xa, sharing, weights, T, decoding_type=2, q_bit=5, cl
             v2cc = quantize(v2cc, q_bit)
         else:
             v2cc = np.clip(v2cc, -clip, clip)
-        v2cc = v2cc + F32(0.0001) * (F32(1) - (np.abs(v2cc) > 0).astype(F32))
+        if decoding_type in (1, 2):                               # :229-230 (not for sum-product)
+            v2cc = v2cc + F32(0.0001) * (F32(1) - (np.abs(v2cc) > 0).astype(F32))
         # ---- D6  CN update (:231-254)
         out = np.empty((B, E, z), dtype=F32)
         for i in range(M):
             es = g.row_edges[i]
             vals = v2cc[:, es, :]                                 # [B, dc, z]
+            if decoding_type == 0:
+                # sum-product (:238-245): tanh(-x/2), a zero factor (a masked entry of the dense tile, but also a true
+                # zero message) counts as 1, product over the other edges in E(C) order, clip at +-(1 - 1e-7) as float32
+                # (= 1 - 2^-23), -2 atanh
+                th = np.tanh(F32(-0.5) * vals).astype(F32)
+                th = th + (F32(1) - (np.abs(th) > 0).astype(F32))
+                lim = F32(1) - F32(1e-7)
+                for p, e in enumerate(es):
+                    prod = np.ones((B, z), dtype=F32)
+                    for p2 in range(len(es)):
+                        if p2 != p:
+                            prod = prod * th[:, p2, :]
+                    out[:, e, :] = F32(-2) * np.arctanh(np.clip(prod, -lim, lim)).astype(F32)
+                continue
             for p, e in enumerate(es):
                 others = np.delete(vals, p, axis=1)
                 if others.shape[1] == 0:

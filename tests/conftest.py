@@ -43,9 +43,11 @@ def load_case(name):
     return case
 
 
-def all_cases():
+def all_cases(sum_product=False):
+    """Golden decode cases; the sum-product ones (decoding_type 0, their own parity criterion) only on request."""
     import glob
-    return sorted(os.path.basename(p)[len("decode_"):-len(".npz")] for p in glob.glob(golden_path("decode_*.npz")))
+    names = sorted(os.path.basename(p)[len("decode_"):-len(".npz")] for p in glob.glob(golden_path("decode_*.npz")))
+    return [n for n in names if ("_sp_" in n) == sum_product]
 
 
 @pytest.fixture(scope="session")

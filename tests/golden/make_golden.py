@@ -171,6 +171,11 @@ def make_decode_cases():
     make_decode_case("5g_r073_z32_float_222_t50", "5g_r073_z32", sh, w, 50, 1, 5, 4, [3.0, 4.0])
     sh, w = shipped("5g_r033_z32_boost50")
     make_decode_case("5g_r033_z32_qms_222_t20", "5g_r033_z32", sh, w, 20, 2, 5, 4, [0.0, 1.0])
+    # sum-product (decoding_type 0, Main_Functions.py:238-245; punctured LLRs are 0.001, Print_Functions.py:53-55)
+    sh, w = shipped("wimax_base20")
+    make_decode_case("wimax_sp_333_t10", "wimax", sh, w, 10, 0, 5, 8, [2.0, 2.5, 3.0, 3.5])
+    sh, w = shipped("5g_r073_z32_boost50")
+    make_decode_case("5g_r073_z32_sp_222_t12", "5g_r073_z32", sh, w, 12, 0, 5, 6, [2.0, 3.0, 4.0])
     rng = np.random.RandomState(7)
     # no weights are shipped for these graphs: synthetic ones
     _, p, z, _, _ = graph_meta("5g_r073_z72")

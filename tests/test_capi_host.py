@@ -107,7 +107,8 @@ def test_decoder_argument_checks(codes):
     assert create([4, 0, 3]) == -3                      # temporal sharing passes the checks (no GPU here -> LDPC_E_CUDA)
     assert create([5, 0, 3]) == -2                      # code 5 has no branch in build_neural_network
     assert create([3, 0, 4]) == -1 and b"sharing[2]" in lib.ldpc_last_error()
-    assert create([3, 3, 3], dt=0) == -2                # sum-product: "next" row N3
+    assert create([3, 3, 3], dt=0) == -3                # sum-product passes the checks (no GPU here -> LDPC_E_CUDA)
+    assert create([3, 3, 3], dt=3) == -2                # decoding_type 3: undocumented in the reference, not offered
     assert create([3, 3, 3], qb=7) == -1
     assert create([3, 3, 3], T=0) == -1
     assert create([3, 3, 3], clip=0.0) == -1

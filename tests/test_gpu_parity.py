@@ -303,3 +303,58 @@ def test_full_size_batch_properties(dt):
     p = dec.decode(llr[perm].contiguous(), early_term=True)
     e = dec.decode(llr, early_term=True)
     assert torch.equal(p.hard_packed, e.hard_packed[perm]) and torch.equal(p.iters, e.iters[perm])
+
+
+@pytest.mark.parametrize("name", all_cases(sum_product=True))
+def test_sum_product_golden(name):
+    """decoding_type 0 (sum-product, Main_Functions.py:238-245) against the reference's own run (numpy tanh / arctanh).
+    Stated criterion: x0 = -2 atanh(prod tanh(-v/2)) has derivative 2 / (1 - x^2), so once messages saturate (|x0| > ~10,
+    1 - |x| < 1e-4) one unit in the last place of the product -- which is all that two correct float32 tanh
+    implementations can promise each other -- moves the output by up to several percent; TensorFlow's own Eigen tanh and
+    the numpy stand-in differ in the same way.  Hence: (1) hard decisions, flags and iteration counts identical on every
+    frame and iteration; (2) the iterations before saturation (t <= 2 here) within the 1e-5 bar of the other paths;
+    (3) at least 95 % of all APP values within 1e-5 relative; (4) every value within 10 %."""
+    import torch
+    case = load_case(name)
+    g, dec = build_decoder(case)
+    assert case["decoding_type"] == 0
+    xa = torch.from_numpy(case["xa"]).cuda()
+    r = dec.decode(xa, app="all", unpack=True)
+    app, ref = r.app.cpu().numpy(), case["app"]
+    err = np.abs(app - ref) / np.maximum(1.0, np.abs(ref))
+    assert np.array_equal(app >= 0, ref >= 0)
+    assert err[:3].max() <= REL_TOL, err[:3].max()
+    assert (err <= REL_TOL).mean() >= 0.95 and err.max() <= 0.1, ((err <= REL_TOL).mean(), err.max())
+    hard_ref, synd_ok, any_one, uncor_any, iters = oracle_flags(g, ref)
+    T = case["T"]
+    assert np.array_equal(r.iters.cpu().numpy(), iters)
+    flags = r.flags.cpu().numpy()
+    assert np.array_equal((flags & 1) != 0, synd_ok[T - 1]) and np.array_equal((flags & 2) != 0, uncor_any)
+    f = dec.decode(xa, app=None, early_term=True, unpack=True)      # unrolled VN phase + early termination
+    stop = iters - 1
+    assert np.array_equal(f.iters.cpu().numpy(), iters)
+    assert np.array_equal(f.hard.cpu().numpy().astype(bool), np.stack([hard_ref[stop[b], b] for b in range(ref.shape[1])]))
+
+
+def test_sum_product_monte_carlo_and_limits():
+    """The fused generator gives punctured bits the reference's 0.001 in sum-product mode (Print_Functions.py:53-55),
+    sum-product beats min-sum at the same Eb/N0, and the training kernel refuses decoding_type 0 with an error code."""
+    import torch
+    import ldpc_error_floor_b200 as L
+    from ldpc_error_floor_b200 import _lib
+    case = load_case("5g_r073_z32_sp_222_t12", )
+    g = L.BaseGraph(case["proto"], case["z"], case["punct"], case["short"])
+    ws = L.WeightSet([3, 0, 0], {0: np.ones((12, 1), np.float32)})
+    sp = L.NMSDecoder(g, ws, iters=12, decoding_type=0)
+    ms = L.NMSDecoder(g, ws, iters=12, decoding_type=1)
+    x = sp.generate(float(g.sigma([3.0])[0]), 64, seed=3).reshape(64, -1).cpu().numpy()
+    ps, pe = case["punct"]
+    assert np.all(x[:, ps - 1:pe] == np.float32(0.001))
+    assert np.all(ms.generate(float(g.sigma([3.0])[0]), 64, seed=3).reshape(64, -1).cpu().numpy()[:, ps - 1:pe] == 0)
+    sigma = float(g.sigma([2.5])[0])
+    c_sp, _, _ = sp.mc_run(sigma, 1 << 16, 5)
+    c_ms, _, _ = ms.mc_run(sigma, 1 << 16, 5)
+    c_sp, c_ms = c_sp.cpu().numpy(), c_ms.cpu().numpy()
+    assert c_sp[0] == c_ms[0] == 1 << 16 and 0 < c_sp[2] < c_ms[2]
+    with pytest.raises(_lib.LdpcError):
+        sp.train_grad(torch.zeros((4, g.NZ), dtype=torch.float32, device="cuda"))

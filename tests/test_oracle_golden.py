@@ -19,11 +19,25 @@ def _check(case, app):
 
 
 @pytest.mark.parametrize("name", all_cases())
-def test_c_oracle_matches_golden(name):
+def test_c_oracle_matches_golden(name):      # all_cases(): min-sum and quantised min-sum (no sum-product branch in C)
     from oracle import c_oracle
     case = load_case(name)
     out = c_oracle.decode(case["proto"], case["z"], case["xa"], case["sharing"], case["weights"], case["T"],
                           case["decoding_type"], case["q_bit"], case["clip"])
+    _check(case, out["app"])
+
+
+@pytest.mark.parametrize("name", all_cases(sum_product=True))
+def test_numpy_oracle_sum_product_matches_golden(name):
+    """decoding_type 0 (Main_Functions.py:238-245): the numpy restatement uses the same float32 tanh / arctanh as the
+    reference under the numpy TF shim and multiplies in E(C) order (numpy's reduce_prod over the dense tile may group the
+    factors differently: bit-identical on the 5G case, 4e-6 on WiMAX).  (The C oracle has no sum-product branch: libm's
+    tanhf differs from numpy's in the last place, and -2 atanh(x) amplifies one ulp of x near 1 to several percent -- see
+    test_gpu_parity.test_sum_product_golden for the criterion that follows from that.)"""
+    from oracle import nms_oracle as ob
+    case = load_case(name)
+    g = ob.OracleGraph(case["proto"], case["z"], case["punct"], case["short"])
+    out = ob.decode(g, case["xa"], case["sharing"], case["weights"], case["T"], 0, case["q_bit"], case["clip"])
     _check(case, out["app"])
 
 
