@@ -38,8 +38,8 @@ GEOMETRIES = {
 # float32 kernels (one frame per lane): same lanes as the packed choice
 GEOMETRIES_F32 = {
     "wimax": [(4, 2), (8, 2)], "wifi": [(7, 2)], "5g_r073_z72": [(4, 2), (3, 2)], "5g_r050_z64": [(2, 2)], "5g_r050_z32": [(4, 2)],
-    "5g_r033_z32": [(4, 2)], "5g_r073_z32": [(4, 2)],
-}   # the z = 1 codes (MacKay, BCH) stay on the generic float kernels: unrolling 48-96 nodes costs minutes of compile time
+    "5g_r033_z32": [(4, 2)], "5g_r073_z32": [(4, 2)], "mackay": [(32, 8)], "bch": [(32, 4)],
+}
 SKIP = {"polar"}   # row degree 64 > 32: generic two-pass kernel
 
 

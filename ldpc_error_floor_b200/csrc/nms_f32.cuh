@@ -98,7 +98,13 @@ __device__ __forceinline__ uint32_t f32_row_mag(const KParams &P, uint32_t mb, f
     const float Z = 0.0001f;
     if constexpr (QM == 0 && CLAMP) m = fminf(m, P.clip);             // :225-226
     if constexpr (QM == 2 && CLAMP) m = fminf(m, P.sat_bound);        // same; a no-op after Q() on the quantised path
-    m = m > Z ? m : __fadd_rn(m, -Z);                                 // :250 (a zero V->C arrives here as 1e-4, :230)
+    if constexpr (QM == 1) {
+        // on the quantiser grid the smallest non-zero magnitude is a whole step, so a zero (which counts as 1e-4, :230) is
+        // still the row's minimum and needs no patching: 0 -> 1e-4 -> 0 (:250)
+        m = m > Z ? m : (m == 0.0f ? 0.0f : __fadd_rn(m, -Z));
+    } else {
+        m = m > Z ? m : __fadd_rn(m, -Z);                             // :250 (a zero V->C arrives here as 1e-4, :230)
+    }
     const float x1 = __fmul_rn(fabsf(m), w);                          // :267-298
     const float x2 = f32_sat_pos<QM>(P, x1 > 0.0f ? x1 : 0.0f);       // :308-313
     return __float_as_uint(x2) ^ (__float_as_uint(m) & SIGN1);
@@ -180,7 +186,7 @@ __device__ __forceinline__ void cn_row_f32(const KParams &P, uint32_t a0, uint32
     for (int p = 0; p < DC; ++p) sx ^= raw[p];
     float m1, m2;
     f32_min12<DC>(raw, m1, m2);
-    if (m1 == 0.0f) {   // a zero V->C counts as +1e-4 (:230): rare, so patch the zeros and redo the minima
+    if (QM != 1 && m1 == 0.0f) {   // a zero V->C counts as +1e-4 (:230): rare on the float path, so patch the zeros and redo the minima
 #pragma unroll
         for (int p = 0; p < DC; ++p) raw[p] = __uint_as_float(raw[p]) == 0.0f ? __float_as_uint(0.0001f) : raw[p];
         f32_min12<DC>(raw, m1, m2);
