@@ -358,3 +358,33 @@ def test_sum_product_monte_carlo_and_limits():
     assert c_sp[0] == c_ms[0] == 1 << 16 and 0 < c_sp[2] < c_ms[2]
     with pytest.raises(_lib.LdpcError):
         sp.train_grad(torch.zeros((4, g.NZ), dtype=torch.float32, device="cuda"))
+
+
+@pytest.mark.parametrize("env", [("LDPC_B200_NO_SPEC",), ("LDPC_B200_NO_SPEC", "LDPC_B200_FORCE_GENERIC")])
+@pytest.mark.parametrize("name", ["wimax_qms_333_t20", "wimax_float_333_t20", "wimax_qms_q6_323_t6", "wimax_qms_112_t6",
+                                  "5g_r073_z32_float_222_t50", "5g_r050_z64_qms_222_t50", "mackay_float_300_t20"])
+def test_generic_kernels_give_the_same_results(name, env, monkeypatch):
+    """A graph that is not known at build time is served by the degree-bucketed generic kernels (table-driven code,
+    same arithmetic headers).  Forced here for shipped graphs: goldens, and bit-identity with the specialised kernels."""
+    import torch
+    case = load_case(name)
+    xa = torch.from_numpy(case["xa"]).cuda()
+    _, spec = build_decoder(case)
+    a = spec.decode(xa, app="all", early_term=False)
+    for e in env:
+        monkeypatch.setenv(e, "1")
+    g, gen = build_decoder(case)
+    assert "_kernel_" in gen.kernel_name and "_spec_" in spec.kernel_name, (gen.kernel_name, spec.kernel_name)
+    if "LDPC_B200_FORCE_GENERIC" in env:
+        assert gen.kernel_name.endswith("_0_0")
+    b = gen.decode(xa, app="all", early_term=False)
+    assert torch.equal(a.app, b.app) and torch.equal(a.hard_packed, b.hard_packed)
+    assert torch.equal(a.flags, b.flags) and torch.equal(a.iters, b.iters) and torch.equal(a.biterr, b.biterr)
+    ref = case["app"]
+    app = b.app.cpu().numpy()
+    if case["decoding_type"] == 2:
+        assert np.array_equal(app, ref)
+    else:
+        assert (np.abs(app - ref) / np.maximum(1.0, np.abs(ref))).max() <= REL_TOL and np.array_equal(app >= 0, ref >= 0)
+    e1, e2 = spec.decode(xa, early_term=True), gen.decode(xa, early_term=True)
+    assert torch.equal(e1.hard_packed, e2.hard_packed) and torch.equal(e1.iters, e2.iters) and torch.equal(e1.flags, e2.flags)
