@@ -365,6 +365,9 @@ def main():
     torch.cuda.synchronize()
     f_ms = f0.elapsed_time(f1) / 5
 
+    # ---- measured pipe rates on this box, same run: FP32/FMA pipe and the integer / min-max pipe
+    probe = _lib.alu_peak_probe(local_rank)
+
     pk, pk_src = peaks()
     sm_max = float(clocks.get("sm_max_mhz") or pk.get("sm_max_mhz", 1965.0))
     alu_peak = SM_COUNT * LANES_PER_SM * sm_max * 1e6 / 1e12          # T lane-ops/s at max clock
@@ -388,6 +391,10 @@ def main():
         "peak_source": f"148 SMs x 128 lanes x clocks.max.sm {sm_max:.0f} MHz (issue-slot roof; MEASURED_PEAKS.json "
                        f"carries no ALU figure)",
         "frac_at_observed_clock": ach / (SM_COUNT * LANES_PER_SM * sm_now * 1e6 / 1e12),
+        "peak_measured": {"unit": "Tlaneop/s", **{k: round(v, 3) for k, v in probe.items()},
+                          "how": "ldpc_alu_peak_probe: 8 independent chains per thread, 2048 threads/SM, volatile PTX; a packed "
+                                 "half2 instruction counts as one lane-op"},
+        "frac_of_measured_fp32_peak": ach / probe["ffma"],
         "frac_of_packed_roof": ach / (2 * alu_peak) if dec.packed else ach / alu_peak,
         "note": "peak = scalar lane-op issue roof; the packed fp16x2 kernel does two frames per lane-op, so its own "
                 "roof is 2x peak (frac_of_packed_roof)",

@@ -228,6 +228,13 @@ int ldpc_train_grad(const ldpc_decoder_t *d, const float *llr_dev, int64_t B, in
                     int32_t loss_type, double etha, double *loss_host, float *g_cn_host, float *g_ucn_host,
                     float *g_vn_host, float *app_dev);
 
+/* ---- measurement aid ----------------------------------------------------------------------------
+ * Instruction-issue micro-benchmark of the SM pipes the decode kernels are bound by (the ALU roofline is
+ * to be measured on the box).  kind: 0 FFMA, 6 FADD (FP32 / FMA pipe), 1 FMNMX, 2 LOP3, 3 IADD (integer / logic /
+ * min-max pipe), 4 HFMA2, 5 HMNMX2 (packed fp16x2).  *lane_ops_per_s = instructions x 32 lanes per second over the whole
+ * GPU (a packed instruction counts once).  Synchronous, a few milliseconds.  No counterpart in the reference. */
+int ldpc_alu_peak_probe(int32_t device, int32_t kind, double *lane_ops_per_s);
+
 /* kernels launched by this library since load (for bench.py's gpu_launches) */
 uint64_t ldpc_launch_count(void);
 

@@ -69,6 +69,7 @@ SYMBOLS = {
     "ldpc_decoder_set_weights": (ctypes.c_int, [_P, _P, _P, _P]),
     "ldpc_train_grad": (ctypes.c_int, [_P, _P, _I64, _I32, _I32, _I32, ctypes.c_double, ctypes.POINTER(ctypes.c_double),
                                        _P, _P, _P, _P]),
+    "ldpc_alu_peak_probe": (ctypes.c_int, [_I32, _I32, ctypes.POINTER(ctypes.c_double)]),
     "ldpc_launch_count": (ctypes.c_uint64, []),
 }
 
@@ -103,3 +104,16 @@ def check(rc: int) -> None:
     if rc != 0:
         msg = load().ldpc_last_error()
         raise LdpcError(rc, msg.decode() if msg else "unknown")
+
+
+ALU_PROBE_KINDS = {"ffma": 0, "fmnmx": 1, "lop3": 2, "iadd": 3, "hfma2": 4, "hmnmx2": 5, "fadd": 6}
+
+
+def alu_peak_probe(device: int = 0, kinds=("ffma", "fmnmx", "lop3", "hfma2", "hmnmx2")) -> dict:
+    """Measured instruction-issue rates (T lane-ops/s) of the SM pipes on `device` (ldpc_alu_peak_probe)."""
+    out = {}
+    for k in kinds:
+        v = ctypes.c_double(0.0)
+        check(load().ldpc_alu_peak_probe(int(device), ALU_PROBE_KINDS[k], ctypes.byref(v)))
+        out[k] = v.value / 1e12
+    return out

@@ -928,4 +928,17 @@ extern "C" int ldpc_train_grad(const ldpc_decoder_t *dc, const float *llr_dev, i
     return LDPC_OK;
 }
 
+extern "C" int nms_alu_probe(int device, int kind, double *lane_ops_per_s);
+
+extern "C" int ldpc_alu_peak_probe(int32_t device, int32_t kind, double *lane_ops_per_s) {
+    if (!lane_ops_per_s || kind < 0 || kind > 6) return fail(LDPC_E_INVALID, "alu_peak_probe: kind 0..6, non-null result");
+    int ndev = 0;
+    if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev <= 0) { cudaGetLastError(); return fail(LDPC_E_CUDA, "no CUDA device"); }
+    if (device < 0 || device >= ndev) return fail(LDPC_E_INVALID, "device %d out of range", device);
+    const int rc = nms_alu_probe(device, kind, lane_ops_per_s);
+    if (rc != 0) return fail(LDPC_E_CUDA, "alu_peak_probe: %s", cudaGetErrorString((cudaError_t)rc));
+    nms_note_launch(); nms_note_launch();
+    return LDPC_OK;
+}
+
 extern "C" uint64_t ldpc_launch_count(void) { return nms_launch_count(); }

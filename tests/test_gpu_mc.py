@@ -152,3 +152,17 @@ def test_compute_results_dropin(tmp_path):
     res1, _ = compute_results(dec, rows.shape[0], rows, np.array([0.0]), 1, 1)
     assert res1[2, 0] == 1.0                                                # none of them is ever corrected
     assert 0.9 <= res1[1, 0] <= 1.0
+
+
+def test_alu_peak_probe_is_plausible():
+    """The on-box pipe micro-benchmark behind bench.py's roofline denominators: FP32 FMA issue close to 148 SMs x 128
+    lanes x clock, the integer / min-max pipe at about half of it, packed half2 instructions at the FP32 rate or half."""
+    import torch
+    from ldpc_error_floor_b200 import _lib
+    p = _lib.alu_peak_probe(0, kinds=("ffma", "fadd", "fmnmx", "lop3", "iadd", "hfma2", "hmnmx2"))
+    sms = torch.cuda.get_device_properties(0).multi_processor_count
+    nominal = sms * 128 * 1.965e9 / 1e12
+    assert 0.6 * nominal < p["ffma"] < 1.05 * nominal, p
+    for k in ("fmnmx", "lop3", "iadd", "hmnmx2"):
+        assert 0.25 * nominal < p[k] < 1.05 * nominal, (k, p)
+    print(p)

@@ -1,13 +1,8 @@
 mkdir -p gpurun_out
-python -m pytest tests -m gpu -x -q 2>&1 | tail -5
-python bench.py > gpurun_out/bench_v7.json 2> gpurun_out/bench_v7.err
-python bench.py --impl reference --steps 3 --warmup 1 > gpurun_out/bench_v7_ref.json 2> /dev/null
 python - <<'PY'
-import json
-j = json.load(open("gpurun_out/bench_v7.json"))
-print("frames/s %.4e" % j["frames_per_s"], "value", j["value"], "e2e %.3e" % j["e2e"]["frames_per_s"], "q8 %.3e" % j["e2e_q8"]["frames_per_s"], "mc", "%.3e %.3e" % (j["mc"]["frames_per_s"], j["mc"]["frames_per_s_early_stop"]), "float %.3e" % j["float_min_sum"]["frames_per_s"], j["roofline"]["frac"], j["clocks"])
+import sys; sys.path.insert(0, ".")
+from ldpc_error_floor_b200 import _lib
+for _ in range(2):
+    print({k: round(v, 2) for k, v in _lib.alu_peak_probe(0, kinds=("ffma", "fadd", "fmnmx", "lop3", "iadd", "hfma2", "hmnmx2")).items()})
 PY
-python bench.py --steps 2 --warmup 3 --frames 262144 --e2e-frames 32768 --skip-cpu > /dev/null 2>&1 && ncu --metrics gpu__time_duration.sum --clock-control none -c 80 --csv --log-file gpurun_out/launches_v7.csv python bench.py --steps 2 --warmup 3 --frames 262144 --e2e-frames 32768 --skip-cpu > gpurun_out/ncu_l7.log 2>&1
-ncu --set full --clock-control none --import-source on -k regex:nms_h2 -s 6 -c 1 -o gpurun_out/prof_h2 -f python bench.py --steps 2 --warmup 3 --frames 262144 --e2e-frames 32768 --skip-cpu > gpurun_out/ncu_h2.log 2>&1
-ncu --set full --clock-control none --import-source on -k regex:nms_f32 -c 1 -o gpurun_out/prof_f32 -f python tools/prof_one.py wimax 1 5 262144 > gpurun_out/ncu_f32.log 2>&1
-python tools/mc_sweep.py wimax 2>&1 | tee gpurun_out/mc_sweep_wimax.txt
+python -m pytest tests/test_gpu_mc.py -x -q 2>&1 | tail -3
