@@ -1,8 +1,9 @@
 mkdir -p gpurun_out
+python -m pytest tests -m gpu -x -q 2>&1 | tail -4
+python bench.py > gpurun_out/bench_v7.json 2> gpurun_out/bench_v7.err
+python bench.py --impl reference --steps 3 --warmup 1 > gpurun_out/bench_v7_ref.json 2> /dev/null
 python - <<'PY'
-import sys; sys.path.insert(0, ".")
-from ldpc_error_floor_b200 import _lib
-for _ in range(2):
-    print({k: round(v, 2) for k, v in _lib.alu_peak_probe(0, kinds=("ffma", "fadd", "fmnmx", "lop3", "iadd", "hfma2", "hmnmx2")).items()})
+import json
+j = json.load(open("gpurun_out/bench_v7.json"))
+print("frames/s %.4e" % j["frames_per_s"], "value", j["value"], "e2e %.3e" % j["e2e"]["frames_per_s"], "q8 %.3e" % j["e2e_q8"]["frames_per_s"], "mc", "%.3e %.3e" % (j["mc"]["frames_per_s"], j["mc"]["frames_per_s_early_stop"]), "float %.3e" % j["float_min_sum"]["frames_per_s"], j["roofline"]["frac"], j["roofline"]["peak_measured"], j["clocks"], j["gpu_launches"])
 PY
-python -m pytest tests/test_gpu_mc.py -x -q 2>&1 | tail -3
