@@ -368,6 +368,7 @@ def main():
     # ---- measured pipe rates on this box, same run: FP32/FMA pipe and the integer / min-max pipe
     probe = _lib.alu_peak_probe(local_rank)
 
+    li = dec.launch_info(early_term=False)      # the timed launches run without early termination
     pk, pk_src = peaks()
     sm_max = float(clocks.get("sm_max_mhz") or pk.get("sm_max_mhz", 1965.0))
     alu_peak = SM_COUNT * LANES_PER_SM * sm_max * 1e6 / 1e12          # T lane-ops/s at max clock
@@ -380,13 +381,13 @@ def main():
     tpath = os.path.join(ROOT, "profiles", "traffic.json")
     if os.path.exists(tpath):
         tj = json.load(open(tpath))
-        ent = next((v for k, v in tj.items() if dec.kernel_name.startswith(k)), None)   # same bytes for any geometry
+        ent = next((v for k, v in tj.items() if li["kernel"].startswith(k)), None)   # same bytes for any geometry
         if ent:
             traffic = ent["dram_bytes_per_frame"] * B
             traffic_src = ent["source"]
             ncu_info = ent.get("ncu")
     roofline = {
-        "bound": "alu", "kernel": dec.kernel_name,
+        "bound": "alu", "kernel": li["kernel"],
         "achieved": ach, "peak": alu_peak, "unit": "Tlaneop/s", "frac": ach / alu_peak,
         "peak_source": f"148 SMs x 128 lanes x clocks.max.sm {sm_max:.0f} MHz (issue-slot roof; MEASURED_PEAKS.json "
                        f"carries no ALU figure)",
@@ -435,8 +436,9 @@ def main():
                           "roofline_frac": Bf / (f_ms / 1e3) * E * z * T * OPS_PER_EDGE_UPDATE_FLOAT / 1e12 / alu_peak,
                           "note": "decoding_type 1 (float32 messages, clip +-20), same words / weights / 20 iterations, "
                                   "no early stop; HBM-resident inputs, kernel-only timing"},
-        "geometry": {"packed_fp16x2": dec.packed, "frames_per_cta": dec.frames_per_cta, "ctas_per_sm": dec.ctas_per_sm,
-                     "threads_per_cta": dec.threads_per_cta, "smem_bytes": dec.smem_bytes},
+        "geometry": {"packed_fp16x2": dec.packed, "frames_per_cta": li["frames_per_cta"], "ctas_per_sm": li["ctas_per_sm"],
+                     "threads_per_cta": li["threads_per_cta"], "smem_bytes": li["smem_bytes"],
+                     "early_termination_launches": dec.launch_info(early_term=True)},
     }
     if world == 1 and not args.skip_cpu:
         wcpu = words[:512].reshape(-1, g.N, g.z).cpu().numpy()

@@ -126,6 +126,10 @@ const char *ldpc_decoder_kernel_name(const ldpc_decoder_t *d);
 /* frames decoded per CTA and CTAs per SM the launcher will use (for sizing batches) */
 int ldpc_decoder_geometry(const ldpc_decoder_t *d, int32_t *frames_per_cta, int32_t *ctas_per_sm,
                           int32_t *threads_per_cta, int32_t *smem_bytes);
+/* Kernel and launch geometry of a call with (early_term != 0) or without early termination: a graph may carry a second
+ * geometry for fixed-iteration launches (more frames per CTA).  kernel_name: caller's buffer of name_cap bytes (nullable). */
+int ldpc_decoder_launch_info(const ldpc_decoder_t *d, int32_t early_term, int32_t *frames_per_cta, int32_t *ctas_per_sm,
+                             int32_t *threads_per_cta, int32_t *smem_bytes, char *kernel_name, int32_t name_cap);
 
 /* ---- decode --------------------------------------------------------------------------
  * Replaces sess.run(ya_output_all / ya_output{t}) (Print_Functions.py:148-151, main_Base.py:160).

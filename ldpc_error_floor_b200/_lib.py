@@ -56,6 +56,8 @@ SYMBOLS = {
     "ldpc_decoder_kernel_name": (ctypes.c_char_p, [_P]),
     "ldpc_decoder_geometry": (ctypes.c_int, [_P, ctypes.POINTER(_I32), ctypes.POINTER(_I32),
                                              ctypes.POINTER(_I32), ctypes.POINTER(_I32)]),
+    "ldpc_decoder_launch_info": (ctypes.c_int, [_P, _I32, ctypes.POINTER(_I32), ctypes.POINTER(_I32), ctypes.POINTER(_I32),
+                                                ctypes.POINTER(_I32), ctypes.c_char_p, _I32]),
     "ldpc_decode": (ctypes.c_int, [_P, _P, _I64, _I32, _I32, _P, _I32, _P, _P, _P, _P, _P]),
     "ldpc_decode_host": (ctypes.c_int, [_P, _P, _I64, _I32, _I32, _P, _I32, _P, _P, _P, _P]),
     "ldpc_decoder_q8_step": (ctypes.c_float, [_P]),

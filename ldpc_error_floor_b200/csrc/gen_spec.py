@@ -25,7 +25,7 @@ GEOMETRIES = {
     # (Fp, R) per graph, measured on B200 with tools/geom_sweep.py (profiles/r01_geometry_sweep.md): few fat warps
     # (R = 2: each warp owns half of the rows / columns, 80-110 registers) beat many thin ones.  More than one
     # entry = variants compiled side by side, first = default, LDPC_B200_FP / LDPC_B200_R select at run time.
-    "wimax": [(4, 2)],
+    "wimax": [(4, 2), (8, 2)],
     "wifi": [(7, 2)],
     "5g_r073_z72": [(3, 2)],
     "5g_r050_z64": [(2, 2)],
@@ -35,6 +35,10 @@ GEOMETRIES = {
     "mackay": [(32, 8)],
     "bch": [(32, 4)],
 }
+# packed kernels: the variant used for launches WITHOUT early termination when it differs from the default.  With every
+# frame running all iterations fewer, fatter CTAs win (WiMAX 8,2: 16 frames per CTA, +5 %); with early termination the
+# slowest frame of a CTA holds the others back, so the default stays at 8 frames per CTA (profiles/r01_geometry_sweep.md).
+GEOMETRIES_NOET = {"wimax": (8, 2)}
 # float32 kernels (one frame per lane): same lanes as the packed choice
 GEOMETRIES_F32 = {
     "wimax": [(4, 2), (8, 2)], "wifi": [(7, 2)], "5g_r073_z72": [(4, 2), (3, 2)], "5g_r050_z64": [(2, 2)], "5g_r050_z32": [(4, 2)],
@@ -166,7 +170,7 @@ extern "C" const void *nms_spec_f32q_func_{name}() {{ return (const void *)nms::
         old = open(path).read() if os.path.exists(path) else None
         if old != src:
             open(path, "w").write(src)
-        return dict(name=name, hash=fnv1a(M, N, z, proto), M=M, N=N, z=z, E=E, Fp=Fp, R=R, path=path)
+        return dict(name=name, hash=fnv1a(M, N, z, proto), M=M, N=N, z=z, E=E, Fp=Fp, R=R, path=path, noet=0)
     # resident CTAs the kernel is compiled for: shared memory, threads, and >= 56 registers per thread
     minb = max(1, min(MAX_SMEM // (smem + 1024), 2048 // threads, 65536 // (threads * 56)))
     h = fnv1a(M, N, z, proto)
@@ -197,7 +201,7 @@ extern "C" const void *nms_spec_func_{name}() {{ return (const void *)nms::nms_h
     old = open(path).read() if os.path.exists(path) else None
     if old != src:
         open(path, "w").write(src)
-    return dict(name=name, hash=h, M=M, N=N, z=z, E=E, Fp=Fp, R=R, path=path)
+    return dict(name=name, hash=h, M=M, N=N, z=z, E=E, Fp=Fp, R=R, path=path, noet=int(GEOMETRIES_NOET.get(key) == (Fp, R)))
 
 
 def main():
@@ -233,15 +237,15 @@ def main():
         reg += [f'extern "C" const void *nms_spec_{tag}_func_{e["name"]}();' for e in entries32]
         reg += ["", f"static const NmsSpecEntry g_spec_{tag}[] = {{"]
         reg += [f'    {{"{e["name"]}", 0x{e["hash"]:016x}ull, {e["M"]}, {e["N"]}, {e["z"]}, {e["E"]}, {e["Fp"]}, {e["R"]}, '
-                f'nms_spec_{tag}_func_{e["name"]}}},' for e in entries32]
-        reg += ["    {nullptr, 0ull, 0, 0, 0, 0, 0, 0, nullptr}", "};", "",
+                f'nms_spec_{tag}_func_{e["name"]}, 0}},' for e in entries32]
+        reg += ["    {nullptr, 0ull, 0, 0, 0, 0, 0, 0, nullptr, 0}", "};", "",
                 f'extern "C" const NmsSpecEntry *nms_spec_{tag}_table(int *count) {{',
                 f"    if (count) *count = {len(entries32)};", f"    return g_spec_{tag};", "}", ""]
     reg += [f'extern "C" const void *nms_spec_func_{e["name"]}();' for e in entries]
     reg += ["", "static const NmsSpecEntry g_spec[] = {"]
     reg += [f'    {{"{e["name"]}", 0x{e["hash"]:016x}ull, {e["M"]}, {e["N"]}, {e["z"]}, {e["E"]}, {e["Fp"]}, {e["R"]}, '
-            f'nms_spec_func_{e["name"]}}},' for e in entries]
-    reg += ["    {nullptr, 0ull, 0, 0, 0, 0, 0, 0, nullptr}", "};", "",
+            f'nms_spec_func_{e["name"]}, {e["noet"]}}},' for e in entries]
+    reg += ["    {nullptr, 0ull, 0, 0, 0, 0, 0, 0, nullptr, 0}", "};", "",
             'extern "C" const NmsSpecEntry *nms_spec_table(int *count) {',
             f"    if (count) *count = {len(entries)};", "    return g_spec;", "}", ""]
     rpath = os.path.join(outdir, "spec_registry.cu")

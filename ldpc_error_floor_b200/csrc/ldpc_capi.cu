@@ -110,6 +110,12 @@ struct ldpc_decoder {
     const char *spec_name = nullptr;
     LaunchGeom geom{};
     KParams base{};
+    // second geometry of the same graph-specialised kernel family for launches WITHOUT early termination (more frames per
+    // CTA: fewer, fatter CTAs win when every frame runs all iterations, but the slowest frame of a CTA holds the others
+    // back when they may stop early); nullptr = none
+    const void *func_alt = nullptr;
+    LaunchGeom geom_alt{};
+    KParams base_alt{};
     float *d_w = nullptr;
     // training step (nms_train.cu): the weights as given ([T*wc | T*wu | T*wv], no "effective" rows), graph tables,
     // per-call workspace -- all created on first use
@@ -326,12 +332,26 @@ int choose_geometry(const ldpc_graph &g, bool packed, bool qms, int w_words, con
     return LDPC_OK;
 }
 
-int launch(const ldpc_decoder *d, const KParams &P, cudaStream_t st) {
+int launch(const ldpc_decoder *d, const KParams &Pin, cudaStream_t st) {
+    const bool alt = d->func_alt != nullptr && !Pin.early_term;
+    KParams Q;
+    if (alt) {   // same call, the other geometry's tables and shared-memory layout
+        Q = d->base_alt;
+        Q.T_run = Pin.T_run; Q.early_term = Pin.early_term;
+        Q.llr = Pin.llr; Q.llr_q8 = Pin.llr_q8; Q.q8_step = Pin.q8_step; Q.n_frames = Pin.n_frames;
+        Q.sigma = Pin.sigma; Q.two_over_s2 = Pin.two_over_s2; Q.seed = Pin.seed; Q.frame_offset = Pin.frame_offset;
+        Q.app = Pin.app; Q.app_all = Pin.app_all; Q.app_stride_t = Pin.app_stride_t;
+        Q.hard = Pin.hard; Q.iters = Pin.iters; Q.flags = Pin.flags; Q.biterr = Pin.biterr; Q.counters = Pin.counters;
+        Q.uncor_buf = Pin.uncor_buf; Q.uncor_count = Pin.uncor_count; Q.uncor_cap = Pin.uncor_cap; Q.harvest_mode = Pin.harvest_mode;
+        Q.w_all = Pin.w_all;
+    }
+    const KParams &P = alt ? Q : Pin;
+    const LaunchGeom &geo = alt ? d->geom_alt : d->geom;
     const long long nb = (P.n_frames + P.FB - 1) / P.FB;
     if (nb <= 0) return LDPC_OK;
-    const int grid = (int)std::min<long long>(nb, (long long)d->sm_count * d->geom.ctas_per_sm);
+    const int grid = (int)std::min<long long>(nb, (long long)d->sm_count * geo.ctas_per_sm);
     void *args[] = {(void *)&P};
-    CUDA_TRY(cudaLaunchKernel(d->func, dim3(grid), dim3(d->geom.threads), args, (size_t)d->geom.smem_bytes, st));
+    CUDA_TRY(cudaLaunchKernel(alt ? d->func_alt : d->func, dim3(grid), dim3(geo.threads), args, (size_t)geo.smem_bytes, st));
     nms_note_launch();
     return LDPC_OK;
 }
@@ -436,8 +456,13 @@ extern "C" int ldpc_decoder_create2(const ldpc_graph_t *g, const int32_t sharing
             const void *f = tab[k].func();
             LaunchGeom geo{};
             if (choose_geometry(d->g, true, qms, w_words, f, tab[k].Fp, tab[k].R, 32, &geo, false, no_xq) == LDPC_OK) {
-                d->func = f; d->geom = geo; d->spec_name = tab[k].name; rc = LDPC_OK;
-                break;
+                if (d->func == nullptr) {
+                    if (tab[k].noet && !want_fp) continue;   // the fixed-iteration variant never is the default
+                    d->func = f; d->geom = geo; d->spec_name = tab[k].name; rc = LDPC_OK;
+                    if (want_fp || want_r) break;            // tuning override: exactly this geometry, no second one
+                } else if (tab[k].noet && d->func_alt == nullptr && !env_on("LDPC_B200_NO_ALT")) {
+                    d->func_alt = f; d->geom_alt = geo;
+                }
             }
         }
     }
@@ -465,10 +490,11 @@ extern "C" int ldpc_decoder_create2(const ldpc_graph_t *g, const int32_t sharing
     }
     if (rc != LDPC_OK) { delete d; return rc; }
 
-    KParams &P = d->base;
+    const char *perr = nullptr;
+    auto fill = [&](KParams &P, const LaunchGeom &geom) {
     std::memset(&P, 0, sizeof P);
     P.M = g->M; P.N = g->N; P.E = g->E; P.z = g->z; P.NZ = g->N * g->z;
-    P.Fp = d->geom.Fp; P.FB = d->geom.FB; P.L = d->geom.L; P.LP = d->geom.LP; P.C = d->geom.C; P.R = d->geom.R;
+    P.Fp = geom.Fp; P.FB = geom.FB; P.L = geom.L; P.LP = geom.LP; P.C = geom.C; P.R = geom.R;
     P.qms = qms; P.sp = decoding_type == 0; P.qmagic = 12582912.0f / qk; P.qmax = qmax; P.clip = clip_llr;
     P.sat_magic = qms ? P.qmagic : 0.0f; P.sat_bound = qms ? qmax : clip_llr;
     P.sharing0 = sharing[0]; P.sharing1 = sharing[1]; P.sharing2 = sharing[2];
@@ -487,7 +513,7 @@ extern "C" int ldpc_decoder_create2(const ldpc_graph_t *g, const int32_t sharing
         else { P.h2w_u = P.h2w_c; P.h2_wu = P.h2_wc; P.h2_mu = P.h2_mc; }
         P.h2w_v = P.off_w + P.w_off_vn; P.h2_wv = wv; P.h2_mv = wv > 1 ? -1 : 0;
     }
-    if (P.smem_words * 4 != d->geom.smem_bytes) { delete d; return fail(LDPC_E_INVALID, "internal: smem layout mismatch"); }
+    if (P.smem_words * 4 != geom.smem_bytes) { perr = "internal: smem layout mismatch"; return; }
     for (int i = 0; i <= g->M; ++i) P.row_ptr[i] = (unsigned short)g->row_ptr[i];
     for (int j = 0; j <= g->N; ++j) P.col_ptr[j] = (unsigned short)g->col_ptr[j];
     {
@@ -496,7 +522,7 @@ extern "C" int ldpc_decoder_create2(const ldpc_graph_t *g, const int32_t sharing
         for (int j = 0; j < g->N; ++j) dv[j] = g->col_ptr[j + 1] - g->col_ptr[j];
         P.n_cn_cls = degree_classes(dc, P.cn_order, P.cn_cls, 32);
         P.n_vn_cls = degree_classes(dv, P.vn_order, P.vn_cls, 32);
-        if (P.n_cn_cls < 0 || P.n_vn_cls < 0) { delete d; return fail(LDPC_E_LIMIT, "more than 32 distinct node degrees"); }
+        if (P.n_cn_cls < 0 || P.n_vn_cls < 0) { perr = "more than 32 distinct node degrees"; return; }
     }
     {
         const int NT = (g->M + P.R - 1) / P.R;   // rows per task slot (slot s owns positions s, s+R, ... of cn_order)
@@ -522,6 +548,11 @@ extern "C" int ldpc_decoder_create2(const ldpc_graph_t *g, const int32_t sharing
         P.vn_edge[k].x = e * P.LP * 4;
         P.vn_edge[k].y = ((P.L - g->shift[e] * P.Fp) % P.L) * 4;
     }
+    };
+    fill(d->base, d->geom);
+    if (!perr && d->func_alt) fill(d->base_alt, d->geom_alt);
+    if (perr) { const std::string msg = perr; delete d; return fail(LDPC_E_LIMIT, "%s", msg.c_str()); }
+    KParams &P = d->base;
     if (!wh.empty()) {
         if (cudaMalloc(&d->d_w, wh.size() * sizeof(float)) != cudaSuccess ||
             cudaMemcpy(d->d_w, wh.data(), wh.size() * sizeof(float), cudaMemcpyHostToDevice) != cudaSuccess) {
@@ -530,6 +561,7 @@ extern "C" int ldpc_decoder_create2(const ldpc_graph_t *g, const int32_t sharing
             return fail(LDPC_E_CUDA, "uploading weights: %s", msg);
         }
         P.w_all = d->d_w;
+        d->base_alt.w_all = d->d_w;
     }
     *out = d;
     return LDPC_OK;
@@ -577,6 +609,24 @@ extern "C" int ldpc_decoder_geometry(const ldpc_decoder_t *d, int32_t *frames_pe
     if (ctas_per_sm) *ctas_per_sm = d->geom.ctas_per_sm;
     if (threads_per_cta) *threads_per_cta = d->geom.threads;
     if (smem_bytes) *smem_bytes = d->geom.smem_bytes;
+    return LDPC_OK;
+}
+
+// the kernel and launch geometry a call with / without early termination uses (they differ when the graph has a second,
+// fixed-iteration geometry: ldpc_decoder::func_alt)
+extern "C" int ldpc_decoder_launch_info(const ldpc_decoder_t *d, int32_t early_term, int32_t *frames_per_cta, int32_t *ctas_per_sm,
+                                        int32_t *threads_per_cta, int32_t *smem_bytes, char *kernel_name, int32_t name_cap) {
+    if (!d) return fail(LDPC_E_INVALID, "decoder_launch_info: null decoder");
+    const bool alt = d->func_alt != nullptr && !early_term;
+    const LaunchGeom &geo = alt ? d->geom_alt : d->geom;
+    if (frames_per_cta) *frames_per_cta = geo.FB;
+    if (ctas_per_sm) *ctas_per_sm = geo.ctas_per_sm;
+    if (threads_per_cta) *threads_per_cta = geo.threads;
+    if (smem_bytes) *smem_bytes = geo.smem_bytes;
+    if (kernel_name && name_cap > 0) {
+        if (alt) snprintf(kernel_name, (size_t)name_cap, "nms_h2_spec_%s_fp%d_r%d", d->spec_name ? std::string(d->spec_name).substr(0, std::string(d->spec_name).rfind("_fp")).c_str() : "", geo.Fp, geo.R);
+        else snprintf(kernel_name, (size_t)name_cap, "%s", ldpc_decoder_kernel_name(d));
+    }
     return LDPC_OK;
 }
 

@@ -91,6 +91,7 @@ struct NmsSpecEntry {
     unsigned long long graph_hash;   // FNV-1a over (M, N, z, proto[])
     int M, N, z, E, Fp, R;
     const void *(*func)();
+    int noet;   // 1: the variant for launches without early termination (never the default geometry)
 };
 extern "C" const NmsSpecEntry *nms_spec_table(int *count);
 extern "C" const NmsSpecEntry *nms_spec_f32_table(int *count);    // float path (decoding_type 1)

@@ -128,6 +128,15 @@ class NMSDecoder:
         self.threads_per_cta, self.smem_bytes = thr.value, smem.value
         self.hard_words = (graph.NZ + 31) // 32
 
+    def launch_info(self, early_term: bool = False) -> Dict:
+        """Kernel and launch geometry a call with / without early termination uses (ldpc_decoder_launch_info)."""
+        fb, cps, thr, smem = (ctypes.c_int32() for _ in range(4))
+        name = ctypes.create_string_buffer(96)
+        _lib.check(_lib.load().ldpc_decoder_launch_info(self._h, 1 if early_term else 0, ctypes.byref(fb), ctypes.byref(cps),
+                                                        ctypes.byref(thr), ctypes.byref(smem), name, 96))
+        return {"kernel": name.value.decode(), "frames_per_cta": fb.value, "ctas_per_sm": cps.value,
+                "threads_per_cta": thr.value, "smem_bytes": smem.value}
+
     def __del__(self):
         h = getattr(self, "_h", None)
         if h:

@@ -388,3 +388,28 @@ def test_generic_kernels_give_the_same_results(name, env, monkeypatch):
         assert (np.abs(app - ref) / np.maximum(1.0, np.abs(ref))).max() <= REL_TOL and np.array_equal(app >= 0, ref >= 0)
     e1, e2 = spec.decode(xa, early_term=True), gen.decode(xa, early_term=True)
     assert torch.equal(e1.hard_packed, e2.hard_packed) and torch.equal(e1.iters, e2.iters) and torch.equal(e1.flags, e2.flags)
+
+
+def test_fixed_iteration_geometry_gives_the_same_results(monkeypatch):
+    """WiMAX carries a second launch geometry (16 frames per CTA) that serves the calls WITHOUT early termination; calls
+    with early termination keep the default (8 frames per CTA).  Same bits from both, and from a decoder without it."""
+    import torch
+    case = load_case("wimax_qms_333_t20")
+    g, dec = build_decoder(case)
+    a, b = dec.launch_info(early_term=False), dec.launch_info(early_term=True)
+    assert a["kernel"] == "nms_h2_spec_wimax_fp8_r2" and a["frames_per_cta"] == 16
+    assert b["kernel"] == "nms_h2_spec_wimax_fp4_r2" and b["frames_per_cta"] == 8
+    x = dec.generate(float(g.sigma([3.0])[0]), 5000, seed=9).reshape(5000, -1)
+    r1 = dec.decode(x)                                   # fixed iterations: the 16-frame geometry
+    cnt1, _ = dec.post_decode(x)
+    monkeypatch.setenv("LDPC_B200_NO_ALT", "1")
+    _, plain = build_decoder(case)
+    assert plain.launch_info(early_term=False)["kernel"] == "nms_h2_spec_wimax_fp4_r2"
+    r2 = plain.decode(x)
+    cnt2, _ = plain.post_decode(x)
+    for f in ("hard_packed", "iters", "flags", "biterr"):
+        assert torch.equal(getattr(r1, f), getattr(r2, f)), f
+    assert torch.equal(cnt1, cnt2)
+    c1, _, _ = dec.mc_run(float(g.sigma([3.0])[0]), 40000, 4, early_term=False)
+    c2, _, _ = plain.mc_run(float(g.sigma([3.0])[0]), 40000, 4, early_term=False)
+    assert torch.equal(c1, c2)

@@ -1,9 +1,9 @@
 mkdir -p gpurun_out
-python -m pytest tests -m gpu -x -q 2>&1 | tail -4
-python bench.py > gpurun_out/bench_v7.json 2> gpurun_out/bench_v7.err
-python bench.py --impl reference --steps 3 --warmup 1 > gpurun_out/bench_v7_ref.json 2> /dev/null
+python -m pytest tests -m gpu -x -q 2>&1 | tail -12
+python bench.py --steps 10 --skip-cpu > gpurun_out/bench_alt.json 2> gpurun_out/bench_alt.err
 python - <<'PY'
 import json
-j = json.load(open("gpurun_out/bench_v7.json"))
-print("frames/s %.4e" % j["frames_per_s"], "value", j["value"], "e2e %.3e" % j["e2e"]["frames_per_s"], "q8 %.3e" % j["e2e_q8"]["frames_per_s"], "mc", "%.3e %.3e" % (j["mc"]["frames_per_s"], j["mc"]["frames_per_s_early_stop"]), "float %.3e" % j["float_min_sum"]["frames_per_s"], j["roofline"]["frac"], j["roofline"]["peak_measured"], j["clocks"], j["gpu_launches"])
+j = json.load(open("gpurun_out/bench_alt.json"))
+print("frames/s %.4e" % j["frames_per_s"], "value", j["value"], "e2e %.3e" % j["e2e"]["frames_per_s"], "q8 %.3e" % j["e2e_q8"]["frames_per_s"], "mc", "%.3e %.3e" % (j["mc"]["frames_per_s"], j["mc"]["frames_per_s_early_stop"]), "float %.3e" % j["float_min_sum"]["frames_per_s"], j["roofline"]["frac"], j["roofline"]["kernel"], j["geometry"])
 PY
+tail -5 gpurun_out/bench_alt.err
