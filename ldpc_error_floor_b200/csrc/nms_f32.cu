@@ -55,7 +55,7 @@ struct F32Policy {
     template <bool INIT>
     static __device__ __forceinline__ void vn_phase(const KParams &P, const Ctx &c, int t, bool need_hb, uint32_t &ones) {
         const F32Ctx h = f32_ctx(P, c);
-        f32_vn_phase_tab<DVB, INIT, 2>(P, c, h, t, need_hb, ones);
+        f32_vn_phase_tab<DVB, INIT, 2>(P, c, h, t, ones);   // float kernels publish their ballots every iteration
     }
 
     static __device__ __forceinline__ uint32_t synd_phase(const KParams &P, const Ctx &c, int tl) { return f32_synd_phase(P, c, (tl + 1) & 1); }

@@ -399,8 +399,7 @@ static __device__ __noinline__ void vn_col_f32_generic(const KParams &P, const C
 // table-driven VN phase over this warp's columns (generic kernels; APP-output / shared-memory-init path of the
 // specialised ones).  DVB = 0: any degree.
 template <int DVB, bool INIT, int QM, int PADMODE = 2>   // PADMODE 0 / 1: L == LP known at compile time, 2: run time
-__device__ __forceinline__ void f32_vn_phase_tab(const KParams &P, const Ctx &c, const F32Ctx &h, int t, bool need_hb,
-                                                 uint32_t &ones) {
+__device__ __forceinline__ void f32_vn_phase_tab(const KParams &P, const Ctx &c, const F32Ctx &h, int t, uint32_t &ones) {
     const bool cold = !INIT && P.app != nullptr;
     const bool pad = PADMODE == 2 ? P.L != P.LP : PADMODE == 1;
     for (int n = c.slot; n < P.N; n += P.R) {

@@ -31,7 +31,7 @@ struct F32SpecPolicy {
     static constexpr bool FUSED_LOAD = true;
     static constexpr uint32_t LP4 = G::LP * 4u;
     static constexpr bool PAD = G::L != G::LP;
-    enum { F_ITER = 0, F_INIT_SMEM = 1, F_INIT_GLOBAL = 2 };
+    enum { F_ITER = 0, F_INIT_GLOBAL = 2 };   // VN column code: iteration t / pass before iteration 0 fed from global memory
     static constexpr int ETW = PAD ? 2 : 1;   // words per (edge, chunk) entry of the syndrome table
 
     // Syndrome table, built once per CTA: entry (e, chunk) tells the lane that serves edge e which two ballot words hold
@@ -224,7 +224,7 @@ struct F32SpecPolicy {
     static __device__ __forceinline__ void vn_phase(const KParams &P, const Ctx &c, int t, bool need_hb, uint32_t &ones) {
         const F32Ctx h = f32_ctx(P, c);
         if (INIT || !unrolled_ok(P)) {   // channel values already in shared memory (generator), or APP output wanted
-            f32_vn_phase_tab<G::DVMAX, INIT, QM, PAD ? 1 : 0>(P, c, h, t, need_hb, ones);
+            f32_vn_phase_tab<G::DVMAX, INIT, QM, PAD ? 1 : 0>(P, c, h, t, ones);
             return;
         }
         const int trow = min(t + 1, P.T_run - 1);
