@@ -1,3 +1,2 @@
 mkdir -p gpurun_out
-python -m pytest tests -m gpu -x -q 2>&1 | tail -4
-python -c "import __graft_entry__ as g; g.smoke()" 2>&1 | tail -2
+timeout 500 python tools/boost_demo.py /tmp/boost_wimax 4 3.5 2>&1 | grep -v "^W\|Warning" | tee gpurun_out/boost_demo.txt
