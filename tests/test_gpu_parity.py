@@ -413,3 +413,33 @@ def test_fixed_iteration_geometry_gives_the_same_results(monkeypatch):
     c1, _, _ = dec.mc_run(float(g.sigma([3.0])[0]), 40000, 4, early_term=False)
     c2, _, _ = plain.mc_run(float(g.sigma([3.0])[0]), 40000, 4, early_term=False)
     assert torch.equal(c1, c2)
+
+
+@pytest.mark.parametrize("name", ["wimax_qms_333_t20", "wimax_float_333_t20", "5g_r050_z64_qms_222_t50"])
+def test_partial_iterations_and_ragged_batches(name):
+    """iters = t + 1 gives ya_output{t} (main_Base.py:160); an empty batch is a no-op; batches of 1 .. 2 x frames-per-CTA + 1
+    frames (ragged last CTA, both launch geometries) reproduce the rows of the full batch."""
+    import torch
+    case = load_case(name)
+    g, dec = build_decoder(case)
+    xa = torch.from_numpy(case["xa"]).cuda()
+    ref = case["app"]
+    for k in (1, 2, case["T"] // 2, case["T"] - 1):
+        r = dec.decode(xa, iters=k, app="last")
+        a = r.app.cpu().numpy()
+        if case["decoding_type"] == 2:
+            assert np.array_equal(a, ref[k - 1]), k
+        else:
+            assert (np.abs(a - ref[k - 1]) / np.maximum(1, np.abs(ref[k - 1]))).max() <= REL_TOL
+    empty = dec.decode(xa[:0])
+    assert empty.hard_packed.shape[0] == 0 and empty.flags.shape[0] == 0
+    big = torch.cat([xa] * 6)[:37]
+    full = dec.decode(big)
+    full_et = dec.decode(big, early_term=True)
+    for n in (1, 2, 3, 7, 8, 9, 15, 16, 17, 33, 37):
+        for et, want in ((False, full), (True, full_et)):
+            r = dec.decode(big[:n].contiguous(), early_term=et)
+            assert torch.equal(r.hard_packed, want.hard_packed[:n]) and torch.equal(r.iters, want.iters[:n])
+            assert torch.equal(r.flags, want.flags[:n]) and torch.equal(r.biterr, want.biterr[:n])
+    h = dec.decode_host(big[:5].cpu().numpy())
+    assert np.array_equal(h["flags"], full.flags[:5].cpu().numpy())
