@@ -196,6 +196,16 @@ int ldpc_mc_run(const ldpc_decoder_t *d, double sigma, int64_t n_frames, uint64_
 
 /* Host-buffer twin of ldpc_mc_run: counters_host u64[LDPC_NUM_COUNTERS] (overwritten),
  * uncor_host f32 [uncor_capacity, N*z], *n_uncor_host = rows written.  Synchronous. */
+/* Two-stage form of ldpc_mc_run with early termination: stage 1 decodes every frame for stage1_iters (< iters) iterations;
+ * frames that have not reached a zero syndrome by then are not counted but listed by global frame index in defer_list_dev
+ * (caller-owned, uint64[n_frames]; defer_count_dev: uint32[1]) and decoded in full by stage 2, which regenerates them from
+ * the same Philox counters.  Counters and harvested words are those of ldpc_mc_run(early_term = 1), bit for bit; the
+ * stragglers no longer keep the CTAs of converged frames busy (a code whose degree-1 parity bits often stay wrong -- 5G NR --
+ * otherwise pays all iterations for most CTAs).  Synchronises `stream` once between the stages.  Not in the reference. */
+int ldpc_mc_run_staged(const ldpc_decoder_t *d, double sigma, int64_t n_frames, uint64_t seed, uint64_t frame_offset,
+                       int32_t iters, int32_t stage1_iters, int32_t harvest_mode, uint64_t *counters_dev,
+                       float *uncor_buf_dev, uint32_t *uncor_count_dev, uint32_t uncor_capacity,
+                       uint64_t *defer_list_dev, uint32_t *defer_count_dev, void *stream);
 int ldpc_mc_run_host(const ldpc_decoder_t *d, double sigma, int64_t n_frames, uint64_t seed,
                      uint64_t frame_offset, int32_t iters, int32_t early_term,
                      int32_t harvest_mode, uint64_t *counters_host, float *uncor_host,

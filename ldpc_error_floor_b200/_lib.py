@@ -65,6 +65,7 @@ SYMBOLS = {
     "ldpc_decode_q8_host": (ctypes.c_int, [_P, _P, ctypes.c_float, _I64, _I32, _I32, _P, _P, _P, _P]),
     "ldpc_llr_generate": (ctypes.c_int, [_P, ctypes.c_double, _I64, _U64, _U64, _P, _P]),
     "ldpc_mc_run": (ctypes.c_int, [_P, ctypes.c_double, _I64, _U64, _U64, _I32, _I32, _I32, _P, _P, _P, _U32, _P]),
+    "ldpc_mc_run_staged": (ctypes.c_int, [_P, ctypes.c_double, _I64, _U64, _U64, _I32, _I32, _I32, _P, _P, _P, _U32, _P, _P, _P]),
     "ldpc_mc_run_host": (ctypes.c_int, [_P, ctypes.c_double, _I64, _U64, _U64, _I32, _I32, _I32, _P, _P, _U32,
                                         ctypes.POINTER(_U32)]),
     "ldpc_post_decode": (ctypes.c_int, [_P, _P, _I64, _I32, _I32, _P, _P, _P, _P, _P]),

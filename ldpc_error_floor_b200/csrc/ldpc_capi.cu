@@ -344,6 +344,7 @@ int launch(const ldpc_decoder *d, const KParams &Pin, cudaStream_t st) {
         Q.hard = Pin.hard; Q.iters = Pin.iters; Q.flags = Pin.flags; Q.biterr = Pin.biterr; Q.counters = Pin.counters;
         Q.uncor_buf = Pin.uncor_buf; Q.uncor_count = Pin.uncor_count; Q.uncor_cap = Pin.uncor_cap; Q.harvest_mode = Pin.harvest_mode;
         Q.w_all = Pin.w_all;
+        Q.frame_list = Pin.frame_list; Q.defer_list = Pin.defer_list; Q.defer_count = Pin.defer_count;
     }
     const KParams &P = alt ? Q : Pin;
     const LaunchGeom &geo = alt ? d->geom_alt : d->geom;
@@ -831,6 +832,44 @@ extern "C" int ldpc_mc_run(const ldpc_decoder_t *d, double sigma, int64_t n_fram
     P.harvest_mode = harvest_mode;
     P.uncor_buf = uncor_buf_dev; P.uncor_count = uncor_count_dev; P.uncor_cap = uncor_capacity;
     return launch(d, P, (cudaStream_t)stream);
+}
+
+extern "C" int ldpc_mc_run_staged(const ldpc_decoder_t *d, double sigma, int64_t n_frames, uint64_t seed, uint64_t frame_offset,
+                                  int32_t iters, int32_t stage1_iters, int32_t harvest_mode, uint64_t *counters_dev,
+                                  float *uncor_buf_dev, uint32_t *uncor_count_dev, uint32_t uncor_capacity,
+                                  uint64_t *defer_list_dev, uint32_t *defer_count_dev, void *stream) {
+    if (!d || n_frames < 0 || !(sigma > 0.0) || !counters_dev || !defer_list_dev || !defer_count_dev)
+        return fail(LDPC_E_INVALID, "mc_run_staged: bad arguments");
+    const int T = iters == 0 ? d->T : iters;
+    if (iters < 0 || iters > d->T) return fail(LDPC_E_INVALID, "mc_run_staged: iters %d outside 0..%d", iters, d->T);
+    if (stage1_iters < 1 || stage1_iters >= T) return fail(LDPC_E_INVALID, "mc_run_staged: stage1_iters %d outside 1..%d", stage1_iters, T - 1);
+    if (harvest_mode < 0 || harvest_mode > 3) return fail(LDPC_E_INVALID, "mc_run_staged: harvest_mode %d", harvest_mode);
+    if (n_frames == 0) return LDPC_OK;
+    if (n_frames > 0xffffffffLL) return fail(LDPC_E_LIMIT, "mc_run_staged: more than 2^32 - 1 frames per call");
+    DeviceGuard guard(d->device);
+    if (!guard.ok) return fail(LDPC_E_CUDA, "cudaSetDevice(%d) failed", d->device);
+    cudaStream_t st = (cudaStream_t)stream;
+    CUDA_TRY(cudaMemsetAsync(defer_count_dev, 0, sizeof(uint32_t), st));
+    KParams P = d->base;
+    fill_channel(P, sigma, seed, frame_offset);
+    P.early_term = 1;
+    P.llr = nullptr;
+    P.counters = (unsigned long long *)counters_dev;
+    P.harvest_mode = harvest_mode;
+    P.uncor_buf = uncor_buf_dev; P.uncor_count = uncor_count_dev; P.uncor_cap = uncor_capacity;
+    // stage 1: every frame, stage1_iters iterations; frames without a zero syndrome by then go to the list
+    P.T_run = stage1_iters; P.n_frames = n_frames;
+    P.defer_list = (unsigned long long *)defer_list_dev; P.defer_count = defer_count_dev;
+    int rc = launch(d, P, st);
+    if (rc != LDPC_OK) return rc;
+    uint32_t n2 = 0;
+    CUDA_TRY(cudaMemcpyAsync(&n2, defer_count_dev, sizeof n2, cudaMemcpyDeviceToHost, st));
+    CUDA_TRY(cudaStreamSynchronize(st));
+    if (n2 == 0) return LDPC_OK;
+    // stage 2: the listed frames regenerated from their global indices, all `iters` iterations (early termination on)
+    P.T_run = T; P.n_frames = (long long)n2;
+    P.frame_list = (const unsigned long long *)defer_list_dev; P.defer_list = nullptr; P.defer_count = nullptr;
+    return launch(d, P, st);
 }
 
 extern "C" int ldpc_mc_run_host(const ldpc_decoder_t *dc, double sigma, int64_t n_frames, uint64_t seed,

@@ -59,6 +59,13 @@ struct KParams {
     long long n_frames;
     float sigma, two_over_s2;
     unsigned long long seed, frame_offset;
+    // two-stage Monte-Carlo (ldpc_mc_run_staged): stage 1 decodes T_run < T iterations with early termination and, instead
+    // of counting a frame that has not reached a zero syndrome, appends its global frame index to defer_list; stage 2
+    // regenerates exactly those frames (frame_list[k] instead of frame_offset + k: the Philox counter is the global index)
+    // and decodes them in full, so the stragglers no longer hold CTAs of converged frames back.  Same counters, bit for bit.
+    const unsigned long long *frame_list;
+    unsigned long long *defer_list;
+    unsigned int *defer_count;
     int punct_s, punct_e, short_s, short_e;
     // outputs (nullable)
     float *app; int app_all; long long app_stride_t;   // elements between iterations (B*NZ)

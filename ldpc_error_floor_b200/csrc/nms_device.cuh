@@ -118,6 +118,11 @@ __device__ __forceinline__ void gen_llr4(const KParams &P, unsigned long long F,
     }
 }
 
+// global (Philox) index of batch frame k: consecutive from frame_offset, or listed (stage 2 of a two-stage Monte-Carlo run)
+__device__ __forceinline__ unsigned long long frame_index(const KParams &P, long long k) {
+    return P.frame_list != nullptr ? __ldg(P.frame_list + k) : P.frame_offset + (unsigned long long)k;
+}
+
 template <bool H2>
 __device__ __forceinline__ void store_xa(const KParams &P, int f, int k, float v) {
     const int j = k / P.z, a = k - j * P.z;
@@ -251,7 +256,7 @@ __device__ __forceinline__ void nms_decode_body(const KParams &P) {
             int f = tid / nquads, quad = tid - f * nquads;   // (frame, quad) advance incrementally: no division per item
             while (f < P.FB) {
                 float v[4] = {0.0f, 0.0f, 0.0f, 0.0f};
-                if (f < c.nvalid) gen_llr4(P, P.frame_offset + (unsigned long long)(c.frame0 + f), quad, v);
+                if (f < c.nvalid) gen_llr4(P, frame_index(P, c.frame0 + f), quad, v);
                 int k = 4 * quad, j = k / P.z, a = k - j * P.z;
 #pragma unroll
                 for (int k4 = 0; k4 < 4; ++k4, ++k) {
@@ -381,7 +386,11 @@ __device__ __forceinline__ void nms_decode_body(const KParams &P) {
 
         // ---------------- per-frame results, Monte-Carlo counters, harvest
         if (tid < 64) {
-            const bool valid = tid < c.nvalid;
+            bool valid = tid < c.nvalid;
+            if (valid && P.defer_list != nullptr && !(st & ST_OUT_SYND_OK)) {   // stage 1: not converged -> stage 2, not counted here
+                P.defer_list[atomicAdd(P.defer_count, 1u)] = frame_index(P, c.frame0 + tid);
+                valid = false;
+            }
             const uint32_t be = misc[MISC_BITERR + tid];
             const bool uncor_any = !(st & ST_EVER_CORRECT), uncor_last = (st & ST_OUT_ONE) != 0u;
             const bool st_out_synd_ok = (st & ST_OUT_SYND_OK) != 0u;

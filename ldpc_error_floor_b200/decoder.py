@@ -315,10 +315,12 @@ class NMSDecoder:
     def mc_run(self, sigma: float, n_frames: int, seed: int, frame_offset: int = 0, iters: int = 0,
                early_term: bool = False, harvest: int = _lib.HARVEST_NONE, capacity: int = 0,
                counters: Optional[torch.Tensor] = None, uncor_buf: Optional[torch.Tensor] = None,
-               uncor_count: Optional[torch.Tensor] = None):
+               uncor_count: Optional[torch.Tensor] = None, stage1_iters: int = 0):
         """Fused generate + decode + count (+ harvest) for one SNR point, asynchronous on the current
         stream.  Returns (counters int64[8] CUDA, uncor_buf f32 [capacity, N*z] CUDA or None,
-        uncor_count int32[1] CUDA); pass the tensors back in to keep accumulating."""
+        uncor_count int32[1] CUDA); pass the tensors back in to keep accumulating.
+        stage1_iters > 0 (with early_term): the two-stage form (ldpc_mc_run_staged) -- same counters, the frames that
+        have not converged after stage1_iters iterations are decoded in a dense second launch."""
         dev = self.device
         if counters is None:
             counters = torch.zeros((_lib.NUM_COUNTERS,), dtype=torch.int64, device=dev)
@@ -328,6 +330,16 @@ class NMSDecoder:
             uncor_buf = torch.empty((capacity, self.graph.NZ), dtype=torch.float32, device=dev)
         cap = 0 if uncor_buf is None else uncor_buf.shape[0]
         stream = torch.cuda.current_stream(dev).cuda_stream
+        T = self.T if iters == 0 else int(iters)
+        if early_term and 0 < stage1_iters < T:
+            if getattr(self, "_defer_list", None) is None or self._defer_list.numel() < n_frames:
+                self._defer_list = torch.empty((int(n_frames),), dtype=torch.int64, device=dev)
+                self._defer_count = torch.zeros((1,), dtype=torch.int32, device=dev)
+            _lib.check(_lib.load().ldpc_mc_run_staged(self._h, float(sigma), int(n_frames), int(seed) & (2**64 - 1),
+                                                      int(frame_offset), int(iters), int(stage1_iters), int(harvest),
+                                                      _ptr(counters), _ptr(uncor_buf), _ptr(uncor_count), cap,
+                                                      _ptr(self._defer_list), _ptr(self._defer_count), ctypes.c_void_p(stream)))
+            return counters, uncor_buf, uncor_count
         _lib.check(_lib.load().ldpc_mc_run(self._h, float(sigma), int(n_frames), int(seed) & (2**64 - 1),
                                            int(frame_offset), int(iters), 1 if early_term else 0, int(harvest),
                                            _ptr(counters), _ptr(uncor_buf), _ptr(uncor_count), cap,

@@ -131,10 +131,13 @@ class MonteCarlo:
 
     def run_point(self, snr_db: float, n_frames: int, *, sigma: Optional[float] = None, iters: int = 0,
                   early_term: bool = False, harvest: int = _lib.HARVEST_NONE, max_uncor: int = 0,
-                  min_frame_errors: Optional[int] = None, frame_base: int = 0, round_chunks: int = 4):
+                  min_frame_errors: Optional[int] = None, frame_base: int = 0, round_chunks: int = 4,
+                  stage1_iters: Optional[int] = None):
         """Decode frames [frame_base, frame_base + n_frames) of this point's global index space.
         Stops early once `min_frame_errors` frame errors (any-iteration criterion) are seen, checked once
-        per round of `round_chunks` chunks per rank.  Returns (SnrPoint, harvested LLR rows [n, N*z])."""
+        per round of `round_chunks` chunks per rank.  Returns (SnrPoint, harvested LLR rows [n, N*z]).
+        stage1_iters: with early termination, split each launch in two (NMSDecoder.mc_run): None = decide after the
+        first chunk from its statistics (see _pick_stage1), 0 = never.  The counters do not depend on it."""
         g = self.dec.graph
         if sigma is None:
             sigma = float(g.sigma([snr_db])[0])
@@ -142,6 +145,7 @@ class MonteCarlo:
         t0 = time.time()
         n_chunks = (n_frames + self.chunk - 1) // self.chunk
         counters = ubuf = ucnt = None
+        stage1 = stage1_iters if early_term else 0
         done_chunks = 0
         while done_chunks < n_chunks:
             hi = min(n_chunks, done_chunks + round_chunks * self.world)
@@ -150,9 +154,12 @@ class MonteCarlo:
                     continue
                 off = c * self.chunk
                 n = min(self.chunk, n_frames - off)
+                if stage1 is None and early_term and counters is not None:
+                    stage1 = _pick_stage1(self._to_numpy(counters), self.dec.T if iters == 0 else iters)
                 counters, ubuf, ucnt = self.dec.mc_run(
                     sigma, n, self.seed, frame_offset=frame_base + off, iters=iters, early_term=early_term,
-                    harvest=harvest, capacity=max_uncor, counters=counters, uncor_buf=ubuf, uncor_count=ucnt)
+                    harvest=harvest, capacity=max_uncor, counters=counters, uncor_buf=ubuf, uncor_count=ucnt,
+                    stage1_iters=stage1 or 0)
             done_chunks = hi
             if min_frame_errors is not None and done_chunks < n_chunks:
                 local = self._to_numpy(counters)
@@ -192,6 +199,26 @@ class MonteCarlo:
         if torch is not None and isinstance(buf, torch.Tensor):
             return buf[:n].detach().cpu().numpy()
         return np.asarray(buf[:n], dtype=np.float32)
+
+
+def _pick_stage1(counters: np.ndarray, T: int) -> int:
+    """Stage-1 iteration count of the two-stage Monte-Carlo launch from the statistics of the chunks decoded so far
+    (0 = one launch).  It pays when a visible share f of the frames never reaches a zero syndrome -- each of them keeps the
+    CTA it sits in busy for all T iterations -- while the others converge early, after a iterations on average: stage 1
+    then runs about 1.3 a iterations and the stragglers are decoded again, densely packed.  Measured on B200
+    (profiles/r01_two_stage_mc.txt): 5G n2112 z72 at 4.5-5.5 dB (f = 8-12 %, a = 4-5) +28..40 %, WiMAX at 3 dB (f = 6 %) +10 %;
+    with f below 3 % (5G n1024 z64, WiMAX above 3.5 dB) or a above T / 2.6 there is nothing to gain, so it stays off."""
+    names = _lib.COUNTER_NAMES
+    frames = float(counters[names.index("frames")])
+    if frames <= 0:
+        return 0
+    fail = float(counters[names.index("synd_fail")])
+    f = fail / frames
+    a = (float(counters[names.index("iters")]) - fail * T) / max(frames - fail, 1.0)
+    s1 = int(min(max(3.0, math.ceil(1.3 * a)), T - 1))
+    if f < 0.03 or f > 0.5 or s1 > T // 2:
+        return 0
+    return s1
 
 
 def compute_results(decoder, sample_num, input_llr, SNR_sigma, batch_size, sampling_type, seed=2044,

@@ -166,3 +166,36 @@ def test_alu_peak_probe_is_plausible():
     for k in ("fmnmx", "lop3", "iadd", "hmnmx2"):
         assert 0.25 * nominal < p[k] < 1.05 * nominal, (k, p)
     print(p)
+
+
+@pytest.mark.parametrize("key,snr,systematic", [("wimax", 3.0, 0), ("wimax", 4.0, 0), ("5g_r050_z64", 2.5, 1), ("5g_r073_z72", 4.5, 1)])
+def test_two_stage_monte_carlo_equals_single_stage(key, snr, systematic, codes):
+    """ldpc_mc_run_staged: stage 1 defers the frames without a zero syndrome by frame index, stage 2 regenerates and
+    decodes them in full -- the eight counters and the set of harvested words are those of the one-launch run."""
+    import torch
+    import ldpc_error_floor_b200 as L
+    from ldpc_error_floor_b200 import _lib, montecarlo
+    proto = codes[f"graph/{key}/proto"].astype(np.int32); meta = codes[f"graph/{key}/meta"]
+    g = L.BaseGraph(proto, int(meta[0]), (int(meta[1]), int(meta[2])), (int(meta[3]), int(meta[4])))
+    wk = {"wimax": "wimax_base20", "5g_r050_z64": "5g_r050_z64_boost50"}.get(key)
+    if wk:
+        ws = L.WeightSet([int(v) for v in codes[f"weights/{wk}/sharing"]], {i: codes[f"weights/{wk}/block{i}"] for i in range(3)})
+    else:
+        ws = L.WeightSet([3, 0, 0], {0: np.full((20, 1), 0.8, np.float32)})
+    dec = L.NMSDecoder(g, ws, iters=20, systematic=systematic)
+    sigma, n = float(g.sigma([snr])[0]), 60000
+    c1, b1, u1 = dec.mc_run(sigma, n, 11, frame_offset=12345, early_term=True, harvest=_lib.HARVEST_UNCOR_ANY, capacity=4000)
+    for s1 in (3, 8, 19):
+        c2, b2, u2 = dec.mc_run(sigma, n, 11, frame_offset=12345, early_term=True, harvest=_lib.HARVEST_UNCOR_ANY, capacity=4000,
+                                stage1_iters=s1)
+        assert torch.equal(c1, c2), (s1, c1.tolist(), c2.tolist())
+        k = int(u1.item())
+        assert int(u2.item()) == k
+        if 0 < k <= 4000:
+            a = b1[:k].cpu().numpy(); b = b2[:k].cpu().numpy()
+            assert np.array_equal(a[np.lexsort(a.T[::-1])], b[np.lexsort(b.T[::-1])])
+    names = _lib.COUNTER_NAMES
+    c = c1.cpu().numpy()
+    assert c[names.index("frames")] == n
+    s1 = montecarlo._pick_stage1(c, 20)
+    assert s1 == 0 or 3 <= s1 <= 10
