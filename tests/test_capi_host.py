@@ -142,3 +142,21 @@ def test_snr_point_statistics():
     assert pt.ber_last == pytest.approx(1456 / 576000)
     lo, hi = pt.fer_ci95()
     assert lo < 0.054 < hi and hi - lo < 0.03
+
+
+def test_two_stage_heuristic():
+    """MonteCarlo's choice of the stage-1 length (montecarlo._pick_stage1) on the statistics measured on B200
+    (profiles/r01_two_stage_mc.txt): on for the 5G n2112 floor region and WiMAX at 3 dB, off where stragglers are rare or
+    convergence is slow."""
+    from ldpc_error_floor_b200 import montecarlo
+
+    def cnt(f, avg, frames=1e6):
+        c = np.zeros(8)
+        c[0], c[5], c[4] = frames, f * frames, avg * frames
+        return c
+    assert [montecarlo._pick_stage1(cnt(f, a), 20) for f, a in ((.128, 8.13), (.116, 7.11), (.101, 6.26), (.083, 5.53))] == [9, 8, 7, 6]
+    assert montecarlo._pick_stage1(cnt(.057, 7.18), 20) == 9          # WiMAX 3 dB
+    assert montecarlo._pick_stage1(cnt(.017, 8.78), 20) == 0          # 5G n1024: stragglers too rare
+    assert montecarlo._pick_stage1(cnt(.0002, 3.18), 20) == 0         # WiMAX 4 dB
+    assert montecarlo._pick_stage1(cnt(.7, 18.0), 20) == 0            # waterfall: most frames fail
+    assert montecarlo._pick_stage1(np.zeros(8), 20) == 0
