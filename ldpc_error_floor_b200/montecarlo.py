@@ -145,7 +145,7 @@ class MonteCarlo:
         t0 = time.time()
         n_chunks = (n_frames + self.chunk - 1) // self.chunk
         counters = ubuf = ucnt = None
-        stage1 = stage1_iters if early_term else 0
+        stage1 = stage1_iters if early_term and _takes_stage1(self.dec) else 0
         done_chunks = 0
         while done_chunks < n_chunks:
             hi = min(n_chunks, done_chunks + round_chunks * self.world)
@@ -156,10 +156,10 @@ class MonteCarlo:
                 n = min(self.chunk, n_frames - off)
                 if stage1 is None and early_term and counters is not None:
                     stage1 = _pick_stage1(self._to_numpy(counters), self.dec.T if iters == 0 else iters)
+                extra = {"stage1_iters": stage1} if stage1 else {}     # only decoders that know the two-stage form see it
                 counters, ubuf, ucnt = self.dec.mc_run(
                     sigma, n, self.seed, frame_offset=frame_base + off, iters=iters, early_term=early_term,
-                    harvest=harvest, capacity=max_uncor, counters=counters, uncor_buf=ubuf, uncor_count=ucnt,
-                    stage1_iters=stage1 or 0)
+                    harvest=harvest, capacity=max_uncor, counters=counters, uncor_buf=ubuf, uncor_count=ucnt, **extra)
             done_chunks = hi
             if min_frame_errors is not None and done_chunks < n_chunks:
                 local = self._to_numpy(counters)
@@ -199,6 +199,15 @@ class MonteCarlo:
         if torch is not None and isinstance(buf, torch.Tensor):
             return buf[:n].detach().cpu().numpy()
         return np.asarray(buf[:n], dtype=np.float32)
+
+
+def _takes_stage1(dec) -> bool:
+    """Does this decoder's mc_run know the two-stage form?  (Test doubles of NMSDecoder need not.)"""
+    import inspect
+    try:
+        return "stage1_iters" in inspect.signature(dec.mc_run).parameters
+    except (TypeError, ValueError):
+        return False
 
 
 def _pick_stage1(counters: np.ndarray, T: int) -> int:
