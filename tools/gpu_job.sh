@@ -1,4 +1,5 @@
 mkdir -p gpurun_out
-python tools/prof_one.py 5g_r073_z72 2 5 65536 2>&1 | tail -1
-ncu --set full --clock-control none --import-source on -k regex:nms_h2_spec_5g -c 1 -o gpurun_out/prof_z72 -f python tools/prof_one.py 5g_r073_z72 2 5 65536 > gpurun_out/ncu_z72.log 2>&1
-tail -1 gpurun_out/ncu_z72.log
+python -m pytest tests -m gpu -x -q 2>&1 | tail -4
+python tools/mc_sweep.py wimax 2>&1 | tee gpurun_out/mc_sweep_wimax.txt
+python tools/prof_mc.py 5g_r073_z72 5.5 2>&1 | tail -1
+python tools/prof_mc.py mackay 5.0 4194304 2>&1 | tail -1
