@@ -1,5 +1,9 @@
 mkdir -p gpurun_out
 python -m pytest tests -m gpu -x -q 2>&1 | tail -4
-python tools/mc_sweep.py wimax 2>&1 | tee gpurun_out/mc_sweep_wimax.txt
-python tools/prof_mc.py 5g_r073_z72 5.5 2>&1 | tail -1
-python tools/prof_mc.py mackay 5.0 4194304 2>&1 | tail -1
+python -c "import __graft_entry__ as g; g.smoke()" 2>&1 | tail -1
+python bench.py --skip-cpu > gpurun_out/bench_final.json 2> gpurun_out/bench_final.err
+python - <<'PY'
+import json
+j = json.load(open("gpurun_out/bench_final.json"))
+print("frames/s %.4e" % j["frames_per_s"], "value", j["value"], "e2e %.3e" % j["e2e"]["frames_per_s"], "q8 %.3e" % j["e2e_q8"]["frames_per_s"], "mc", "%.3e %.3e" % (j["mc"]["frames_per_s"], j["mc"]["frames_per_s_early_stop"]), "float %.3e" % j["float_min_sum"]["frames_per_s"], j["roofline"]["frac"], j["gpu_launches"])
+PY
