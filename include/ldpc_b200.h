@@ -183,6 +183,13 @@ int ldpc_decode_q8_host(const ldpc_decoder_t *d, const int8_t *llr_q8_host, floa
 int ldpc_llr_generate(const ldpc_decoder_t *d, double sigma, int64_t n_frames, uint64_t seed,
                       uint64_t frame_offset, float *llr_dev, void *stream);
 
+/* The generator's N(0,1) stream on its own (same Philox counters: frame f, quad q -> normals 4q..4q+3 of frame
+ * frame_offset + f): normals_dev f32 [n_frames * quads_per_frame * 4] (NULL = no copy-out) and/or tail_counts_dev
+ * u64[6], ACCUMULATED: samples with |n| > 3, 4, 5, 6, 7 sigma and the total.  Test hook for the distribution the
+ * error-floor estimates rest on (the reference draws float64 normals, Print_Functions.py:45). */
+int ldpc_normal_probe(int32_t device, uint64_t seed, uint64_t frame_offset, int64_t n_frames, int32_t quads_per_frame,
+                      float *normals_dev, uint64_t *tail_counts_dev, void *stream);
+
 /* ---- fused Monte-Carlo ---------------------------------------------------------------------
  * Replaces Print_Functions.compute_results (:130-165) for one SNR point: generate, decode,
  * count, harvest, all on the device.  counters_dev: u64[LDPC_NUM_COUNTERS], ACCUMULATED
@@ -194,18 +201,27 @@ int ldpc_mc_run(const ldpc_decoder_t *d, double sigma, int64_t n_frames, uint64_
                 uint64_t *counters_dev, float *uncor_buf_dev, uint32_t *uncor_count_dev,
                 uint32_t uncor_capacity, void *stream);
 
+/* Kernel and launch geometry ldpc_mc_run(early_term = 1) uses.  *persistent = 1: the graph has a persistent-slot
+ * Monte-Carlo kernel (csrc/nms_mcp.cuh): a CTA owns frames_per_cta frame slots, every slot runs its own frame at its
+ * own iteration and is refilled the moment that frame stops -- the device-side replacement of the batch loop
+ * `for batch_idx ...` of Print_Functions.compute_results (:136-161).  Same counters and harvested words as the batch
+ * kernels, bit for bit (the Philox counter is the global frame index either way). */
+int ldpc_decoder_mc_info(const ldpc_decoder_t *d, int32_t *persistent, int32_t *frames_per_cta, int32_t *ctas_per_sm,
+                         int32_t *threads_per_cta, int32_t *smem_bytes, char *kernel_name, int32_t name_cap);
+
 /* Host-buffer twin of ldpc_mc_run: counters_host u64[LDPC_NUM_COUNTERS] (overwritten),
  * uncor_host f32 [uncor_capacity, N*z], *n_uncor_host = rows written.  Synchronous. */
 /* Two-stage form of ldpc_mc_run with early termination: stage 1 decodes every frame for stage1_iters (< iters) iterations;
  * frames that have not reached a zero syndrome by then are not counted but listed by global frame index in defer_list_dev
- * (caller-owned, uint64[n_frames]; defer_count_dev: uint32[1]) and decoded in full by stage 2, which regenerates them from
+ * (caller-owned, uint64[defer_capacity]; defer_count_dev: uint32[1]; n_frames entries always suffice, and when more frames are
+ * deferred than the list holds the call fails with LDPC_E_LIMIT instead of writing past it) and decoded in full by stage 2, which regenerates them from
  * the same Philox counters.  Counters and harvested words are those of ldpc_mc_run(early_term = 1), bit for bit; the
  * stragglers no longer keep the CTAs of converged frames busy (a code whose degree-1 parity bits often stay wrong -- 5G NR --
  * otherwise pays all iterations for most CTAs).  Synchronises `stream` once between the stages.  Not in the reference. */
 int ldpc_mc_run_staged(const ldpc_decoder_t *d, double sigma, int64_t n_frames, uint64_t seed, uint64_t frame_offset,
                        int32_t iters, int32_t stage1_iters, int32_t harvest_mode, uint64_t *counters_dev,
                        float *uncor_buf_dev, uint32_t *uncor_count_dev, uint32_t uncor_capacity,
-                       uint64_t *defer_list_dev, uint32_t *defer_count_dev, void *stream);
+                       uint64_t *defer_list_dev, uint32_t *defer_count_dev, uint32_t defer_capacity, void *stream);
 int ldpc_mc_run_host(const ldpc_decoder_t *d, double sigma, int64_t n_frames, uint64_t seed,
                      uint64_t frame_offset, int32_t iters, int32_t early_term,
                      int32_t harvest_mode, uint64_t *counters_host, float *uncor_host,

@@ -58,14 +58,17 @@ SYMBOLS = {
                                              ctypes.POINTER(_I32), ctypes.POINTER(_I32)]),
     "ldpc_decoder_launch_info": (ctypes.c_int, [_P, _I32, ctypes.POINTER(_I32), ctypes.POINTER(_I32), ctypes.POINTER(_I32),
                                                 ctypes.POINTER(_I32), ctypes.c_char_p, _I32]),
+    "ldpc_decoder_mc_info": (ctypes.c_int, [_P, ctypes.POINTER(_I32), ctypes.POINTER(_I32), ctypes.POINTER(_I32),
+                                            ctypes.POINTER(_I32), ctypes.POINTER(_I32), ctypes.c_char_p, _I32]),
     "ldpc_decode": (ctypes.c_int, [_P, _P, _I64, _I32, _I32, _P, _I32, _P, _P, _P, _P, _P]),
     "ldpc_decode_host": (ctypes.c_int, [_P, _P, _I64, _I32, _I32, _P, _I32, _P, _P, _P, _P]),
     "ldpc_decoder_q8_step": (ctypes.c_float, [_P]),
     "ldpc_decode_q8": (ctypes.c_int, [_P, _P, ctypes.c_float, _I64, _I32, _I32, _P, _P, _P, _P, _P, _P]),
     "ldpc_decode_q8_host": (ctypes.c_int, [_P, _P, ctypes.c_float, _I64, _I32, _I32, _P, _P, _P, _P]),
     "ldpc_llr_generate": (ctypes.c_int, [_P, ctypes.c_double, _I64, _U64, _U64, _P, _P]),
+    "ldpc_normal_probe": (ctypes.c_int, [_I32, _U64, _U64, _I64, _I32, _P, _P, _P]),
     "ldpc_mc_run": (ctypes.c_int, [_P, ctypes.c_double, _I64, _U64, _U64, _I32, _I32, _I32, _P, _P, _P, _U32, _P]),
-    "ldpc_mc_run_staged": (ctypes.c_int, [_P, ctypes.c_double, _I64, _U64, _U64, _I32, _I32, _I32, _P, _P, _P, _U32, _P, _P, _P]),
+    "ldpc_mc_run_staged": (ctypes.c_int, [_P, ctypes.c_double, _I64, _U64, _U64, _I32, _I32, _I32, _P, _P, _P, _U32, _P, _P, _U32, _P]),
     "ldpc_mc_run_host": (ctypes.c_int, [_P, ctypes.c_double, _I64, _U64, _U64, _I32, _I32, _I32, _P, _P, _U32,
                                         ctypes.POINTER(_U32)]),
     "ldpc_post_decode": (ctypes.c_int, [_P, _P, _I64, _I32, _I32, _P, _P, _P, _P, _P]),

@@ -44,6 +44,13 @@ GEOMETRIES_F32 = {
     "wimax": [(4, 2), (8, 2)], "wifi": [(7, 2)], "5g_r073_z72": [(4, 2), (3, 2)], "5g_r050_z64": [(2, 2)], "5g_r050_z32": [(4, 2)],
     "5g_r033_z32": [(4, 2)], "5g_r073_z32": [(4, 2)], "mackay": [(32, 8)], "bch": [(32, 4)],
 }
+# persistent-slot Monte-Carlo kernels (nms_mcp.cuh: no float channel array, no ballots -> smaller CTAs, more of them per SM).
+# First entry = default; LDPC_B200_MCP_FP / LDPC_B200_MCP_R select another compiled one at run time.
+GEOMETRIES_MCP = {
+    "wimax": [(4, 2), (2, 2)], "wifi": [(7, 2), (3, 2)], "5g_r073_z72": [(2, 2), (3, 2), (3, 3)], "5g_r050_z64": [(2, 2), (1, 2)],
+    "5g_r050_z32": [(4, 2)], "5g_r033_z32": [(4, 2)], "5g_r073_z32": [(4, 2)],
+}
+MCP_MISC_WORDS = 112 + 32 * 8 * 2
 SKIP = {"polar"}   # row degree 64 > 32: generic two-pass kernel
 
 
@@ -103,7 +110,7 @@ def arr(name, vals, ty="short"):
     return f"    static constexpr {ty} {name}[{max(len(vals), 1)}] = {{{', '.join(str(int(v)) for v in vals) or '0'}}};"
 
 
-def emit(key, proto, z, Fp, R, outdir, f32=False):
+def emit(key, proto, z, Fp, R, outdir, f32=False, mcp=False):
     M, N = proto.shape
     row, col, shift, row_ptr = [], [], [], [0]
     for i in range(M):
@@ -135,6 +142,44 @@ def emit(key, proto, z, Fp, R, outdir, f32=False):
     threads = C * R * 32
     smem = (layout(E, N, LP, C, 256)[-1] - N * LP) * 4   # without the xq array (decoders with VN weights drop it)
     name = f"{key}_fp{Fp}_r{R}"
+    # CN phase: degree classes in descending order and how many rows of each class a slot owns (slot s: positions s, s+R, ...)
+    degs_desc = sorted(set(dc), reverse=True)
+    cls_cnt = [sum(1 for p in range(s_, M, R) if dc[cn_order[p]] == dg) for s_ in range(R) for dg in degs_desc]
+    cn_tables = arr('cn_degs_desc', degs_desc) + "\n" + arr('cn_cls_cnt', cls_cnt)
+    if mcp:
+        if 2 * Fp > 32:
+            return None
+        words = ((E * LP + 3) & ~3) + N * LP + 256 + MCP_MISC_WORDS
+        minb = max(1, min(MAX_SMEM // (words * 4 + 1024), 2048 // threads, 65536 // (threads * 56)))
+        src = f"""// GENERATED by gen_spec.py -- do not edit.  Graph "{key}": {M}x{N}, z={z}, E={E}; persistent-slot Monte-Carlo geometry Fp={Fp} R={R}.
+#include "../nms_mcp.cuh"
+
+namespace nms {{
+struct GM_{name} {{
+    static constexpr int M = {M}, N = {N}, E = {E}, z = {z}, Fp = {Fp}, L = {L}, LP = {LP}, C = {C}, R = {R};
+{arr('row_ptr', row_ptr)}
+{arr('col_ptr', col_ptr)}
+{arr('cn_order', cn_order)}
+{arr('vn_order', vn_order)}
+{arr('vn_e', vn_e)}
+{arr('vn_rot', vn_rot)}
+    static constexpr int NDEG = {len(sorted(set(dc)))};
+{arr('cn_degs', sorted(set(dc)))}
+{cn_tables}
+}};
+
+__global__ void __launch_bounds__({threads}, {minb}) nms_mcp_spec_{name}(const __grid_constant__ KParams P) {{
+    McpKernel<GM_{name}>::run(P);
+}}
+}}   // namespace nms
+
+extern "C" const void *nms_spec_mcp_func_{name}() {{ return (const void *)nms::nms_mcp_spec_{name}; }}
+"""
+        path = os.path.join(outdir, f"spec_mcp_{name}.cu")
+        old = open(path).read() if os.path.exists(path) else None
+        if old != src:
+            open(path, "w").write(src)
+        return dict(name=name, hash=fnv1a(M, N, z, proto), M=M, N=N, z=z, E=E, Fp=Fp, R=R, path=path, noet=0)
     if f32:
         # float path: msg + xa + ballots + weights + misc; the quantised twin adds the xq array
         words = E * LP + N * LP + 2 * N * C + E + 1 + E * C * (2 if L != LP else 1) + 256 + MISC_WORDS
@@ -188,6 +233,7 @@ struct G_{name} {{
 {arr('vn_rot', vn_rot)}
     static constexpr int NDEG = {len(sorted(set(dc)))};
 {arr('cn_degs', sorted(set(dc)))}
+{cn_tables}
 }};
 
 __global__ void __launch_bounds__({threads}, {minb}) nms_h2_spec_{name}(const __grid_constant__ KParams P) {{
@@ -232,15 +278,25 @@ def main():
             e = emit(key, proto, z, Fp, R, outdir, f32=True)
             if e:
                 entries32.append(e)
+    entries_mcp = []
+    for key in keys:
+        if key in SKIP or key not in GEOMETRIES_MCP:
+            continue
+        proto = d[f"graph/{key}/proto"].astype(np.int64)
+        z = int(d[f"graph/{key}/meta"][0])
+        for Fp, R in GEOMETRIES_MCP[key]:
+            e = emit(key, proto, z, Fp, R, outdir, mcp=True)
+            if e:
+                entries_mcp.append(e)
     reg = ["// GENERATED by gen_spec.py -- do not edit.", '#include "../nms_common.cuh"', ""]
-    for tag in ("f32", "f32q"):
-        reg += [f'extern "C" const void *nms_spec_{tag}_func_{e["name"]}();' for e in entries32]
+    for tag, ents in (("f32", entries32), ("f32q", entries32), ("mcp", entries_mcp)):
+        reg += [f'extern "C" const void *nms_spec_{tag}_func_{e["name"]}();' for e in ents]
         reg += ["", f"static const NmsSpecEntry g_spec_{tag}[] = {{"]
         reg += [f'    {{"{e["name"]}", 0x{e["hash"]:016x}ull, {e["M"]}, {e["N"]}, {e["z"]}, {e["E"]}, {e["Fp"]}, {e["R"]}, '
-                f'nms_spec_{tag}_func_{e["name"]}, 0}},' for e in entries32]
+                f'nms_spec_{tag}_func_{e["name"]}, 0}},' for e in ents]
         reg += ["    {nullptr, 0ull, 0, 0, 0, 0, 0, 0, nullptr, 0}", "};", "",
                 f'extern "C" const NmsSpecEntry *nms_spec_{tag}_table(int *count) {{',
-                f"    if (count) *count = {len(entries32)};", f"    return g_spec_{tag};", "}", ""]
+                f"    if (count) *count = {len(ents)};", f"    return g_spec_{tag};", "}", ""]
     reg += [f'extern "C" const void *nms_spec_func_{e["name"]}();' for e in entries]
     reg += ["", "static const NmsSpecEntry g_spec[] = {"]
     reg += [f'    {{"{e["name"]}", 0x{e["hash"]:016x}ull, {e["M"]}, {e["N"]}, {e["z"]}, {e["E"]}, {e["Fp"]}, {e["R"]}, '
@@ -252,7 +308,7 @@ def main():
     txt = "\n".join(reg)
     if not os.path.exists(rpath) or open(rpath).read() != txt:
         open(rpath, "w").write(txt)
-    for e in entries + entries32:
+    for e in entries + entries32 + entries_mcp:
         print(os.path.basename(e["path"]))
     print("spec_registry.cu")
 

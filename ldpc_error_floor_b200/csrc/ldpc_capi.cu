@@ -116,6 +116,11 @@ struct ldpc_decoder {
     const void *func_alt = nullptr;
     LaunchGeom geom_alt{};
     KParams base_alt{};
+    // persistent-slot Monte-Carlo kernel (nms_mcp.cuh) of the same graph: serves ldpc_mc_run with early termination
+    const void *func_mc = nullptr;
+    const char *mc_name = nullptr;
+    LaunchGeom geom_mc{};
+    KParams base_mc{};
     float *d_w = nullptr;
     // training step (nms_train.cu): the weights as given ([T*wc | T*wu | T*wv], no "effective" rows), graph tables,
     // per-call workspace -- all created on first use
@@ -273,6 +278,17 @@ void fill_smem_layout(KParams *P, bool packed, bool spec_f32 = false) {
     P->smem_words = off;
 }
 
+// persistent-slot Monte-Carlo kernel: msg | xq (half2) | weights | state -- no float channel array, no ballots
+void fill_smem_layout_mc(KParams *P) {
+    int off = P->E * P->LP;
+    off = (off + 3) & ~3;
+    P->off_xa = off; P->off_xq = off; off += P->N * P->LP;
+    P->off_hb = off; P->off_et = off; P->off_et2 = off;
+    P->off_w = off; off += (P->w_words + 3) & ~3;      // the state block holds 64-bit counters
+    P->off_misc = off; off += NMS_MCP_MISC_WORDS;
+    P->smem_words = off;
+}
+
 unsigned long long graph_hash(const ldpc_graph &g) {   // FNV-1a over (M, N, z, proto[]) -- same as gen_spec.py
     unsigned long long h = 0xcbf29ce484222325ull;
     auto mix = [&](int v) {
@@ -332,27 +348,37 @@ int choose_geometry(const ldpc_graph &g, bool packed, bool qms, int w_words, con
     return LDPC_OK;
 }
 
+// does this call go to the persistent-slot Monte-Carlo kernel?  (in-kernel samples, per-frame early termination,
+// no per-frame outputs; LDPC_B200_NO_PERSIST=1 keeps the batch kernels: the A/B switch of the tests)
+bool takes_mc_kernel(const ldpc_decoder *d, const KParams &P) {
+    return d->func_mc != nullptr && P.llr == nullptr && P.llr_q8 == nullptr && P.early_term && P.frame_list == nullptr &&
+           P.defer_list == nullptr && P.app == nullptr && P.hard == nullptr && P.iters == nullptr && P.flags == nullptr &&
+           P.biterr == nullptr && !env_on("LDPC_B200_NO_PERSIST");
+}
+
 int launch(const ldpc_decoder *d, const KParams &Pin, cudaStream_t st) {
-    const bool alt = d->func_alt != nullptr && !Pin.early_term;
+    const bool mc = takes_mc_kernel(d, Pin);
+    const bool alt = mc || (d->func_alt != nullptr && !Pin.early_term);
     KParams Q;
     if (alt) {   // same call, the other geometry's tables and shared-memory layout
-        Q = d->base_alt;
+        Q = mc ? d->base_mc : d->base_alt;
         Q.T_run = Pin.T_run; Q.early_term = Pin.early_term;
         Q.llr = Pin.llr; Q.llr_q8 = Pin.llr_q8; Q.q8_step = Pin.q8_step; Q.n_frames = Pin.n_frames;
-        Q.sigma = Pin.sigma; Q.two_over_s2 = Pin.two_over_s2; Q.seed = Pin.seed; Q.frame_offset = Pin.frame_offset;
+        Q.sigma = Pin.sigma; Q.two_over_s2 = Pin.two_over_s2; Q.two_over_s = Pin.two_over_s; Q.seed = Pin.seed; Q.frame_offset = Pin.frame_offset;
         Q.app = Pin.app; Q.app_all = Pin.app_all; Q.app_stride_t = Pin.app_stride_t;
         Q.hard = Pin.hard; Q.iters = Pin.iters; Q.flags = Pin.flags; Q.biterr = Pin.biterr; Q.counters = Pin.counters;
         Q.uncor_buf = Pin.uncor_buf; Q.uncor_count = Pin.uncor_count; Q.uncor_cap = Pin.uncor_cap; Q.harvest_mode = Pin.harvest_mode;
         Q.w_all = Pin.w_all;
-        Q.frame_list = Pin.frame_list; Q.defer_list = Pin.defer_list; Q.defer_count = Pin.defer_count;
+        Q.frame_list = Pin.frame_list; Q.defer_list = Pin.defer_list; Q.defer_count = Pin.defer_count; Q.defer_cap = Pin.defer_cap;
     }
     const KParams &P = alt ? Q : Pin;
-    const LaunchGeom &geo = alt ? d->geom_alt : d->geom;
+    const LaunchGeom &geo = mc ? d->geom_mc : (alt ? d->geom_alt : d->geom);
     const long long nb = (P.n_frames + P.FB - 1) / P.FB;
     if (nb <= 0) return LDPC_OK;
     const int grid = (int)std::min<long long>(nb, (long long)d->sm_count * geo.ctas_per_sm);
     void *args[] = {(void *)&P};
-    CUDA_TRY(cudaLaunchKernel(alt ? d->func_alt : d->func, dim3(grid), dim3(geo.threads), args, (size_t)geo.smem_bytes, st));
+    const void *func = mc ? d->func_mc : (alt ? d->func_alt : d->func);
+    CUDA_TRY(cudaLaunchKernel(func, dim3(grid), dim3(geo.threads), args, (size_t)geo.smem_bytes, st));
     nms_note_launch();
     return LDPC_OK;
 }
@@ -467,6 +493,34 @@ extern "C" int ldpc_decoder_create2(const ldpc_graph_t *g, const int32_t sharing
             }
         }
     }
+    // persistent-slot Monte-Carlo kernel of the same graph (slot masks are one word: at most 32 frames per CTA)
+    if (d->packed && d->spec_name != nullptr && g->N * g->z < 65536 && !env_on("LDPC_B200_NO_SPEC")) {
+        int n = 0;
+        const NmsSpecEntry *tab = nms_spec_mcp_table(&n);
+        const unsigned long long h = graph_hash(d->g);
+        const int want_fp = getenv("LDPC_B200_MCP_FP") ? atoi(getenv("LDPC_B200_MCP_FP")) : 0;
+        const int want_r = getenv("LDPC_B200_MCP_R") ? atoi(getenv("LDPC_B200_MCP_R")) : 0;
+        for (int k = 0; k < n && d->func_mc == nullptr; ++k) {
+            if (tab[k].graph_hash != h || tab[k].M != g->M || tab[k].N != g->N || tab[k].z != g->z) continue;
+            if ((want_fp && tab[k].Fp != want_fp) || (want_r && tab[k].R != want_r)) continue;
+            const void *f = tab[k].func();
+            LaunchGeom geo{};
+            geo.Fp = tab[k].Fp; geo.FB = 2 * geo.Fp; geo.L = g->z * geo.Fp; geo.LP = (geo.L + 31) & ~31; geo.C = geo.LP / 32;
+            geo.R = tab[k].R; geo.threads = geo.C * geo.R * 32;
+            KParams tmp{};
+            tmp.E = g->E; tmp.N = g->N; tmp.LP = geo.LP; tmp.w_words = w_words;
+            fill_smem_layout_mc(&tmp);
+            geo.smem_bytes = tmp.smem_words * 4;
+            if (geo.smem_bytes > 227 * 1024) continue;
+            if (cudaFuncSetAttribute(f, cudaFuncAttributeMaxDynamicSharedMemorySize, geo.smem_bytes) != cudaSuccess ||
+                cudaOccupancyMaxActiveBlocksPerMultiprocessor(&geo.ctas_per_sm, f, geo.threads, geo.smem_bytes) != cudaSuccess ||
+                geo.ctas_per_sm < 1) {
+                cudaGetLastError();
+                continue;
+            }
+            d->func_mc = f; d->geom_mc = geo; d->mc_name = tab[k].name;
+        }
+    }
     // graph-specialised float32 kernel (float / quantised twin); it reads its weights from shared memory
     if (!d->packed && w_words <= NMS_WSTAGE_MAX_WORDS && !env_on("LDPC_B200_NO_SPEC")) {
         int n = 0;
@@ -492,7 +546,7 @@ extern "C" int ldpc_decoder_create2(const ldpc_graph_t *g, const int32_t sharing
     if (rc != LDPC_OK) { delete d; return rc; }
 
     const char *perr = nullptr;
-    auto fill = [&](KParams &P, const LaunchGeom &geom) {
+    auto fill = [&](KParams &P, const LaunchGeom &geom, bool mc_layout = false) {
     std::memset(&P, 0, sizeof P);
     P.M = g->M; P.N = g->N; P.E = g->E; P.z = g->z; P.NZ = g->N * g->z;
     P.Fp = geom.Fp; P.FB = geom.FB; P.L = geom.L; P.LP = geom.LP; P.C = geom.C; P.R = geom.R;
@@ -507,7 +561,8 @@ extern "C" int ldpc_decoder_create2(const ldpc_graph_t *g, const int32_t sharing
     P.target_n = target_node > 0 ? target_node : g->N;
     P.punct_s = g->punct_s; P.punct_e = g->punct_e; P.short_s = g->short_s; P.short_e = g->short_e;
     P.HW = (P.NZ + 31) / 32;
-    fill_smem_layout(&P, d->packed, !d->packed && d->spec_name != nullptr);
+    if (mc_layout) fill_smem_layout_mc(&P);
+    else fill_smem_layout(&P, d->packed, !d->packed && d->spec_name != nullptr);
     if (d->packed) {
         P.h2w_c = P.off_w + P.w_off_cn; P.h2_wc = wc; P.h2_mc = wc > 1 ? -1 : 0;
         if (wu) { P.h2w_u = P.off_w + P.w_off_ucn; P.h2_wu = wu; P.h2_mu = wu > 1 ? -1 : 0; }
@@ -527,8 +582,9 @@ extern "C" int ldpc_decoder_create2(const ldpc_graph_t *g, const int32_t sharing
     }
     {
         const int NT = (g->M + P.R - 1) / P.R;   // rows per task slot (slot s owns positions s, s+R, ... of cn_order)
-        for (int s = 0; s < P.R && s * NT < LDPC_MAX_M; ++s)
-            for (int n = 0; n < NT && s * NT + n < LDPC_MAX_M; ++n) {
+        if (P.R > 32 || P.R * NT + 1 > (int)(sizeof P.cn_task / sizeof P.cn_task[0])) { perr = "row task table too small"; return; }
+        for (int s = 0; s < P.R; ++s)
+            for (int n = 0; n < NT; ++n) {
                 const int p = s + n * P.R;
                 uint2 tk = make_uint2(0u, 0u);
                 if (p < g->M) {
@@ -552,6 +608,7 @@ extern "C" int ldpc_decoder_create2(const ldpc_graph_t *g, const int32_t sharing
     };
     fill(d->base, d->geom);
     if (!perr && d->func_alt) fill(d->base_alt, d->geom_alt);
+    if (!perr && d->func_mc) fill(d->base_mc, d->geom_mc, true);
     if (perr) { const std::string msg = perr; delete d; return fail(LDPC_E_LIMIT, "%s", msg.c_str()); }
     KParams &P = d->base;
     if (!wh.empty()) {
@@ -563,6 +620,7 @@ extern "C" int ldpc_decoder_create2(const ldpc_graph_t *g, const int32_t sharing
         }
         P.w_all = d->d_w;
         d->base_alt.w_all = d->d_w;
+        d->base_mc.w_all = d->d_w;
     }
     *out = d;
     return LDPC_OK;
@@ -628,6 +686,24 @@ extern "C" int ldpc_decoder_launch_info(const ldpc_decoder_t *d, int32_t early_t
         if (alt) snprintf(kernel_name, (size_t)name_cap, "nms_h2_spec_%s_fp%d_r%d", d->spec_name ? std::string(d->spec_name).substr(0, std::string(d->spec_name).rfind("_fp")).c_str() : "", geo.Fp, geo.R);
         else snprintf(kernel_name, (size_t)name_cap, "%s", ldpc_decoder_kernel_name(d));
     }
+    return LDPC_OK;
+}
+
+// kernel and launch geometry of ldpc_mc_run(early_term = 1): the persistent-slot kernel when the graph has one
+extern "C" int ldpc_decoder_mc_info(const ldpc_decoder_t *d, int32_t *persistent, int32_t *frames_per_cta, int32_t *ctas_per_sm,
+                                    int32_t *threads_per_cta, int32_t *smem_bytes, char *kernel_name, int32_t name_cap) {
+    if (!d) return fail(LDPC_E_INVALID, "decoder_mc_info: null decoder");
+    const bool mc = d->func_mc != nullptr && !env_on("LDPC_B200_NO_PERSIST");
+    if (!mc) {
+        if (persistent) *persistent = 0;
+        return ldpc_decoder_launch_info(d, 1, frames_per_cta, ctas_per_sm, threads_per_cta, smem_bytes, kernel_name, name_cap);
+    }
+    if (persistent) *persistent = 1;
+    if (frames_per_cta) *frames_per_cta = d->geom_mc.FB;
+    if (ctas_per_sm) *ctas_per_sm = d->geom_mc.ctas_per_sm;
+    if (threads_per_cta) *threads_per_cta = d->geom_mc.threads;
+    if (smem_bytes) *smem_bytes = d->geom_mc.smem_bytes;
+    if (kernel_name && name_cap > 0) snprintf(kernel_name, (size_t)name_cap, "nms_mcp_spec_%s", d->mc_name);
     return LDPC_OK;
 }
 
@@ -798,6 +874,7 @@ namespace {
 void fill_channel(KParams &P, double sigma, uint64_t seed, uint64_t frame_offset) {
     P.sigma = (float)sigma;
     P.two_over_s2 = (float)(2.0 / (sigma * sigma));
+    P.two_over_s = (float)(2.0 / sigma);
     P.seed = seed; P.frame_offset = frame_offset;
 }
 }   // namespace
@@ -811,6 +888,20 @@ extern "C" int ldpc_llr_generate(const ldpc_decoder_t *d, double sigma, int64_t 
     KParams P = d->base;
     fill_channel(P, sigma, seed, frame_offset);
     CUDA_TRY(nms_launch_generate(P, llr_dev, n_frames, (cudaStream_t)stream));
+    return LDPC_OK;
+}
+
+extern "C" int ldpc_normal_probe(int32_t device, uint64_t seed, uint64_t frame_offset, int64_t n_frames, int32_t quads_per_frame,
+                                 float *normals_dev, uint64_t *tail_counts_dev, void *stream) {
+    if (n_frames < 0 || quads_per_frame <= 0 || (!normals_dev && !tail_counts_dev))
+        return fail(LDPC_E_INVALID, "normal_probe: bad arguments");
+    int ndev = 0;
+    if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev <= 0) { cudaGetLastError(); return fail(LDPC_E_CUDA, "no CUDA device"); }
+    if (device < 0 || device >= ndev) return fail(LDPC_E_INVALID, "device %d out of range", device);
+    DeviceGuard guard(device);
+    if (!guard.ok) return fail(LDPC_E_CUDA, "cudaSetDevice(%d) failed", device);
+    CUDA_TRY(nms_launch_normal_probe(seed, frame_offset, n_frames, quads_per_frame, normals_dev,
+                                     (unsigned long long *)tail_counts_dev, (cudaStream_t)stream));
     return LDPC_OK;
 }
 
@@ -837,7 +928,7 @@ extern "C" int ldpc_mc_run(const ldpc_decoder_t *d, double sigma, int64_t n_fram
 extern "C" int ldpc_mc_run_staged(const ldpc_decoder_t *d, double sigma, int64_t n_frames, uint64_t seed, uint64_t frame_offset,
                                   int32_t iters, int32_t stage1_iters, int32_t harvest_mode, uint64_t *counters_dev,
                                   float *uncor_buf_dev, uint32_t *uncor_count_dev, uint32_t uncor_capacity,
-                                  uint64_t *defer_list_dev, uint32_t *defer_count_dev, void *stream) {
+                                  uint64_t *defer_list_dev, uint32_t *defer_count_dev, uint32_t defer_capacity, void *stream) {
     if (!d || n_frames < 0 || !(sigma > 0.0) || !counters_dev || !defer_list_dev || !defer_count_dev)
         return fail(LDPC_E_INVALID, "mc_run_staged: bad arguments");
     const int T = iters == 0 ? d->T : iters;
@@ -845,6 +936,11 @@ extern "C" int ldpc_mc_run_staged(const ldpc_decoder_t *d, double sigma, int64_t
     if (stage1_iters < 1 || stage1_iters >= T) return fail(LDPC_E_INVALID, "mc_run_staged: stage1_iters %d outside 1..%d", stage1_iters, T - 1);
     if (harvest_mode < 0 || harvest_mode > 3) return fail(LDPC_E_INVALID, "mc_run_staged: harvest_mode %d", harvest_mode);
     if (n_frames == 0) return LDPC_OK;
+    // a graph with a persistent-slot kernel needs no staging: its slots are refilled frame by frame (same counters)
+    if (defer_capacity == 0) return fail(LDPC_E_INVALID, "mc_run_staged: defer_capacity is 0");
+    if (d->func_mc != nullptr && !env_on("LDPC_B200_NO_PERSIST"))
+        return ldpc_mc_run(d, sigma, n_frames, seed, frame_offset, iters, 1, harvest_mode, counters_dev, uncor_buf_dev,
+                           uncor_count_dev, uncor_capacity, stream);
     if (n_frames > 0xffffffffLL) return fail(LDPC_E_LIMIT, "mc_run_staged: more than 2^32 - 1 frames per call");
     DeviceGuard guard(d->device);
     if (!guard.ok) return fail(LDPC_E_CUDA, "cudaSetDevice(%d) failed", d->device);
@@ -859,13 +955,16 @@ extern "C" int ldpc_mc_run_staged(const ldpc_decoder_t *d, double sigma, int64_t
     P.uncor_buf = uncor_buf_dev; P.uncor_count = uncor_count_dev; P.uncor_cap = uncor_capacity;
     // stage 1: every frame, stage1_iters iterations; frames without a zero syndrome by then go to the list
     P.T_run = stage1_iters; P.n_frames = n_frames;
-    P.defer_list = (unsigned long long *)defer_list_dev; P.defer_count = defer_count_dev;
+    P.defer_list = (unsigned long long *)defer_list_dev; P.defer_count = defer_count_dev; P.defer_cap = defer_capacity;
     int rc = launch(d, P, st);
     if (rc != LDPC_OK) return rc;
     uint32_t n2 = 0;
     CUDA_TRY(cudaMemcpyAsync(&n2, defer_count_dev, sizeof n2, cudaMemcpyDeviceToHost, st));
     CUDA_TRY(cudaStreamSynchronize(st));
     if (n2 == 0) return LDPC_OK;
+    if (n2 > defer_capacity)
+        return fail(LDPC_E_LIMIT, "mc_run_staged: %u frames deferred, defer_list holds %u (counters already hold stage 1: "
+                                  "zero them and call again with a larger list)", n2, defer_capacity);
     // stage 2: the listed frames regenerated from their global indices, all `iters` iterations (early termination on)
     P.T_run = T; P.n_frames = (long long)n2;
     P.frame_list = (const unsigned long long *)defer_list_dev; P.defer_list = nullptr; P.defer_count = nullptr;

@@ -57,7 +57,7 @@ struct KParams {
     const signed char *llr_q8;
     float q8_step;
     long long n_frames;
-    float sigma, two_over_s2;
+    float sigma, two_over_s2, two_over_s;   // channel: llr = (2/sigma) * n - 2/sigma^2
     unsigned long long seed, frame_offset;
     // two-stage Monte-Carlo (ldpc_mc_run_staged): stage 1 decodes T_run < T iterations with early termination and, instead
     // of counting a frame that has not reached a zero syndrome, appends its global frame index to defer_list; stage 2
@@ -66,6 +66,7 @@ struct KParams {
     const unsigned long long *frame_list;
     unsigned long long *defer_list;
     unsigned int *defer_count;
+    unsigned int defer_cap;       // entries defer_list holds; frames beyond it are counted in defer_count but not listed
     int punct_s, punct_e, short_s, short_e;
     // outputs (nullable)
     float *app; int app_all; long long app_stride_t;   // elements between iterations (B*NZ)
@@ -82,7 +83,9 @@ struct KParams {
     unsigned short vn_order[LDPC_MAX_N];      // columns likewise
     int n_cn_cls, n_vn_cls;                   // runs of equal degree inside cn_order / vn_order
     ushort4 cn_cls[32], vn_cls[32];           // {degree, first position, end position, 0}
-    uint2 cn_task[LDPC_MAX_M];                // slot-major row list: [slot * ceil(M/R) + n] = {e0*LP*4, dc | row << 16}; dc 0 = none
+    // slot-major row list: [slot * ceil(M/R) + n] = {e0*LP*4, dc | row << 16}; dc 0 = none.  R * ceil(M/R) can exceed M by R - 1
+    // and the specialised kernels prefetch one entry ahead: hence the slack (the host refuses R > 32)
+    uint2 cn_task[LDPC_MAX_M + 34];
     unsigned short e_col[LDPC_MAX_E];         // proto column of E(C) edge e
     unsigned short e_sF[LDPC_MAX_E];          // s_e*Fp: check lane q -> variable lane (q + sF) mod L
     int2 vn_edge[LDPC_MAX_E];                 // column-sorted: {e*LP*4, ((L - s_e*Fp) mod L)*4}: byte offsets
@@ -103,6 +106,8 @@ struct NmsSpecEntry {
 extern "C" const NmsSpecEntry *nms_spec_table(int *count);
 extern "C" const NmsSpecEntry *nms_spec_f32_table(int *count);    // float path (decoding_type 1)
 extern "C" const NmsSpecEntry *nms_spec_f32q_table(int *count);   // quantised twin (q_bit 6, per-edge weights)
+extern "C" const NmsSpecEntry *nms_spec_mcp_table(int *count);    // persistent-slot Monte-Carlo kernels (nms_mcp.cuh)
+#define NMS_MCP_MISC_WORDS (112 + 32 * 8 * 2)   // their per-CTA state words (== nms::MCP_MISC_WORDS)
 
 // ---- Philox4x32-10 (Salmon et al., SC'11), written out so the host tests can restate it
 __host__ __device__ __forceinline__ void philox4x32_10(uint32_t c0, uint32_t c1, uint32_t c2, uint32_t c3,
@@ -120,5 +125,7 @@ __host__ __device__ __forceinline__ void philox4x32_10(uint32_t c0, uint32_t c1,
 }
 
 cudaError_t nms_launch_generate(const KParams &P, float *out, long long n_frames, cudaStream_t st);
+cudaError_t nms_launch_normal_probe(unsigned long long seed, unsigned long long frame_offset, long long n_frames, int nquads,
+                                    float *out, unsigned long long *counts, cudaStream_t st);
 void nms_note_launch();
 unsigned long long nms_launch_count();

@@ -88,18 +88,29 @@ __device__ __forceinline__ void app_store(const KParams &P, const Ctx &c, int j,
 }
 
 // ------------------------------------------------------------------------- sample generation
-// One Philox4x32-10 block -> four N(0,1) via Box-Muller -> four channel LLRs of frame F, bits 4*quad..4*quad+3.
-// Print_Functions.py:45-60: x = n*sigma - 1 (all-zero word), llr = 2x/sigma^2, quantise, puncture, shorten.
-__device__ __forceinline__ void gen_llr4(const KParams &P, unsigned long long F, int quad, float out[4]) {
+// Tail refinement of a Box-Muller radius.  u1 = (r + 0.5) / 2^32 from one 32-bit word stops at 2^-33, i.e. at a radius
+// of 6.76 sigma, and has only a few hundred distinct values beyond 5.8 sigma.  When the word is below 2^8 (once in
+// 1.7e7 pairs) a second Philox block (same frame and quad, counter word c3 = 1 + pair) supplies 32 more bits:
+// u1 = (r + (r' + 0.5) / 2^32) / 2^32 >= 2^-65, radius up to 9.5 sigma with a smooth tail.  Out of line: the hot loop
+// pays one compare.
+static __device__ __noinline__ float gen_tail_u1(unsigned long long F, int quad, int pair, uint32_t r, unsigned long long seed) {
+    uint32_t x[4];
+    philox4x32_10((uint32_t)F, (uint32_t)(F >> 32), (uint32_t)quad, 1u + (uint32_t)pair, (uint32_t)seed, (uint32_t)(seed >> 32), x);
+    const float lowbits = fmaf((float)x[0], 2.3283064365386963e-10f, 1.1641532182693481e-10f);   // (r' + 0.5) / 2^32 in (0, 1)
+    return ((float)r + lowbits) * 2.3283064365386963e-10f;
+}
+
+// One Philox4x32-10 block -> four N(0,1) via Box-Muller (frame F, bits 4*quad..4*quad+3)
+__device__ __forceinline__ void gen_normal4(unsigned long long seed, unsigned long long F, int quad, float n[4]) {
     uint32_t r[4];
-    philox4x32_10((uint32_t)F, (uint32_t)(F >> 32), (uint32_t)quad, 0u, (uint32_t)P.seed, (uint32_t)(P.seed >> 32), r);
-    float n[4];
+    philox4x32_10((uint32_t)F, (uint32_t)(F >> 32), (uint32_t)quad, 0u, (uint32_t)seed, (uint32_t)(seed >> 32), r);
 #pragma unroll
     for (int h = 0; h < 2; ++h) {
-        const float u1 = fmaf((float)r[2 * h], 2.3283064365386963e-10f, 1.1641532182693481e-10f);   // (r+0.5)/2^32
+        float u1 = fmaf((float)r[2 * h], 2.3283064365386963e-10f, 1.1641532182693481e-10f);   // (r+0.5)/2^32
+        if (r[2 * h] < 256u) u1 = gen_tail_u1(F, quad, h, r[2 * h], seed);
         const float u2 = (float)r[2 * h + 1] * 2.3283064365386963e-10f;
         // hardware log2 / rsqrt / sin / cos (MUFU): ~1e-6 absolute on the normals, far below the quantiser step and
-        // the Monte-Carlo noise; ldpc_llr_generate and the fused loop share this code, so they stay identical
+        // the Monte-Carlo noise; ldpc_llr_generate and the fused loops share this code, so they stay identical
         const float x = -2.0f * __logf(u1);
         const float rad = x > 0.0f ? x * rsqrtf(x) : 0.0f;
         float sn, cs;
@@ -107,11 +118,23 @@ __device__ __forceinline__ void gen_llr4(const KParams &P, unsigned long long F,
         n[2 * h] = rad * cs;
         n[2 * h + 1] = rad * sn;
     }
+}
+
+// N(0,1) sample -> channel LLR of a zero bit.  Print_Functions.py:45-50: x = n*sigma - 1 (all-zero word), llr = 2x/sigma^2
+// (float64 there), quantised on the QMS path.  Here llr = fma(n, 2/sigma, -2/sigma^2): one rounding.
+__device__ __forceinline__ float llr_from_normal(const KParams &P, float n) {
+    const float llr = fmaf(n, P.two_over_s, -P.two_over_s2);
+    return P.qms ? qf(P, llr) : llr;                                          // :49-50
+}
+
+// One Philox block -> four channel LLRs (bits 4*quad .. 4*quad+3 of frame F), punctured and shortened (:53-60)
+__device__ __forceinline__ void gen_llr4(const KParams &P, unsigned long long F, int quad, float out[4]) {
+    float n[4];
+    gen_normal4(P.seed, F, quad, n);
 #pragma unroll
     for (int k4 = 0; k4 < 4; ++k4) {
         const int k = 4 * quad + k4 + 1;   // 1-based bit index
-        float llr = __fmul_rn(__fadd_rn(__fmul_rn(n[k4], P.sigma), -1.0f), P.two_over_s2);
-        if (P.qms) llr = qf(P, llr);                                          // :49-50
+        float llr = llr_from_normal(P, n[k4]);
         if (P.punct_s > 0 && k >= P.punct_s && k <= P.punct_e) llr = P.sp ? 0.001f : 0.0f;    // :53-57
         if (P.short_s > 0 && k >= P.short_s && k <= P.short_e) llr = -P.clip; // :59-60
         out[k4] = llr;
@@ -388,7 +411,8 @@ __device__ __forceinline__ void nms_decode_body(const KParams &P) {
         if (tid < 64) {
             bool valid = tid < c.nvalid;
             if (valid && P.defer_list != nullptr && !(st & ST_OUT_SYND_OK)) {   // stage 1: not converged -> stage 2, not counted here
-                P.defer_list[atomicAdd(P.defer_count, 1u)] = frame_index(P, c.frame0 + tid);
+                const unsigned slot_idx = atomicAdd(P.defer_count, 1u);
+                if (slot_idx < P.defer_cap) P.defer_list[slot_idx] = frame_index(P, c.frame0 + tid);   // overflow: the host sees count > capacity
                 valid = false;
             }
             const uint32_t be = misc[MISC_BITERR + tid];

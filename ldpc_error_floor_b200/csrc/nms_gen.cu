@@ -23,7 +23,47 @@ __global__ void llr_generate_kernel(const __grid_constant__ KParams P, float *ou
     }
 }
 
+// The generator's normals, bare: optional copy-out and tail counts (|n| > 3, 4, 5, 6, 7 sigma, total) -- what the tests
+// hold against erfc and a Kolmogorov-Smirnov bound (tests/test_gpu_mc.py)
+__global__ void normal_probe_kernel(unsigned long long seed, unsigned long long frame_offset, long long n_frames, int nquads,
+                                    float *out, unsigned long long *counts) {
+    const long long total = n_frames * nquads;
+    unsigned c3 = 0, c4 = 0, c5 = 0, c6 = 0, c7 = 0;
+    for (long long it = blockIdx.x * (long long)blockDim.x + threadIdx.x; it < total; it += (long long)gridDim.x * blockDim.x) {
+        const long long f = it / nquads;
+        const int quad = (int)(it - f * nquads);
+        float n[4];
+        gen_normal4(seed, frame_offset + (unsigned long long)f, quad, n);
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+            const float a = fabsf(n[k]);
+            c3 += a > 3.0f; c4 += a > 4.0f; c5 += a > 5.0f; c6 += a > 6.0f; c7 += a > 7.0f;
+            if (out != nullptr) out[it * 4 + k] = n[k];
+        }
+    }
+    if (counts != nullptr) {
+        const unsigned v[5] = {c3, c4, c5, c6, c7};
+#pragma unroll
+        for (int k = 0; k < 5; ++k) {
+            const unsigned r = __reduce_add_sync(0xffffffffu, v[k]);
+            if ((threadIdx.x & 31) == 0 && r) atomicAdd(counts + k, (unsigned long long)r);
+        }
+        if (blockIdx.x == 0 && threadIdx.x == 0) atomicAdd(counts + 5, (unsigned long long)total * 4ull);
+    }
+}
+
 }   // namespace nms
+
+cudaError_t nms_launch_normal_probe(unsigned long long seed, unsigned long long frame_offset, long long n_frames, int nquads,
+                                    float *out, unsigned long long *counts, cudaStream_t st) {
+    const long long items = n_frames * nquads;
+    if (items <= 0) return cudaSuccess;
+    const int threads = 256;
+    const int grid = (int)std::min<long long>((items + threads - 1) / threads, 148LL * 8);
+    nms::normal_probe_kernel<<<grid, threads, 0, st>>>(seed, frame_offset, n_frames, nquads, out, counts);
+    nms_note_launch();
+    return cudaGetLastError();
+}
 
 static std::atomic<unsigned long long> g_launches{0};
 void nms_note_launch() { ++g_launches; }

@@ -52,9 +52,17 @@ struct H2Ctx {
     uint32_t xq4;     // sb + off_xq*4 + q*4   (+ j*LP*4 per column)
 };
 
+// shared-window address of nms_smem[0].  volatile: computed where written, once -- left to itself the compiler rematerialises
+// the conversion (S2R SR_CgaCtaId + LEA, ~25 cycles of latency) next to every use that is short of registers
+__device__ __forceinline__ uint32_t smem_base() {
+    uint32_t sb;
+    asm volatile("{ .reg .u64 t; cvta.to.shared.u64 t, %1; cvt.u32.u64 %0, t; }" : "=r"(sb) : "l"((const void *)nms_smem));
+    return sb;
+}
+
 __device__ __forceinline__ H2Ctx h2_ctx(const KParams &P, const Ctx &c) {
     H2Ctx h;
-    h.sb = (uint32_t)__cvta_generic_to_shared(nms_smem);   // warp-uniform: ends up in a uniform register
+    h.sb = smem_base();
     h.q4 = (uint32_t)c.q * 4u;
     h.amask = c.act ? 0xffffffffu : 0u;
     h.Lthr4 = c.act ? (uint32_t)P.L * 4u : 0x40000000u;
@@ -90,13 +98,15 @@ __device__ __forceinline__ __half2 q2(const KParams &P, float lo, float hi) {
 
 // weighted, quantised magnitudes for "edge is not the minimum" (A) and "edge is the minimum" (B), with the
 // row's sign parity folded in.  par: XOR of all raw V->C words of the row; w0 / w1: CN / UCN weight.
-__device__ __forceinline__ void h2_row_mags(const KParams &P, float w0, float w1, bool dc_odd, uint32_t par,
-                                            __half2 m1, __half2 m2, uint32_t &A, uint32_t &B) {
+// The two frames of a lane may be at different iterations (persistent-slot Monte-Carlo kernel, nms_mcp.cuh), hence one
+// (CN, UCN) weight pair per half.
+__device__ __forceinline__ void h2_row_mags(const KParams &P, float w0lo, float w0hi, float w1lo, float w1hi, bool dc_odd,
+                                            uint32_t par, __half2 m1, __half2 m2, uint32_t &A, uint32_t &B) {
     const __half2 qm = __float2half2_rn(P.qmax), zero = __float2half2_rn(0.0f);
     // drop the piggy-backed hard bits; V->C saturation (:223-224) applied to the two minima
     const __half2 m1c = __hmin2(u2h(h2u(m1) & ~LSB2), qm), m2c = __hmin2(u2h(h2u(m2) & ~LSB2), qm);
-    const float wlo = (par & 1u) ? w1 : w0;         // unsatisfied check -> UCN weight (:275,:285,:295)
-    const float whi = (par & 0x10000u) ? w1 : w0;
+    const float wlo = (par & 1u) ? w1lo : w0lo;     // unsatisfied check -> UCN weight (:275,:285,:295)
+    const float whi = (par & 0x10000u) ? w1hi : w0hi;
     // Q(relu(min * w)) (:308-311)
     __half2 magA = __floats2half2_rn(qround(__fmul_rn(__low2float(m1c), wlo), P.qmagic),
                                      qround(__fmul_rn(__high2float(m1c), whi), P.qmagic));
@@ -108,6 +118,10 @@ __device__ __forceinline__ void h2_row_mags(const KParams &P, float w0, float w1
     const uint32_t s0 = (par & SIGN2) ^ (dc_odd ? SIGN2 : 0u);
     A = h2u(magA) ^ s0;
     B = h2u(magB) ^ s0;
+}
+__device__ __forceinline__ void h2_row_mags(const KParams &P, float w0, float w1, bool dc_odd, uint32_t par,
+                                            __half2 m1, __half2 m2, uint32_t &A, uint32_t &B) {
+    h2_row_mags(P, w0, w0, w1, w1, dc_odd, par, m1, m2, A, B);
 }
 
 // (min1, min2) of |raw[LO..HI)| as a tournament: pairs are sorted with one min and one max, two sorted pairs merge with
@@ -141,8 +155,8 @@ __device__ __forceinline__ void h2_min12(const uint32_t (&raw)[DC], __half2 &m1,
 
 // one check row held in registers.  a0: byte address of msg[e0][q]; stride4: bytes between edges (LP*4)
 template <int DC>
-__device__ __forceinline__ void cn_row_h2(const KParams &P, uint32_t a0, uint32_t stride4, float w0, float w1,
-                                          uint32_t &bad) {
+__device__ __forceinline__ void cn_row_h2(const KParams &P, uint32_t a0, uint32_t stride4, float w0lo, float w0hi,
+                                          float w1lo, float w1hi, uint32_t &bad) {
     uint32_t raw[DC];
 #pragma unroll
     for (int p = 0; p < DC; ++p) raw[p] = lds32(a0 + p * stride4);
@@ -153,7 +167,7 @@ __device__ __forceinline__ void cn_row_h2(const KParams &P, uint32_t a0, uint32_
     __half2 m1, m2;
     h2_min12<DC, 0, DC>(raw, m1, m2);
     uint32_t A, B;
-    h2_row_mags(P, w0, w1, (DC & 1) != 0, par, m1, m2, A, B);
+    h2_row_mags(P, w0lo, w0hi, w1lo, w1hi, (DC & 1) != 0, par, m1, m2, A, B);
     // |v| > min1 -> the others' minimum is min1 (A), else min2 (B).  The select is done as B + g (A - B) with g in {0, 1}
     // on the FMA pipe instead of a second LOP3: the integer / logic pipe runs at half the issue rate and is the busiest
     // pipe of this kernel.  Exact: A, B are on-grid values of one sign, so A - B and the sum are representable.
@@ -163,6 +177,12 @@ __device__ __forceinline__ void cn_row_h2(const KParams &P, uint32_t a0, uint32_
         const __half2 g = __hgt2(__habs2(u2h(raw[p])), m1);
         sts32(a0 + p * stride4, h2u(__hfma2(g, dAB, u2h(B))) ^ (raw[p] & SIGN2));
     }
+}
+
+template <int DC>
+__device__ __forceinline__ void cn_row_h2(const KParams &P, uint32_t a0, uint32_t stride4, float w0, float w1,
+                                          uint32_t &bad) {
+    cn_row_h2<DC>(P, a0, stride4, w0, w0, w1, w1, bad);
 }
 
 // any degree: two passes over shared memory instead of a register array

@@ -32,6 +32,65 @@ __device__ __forceinline__ uint32_t spec_rot(const H2Ctx &h) {
 
 enum { VN_ITER = 0, VN_INIT_SMEM = 1, VN_INIT_GLOBAL = 2 };
 
+// ------------------------------------------------------------------------------------ CN phase of the specialised kernels
+// Rows of one degree share a body (the loop stays small in the instruction cache); a slot's rows come sorted by degree, so
+// the phase is one counted loop per degree class -- G::cn_cls_cnt[slot][class] rows -- instead of a compare-and-branch chain
+// per row.  The row list {byte offset of the row's first message, degree | row << 16} is host-built (KParams::cn_task) and
+// read one entry ahead.  WROW: the weights differ from row to row (sharing code 2); otherwise they are loaded once per phase.
+// UCN: unsatisfied-check weights exist.  PERHALF: the two frames of a lane are at different iterations (persistent-slot
+// Monte-Carlo kernel), i.e. one weight row per half; otherwise *_hi == *_lo.
+template <class G, bool PERHALF, bool WROW, bool UCN>
+__device__ __forceinline__ void spec_cn_rows(const KParams &P, const H2Ctx &h, int slot, uint32_t wc_lo, uint32_t wc_hi,
+                                             uint32_t wu_lo, uint32_t wu_hi, uint32_t &bad) {
+    constexpr uint32_t LP4 = G::LP * 4u;
+    constexpr int NT = (G::M + G::R - 1) / G::R;
+    float w0l = 1.0f, w0h = 1.0f, w1l = 1.0f, w1h = 1.0f;
+    if constexpr (!WROW) {
+        w0l = ldsf(wc_lo);
+        w0h = PERHALF ? ldsf(wc_hi) : w0l;
+        w1l = UCN ? ldsf(wu_lo) : w0l;
+        w1h = UCN ? (PERHALF ? ldsf(wu_hi) : w1l) : w0h;
+    }
+    const uint2 *task = P.cn_task + slot * NT;
+    uint2 tk = task[0];
+    static_for<0, G::NDEG>([&](auto k) {
+        constexpr int K = decltype(k)::v;
+        constexpr int DC = G::cn_degs_desc[K];
+        int nk = 0;                                         // rows of this class in this warp's slot (compile-time table)
+        static_for<0, G::R>([&](auto sl) {
+            constexpr int CNT = G::cn_cls_cnt[decltype(sl)::v * G::NDEG + K];
+            if (slot == decltype(sl)::v) nk = CNT;
+        });
+#pragma unroll 1
+        for (int n = 0; n < nk; ++n) {
+            const uint2 cur = tk;
+            tk = *++task;                                   // next row's entry: its latency hides behind this row
+            const uint32_t a0 = h.sb + cur.x + h.q4;
+            if constexpr (WROW) {
+                const uint32_t i4 = (cur.y >> 14) & ~3u;    // row index * 4
+                w0l = ldsf(wc_lo + (i4 & (uint32_t)P.h2_mc));
+                w0h = PERHALF ? ldsf(wc_hi + (i4 & (uint32_t)P.h2_mc)) : w0l;
+                w1l = UCN ? ldsf(wu_lo + (i4 & (uint32_t)P.h2_mu)) : w0l;
+                w1h = UCN ? (PERHALF ? ldsf(wu_hi + (i4 & (uint32_t)P.h2_mu)) : w1l) : w0h;
+            }
+            cn_row_h2<DC>(P, a0, LP4, w0l, w0h, w1l, w1h, bad);
+        }
+    });
+}
+
+template <class G, bool PERHALF>
+__device__ __forceinline__ void spec_cn_phase(const KParams &P, const H2Ctx &h, int slot, uint32_t wc_lo, uint32_t wc_hi,
+                                              uint32_t wu_lo, uint32_t wu_hi, uint32_t &bad) {
+    const bool wrow = (P.h2_mc | P.h2_mu) != 0, ucn = P.h2w_u != P.h2w_c;   // uniform
+    if (wrow) {
+        if (ucn) spec_cn_rows<G, PERHALF, true, true>(P, h, slot, wc_lo, wc_hi, wu_lo, wu_hi, bad);
+        else spec_cn_rows<G, PERHALF, true, false>(P, h, slot, wc_lo, wc_hi, wu_lo, wu_hi, bad);
+    } else {
+        if (ucn) spec_cn_rows<G, PERHALF, false, true>(P, h, slot, wc_lo, wc_hi, wu_lo, wu_hi, bad);
+        else spec_cn_rows<G, PERHALF, false, false>(P, h, slot, wc_lo, wc_hi, wu_lo, wu_hi, bad);
+    }
+}
+
 template <class G>
 struct H2SpecPolicy {
     static constexpr bool H2 = true;
@@ -41,24 +100,10 @@ struct H2SpecPolicy {
     static __device__ __forceinline__ void setup(const KParams &, int) {}
 
     // ------------------------------------------------------------------------------ CN phase
-    // rows of one degree share a body; the row's base offset and weights are the only per-row values
     static __device__ __forceinline__ void cn_phase(const KParams &P, const Ctx &c, int t, uint32_t &bad) {
         const H2Ctx h = h2_ctx(P, c);
         const uint32_t wcrow = h2_wrow(h, P.h2w_c, t, P.h2_wc), wurow = h2_wrow(h, P.h2w_u, t, P.h2_wu);
-        constexpr int NT = (G::M + G::R - 1) / G::R;
-        const uint2 *task = P.cn_task + c.slot * NT;   // host-built: {row offset in bytes, degree | row index << 16}
-#pragma unroll 1
-        for (int n = 0; n < NT; ++n) {
-            const uint2 tk = task[n];
-            const int dc = (int)(tk.y & 0xffffu), i = (int)(tk.y >> 16);
-            if (dc == 0) break;
-            const uint32_t a0 = h.sb + tk.x + h.q4;
-            const float w0 = h2_w(wcrow, i, P.h2_mc), w1 = h2_w(wurow, i, P.h2_mu);
-            static_for<0, G::NDEG>([&](auto k) {
-                constexpr int DC = G::cn_degs[decltype(k)::v];
-                if (dc == DC) cn_row_h2<DC>(P, a0, LP4, w0, w1, bad);
-            });
-        }
+        spec_cn_phase<G, false>(P, h, c.slot, wcrow, wcrow, wurow, wurow, bad);
     }
 
     // ------------------------------------------------------------------------------ VN phase
@@ -212,7 +257,7 @@ struct H2SpecPolicy {
 
     // ------------------------------------------------------------------ final syndrome pass
     static __device__ __forceinline__ uint32_t synd_phase(const KParams &P, const Ctx &c, int tl) {
-        const uint32_t a0 = (uint32_t)__cvta_generic_to_shared(nms_smem) + (uint32_t)c.q * 4u;
+        const uint32_t a0 = smem_base() + (uint32_t)c.q * 4u;
         uint32_t bad = 0;
         static_for<0, G::R>([&](auto s) {
             constexpr int SLOT = decltype(s)::v;

@@ -1,0 +1,340 @@
+// nms_mcp.cuh -- persistent-slot Monte-Carlo kernel (packed fp16x2, graph-specialised).
+//
+// The batch kernels of nms_device.cuh give a CTA FB frames, decode them together and fetch the next FB when ALL of
+// them have stopped: with per-frame early termination the slowest frame of a batch sets the pace, and at error-floor
+// SNRs (average 2-6 iterations, a few per cent of stragglers that run all T) most lanes idle most of the time.  Here a
+// CTA owns FB frame SLOTS instead.  Every loop step is one flooding iteration for whatever frames sit in the slots --
+// each at its own iteration index -- and a slot whose frame has stopped (zero syndrome, or T iterations done) is
+// refilled on the spot with the next frame of the CTA's share of the global frame index space:
+//
+//   step s:  [generate the channel values of the frames entering now]      (all threads, only if a slot was refilled)
+//            VN phase  -- for a slot that was just refilled the stale C->V words are multiplied by 0 (the sum is an FMA
+//                         chain S = cv * keep + S, the extrinsic output SX - cv an FMA cv * (-keep) + SX: no extra
+//                         instruction per edge), which makes the phase the "init pass" of that frame
+//            CN phase  -- weights of iteration t_f per half (the two frames of a lane need not be at the same iteration)
+//            bookkeeping (warp 0, one lane per slot): syndrome / ones of the previous hard decision -> stop or go on,
+//                         counters in registers, harvest, next frame index
+//
+// Samples: exactly those of ldpc_llr_generate / the batch kernels (Philox counter = global frame index), so the eight
+// counters and the harvested words of a run do not depend on which kernel, launch geometry or number of GPUs produced
+// them (tests/test_gpu_mc.py::test_persistent_kernel_counts_like_the_batch_kernel).
+//
+// Shared memory: msg[E][LP] (V->C / C->V in place) | xq[N][LP] (quantised channel values, half2) | weights | state.
+// No float channel array and no hard-decision ballots: Monte-Carlo samples are on the quantiser grid already
+// (xa == Q(xa)), and the all-zero codeword needs bit COUNTS, not bits -- z72 fits 2 CTAs per SM this way.
+//
+// Reference semantics restated: decode Main_Functions.py:161-335, samples Print_Functions.py:29-72, metrics :100-118,
+// loop being replaced :136-161.
+#pragma once
+#include "nms_h2_spec.cuh"
+
+namespace nms {
+
+// state words, relative to P.off_misc; [2] = double-buffered by step parity
+constexpr int MCP_SYND = 0;    // [2] slot mask: the previous hard decision violates a check
+constexpr int MCP_GE1 = 2;     // [2] slots whose frame is at iteration >= 1 (its syndrome means something)
+constexpr int MCP_ATT = 4;     // [2] slots whose frame has used up its iterations: it stops whatever the syndrome says
+constexpr int MCP_ACT = 6;     // [2] slots that hold a frame
+constexpr int MCP_HMASK = 8;   // slots whose frame is copied to the harvest buffer in this step
+constexpr int MCP_TP = 16;     // [2][16] per slot pair: iteration index of the low | high << 16 frame
+constexpr int MCP_CNT = 48;    // [2][16] per slot pair: ones in the counted columns of the last hard decision, low | high << 16
+constexpr int MCP_HROW = 80;   // [32] harvest row of the slot's frame
+constexpr int MCP_ACC = 112;   // [32][8] uint64: the eight Monte-Carlo counters per slot, flushed once per launch
+constexpr int MCP_MISC_WORDS = MCP_ACC + 32 * 8 * 2;
+
+__device__ __forceinline__ void sts16(uint32_t a, unsigned short v) { asm volatile("st.shared.u16 [%0], %1;" ::"r"(a), "h"(v)); }
+
+template <class G>
+struct McpKernel {
+    static constexpr int FB = 2 * G::Fp;
+    static constexpr int NTHR = G::C * G::R * 32;
+    static constexpr uint32_t LP4 = G::LP * 4u;
+    static constexpr bool PAD = G::L != G::LP;
+    static constexpr int NZ = G::N * G::z;
+    static constexpr int NQUADS = (NZ + 3) / 4;
+    static constexpr uint32_t FBMASK = FB >= 32 ? 0xffffffffu : ((1u << FB) - 1u);
+    static_assert(FB <= 32, "slot masks are one word");
+
+    // ---------------------------------------------------------------------------------------- sample generation
+    // channel values of the frames entering the slots in `fresh` (rank r in the mask -> global frame first + r), written
+    // as halves into the xq array; same samples, same order as gen_llr4 draws them for everyone else
+    static __device__ __forceinline__ void generate(const KParams &P, uint32_t sb, uint32_t fresh, unsigned long long first) {
+        const int total = __popc(fresh) * NQUADS;
+        const unsigned short hneg = __half_as_ushort(__float2half_rn(-P.qmax));   // a shortened bit: Q(-clip_LLR) to the decoder
+        for (int it = threadIdx.x; it < total; it += NTHR) {
+            const int r = it / NQUADS, quad = it - r * NQUADS;
+            uint32_t m = fresh;
+            for (int i = 0; i < r; ++i) m &= m - 1u;
+            const int f = __ffs(m) - 1;                                            // the r-th lowest refilled slot
+            const int k0 = 4 * quad, j0 = k0 / G::z, a0 = k0 - j0 * G::z;
+            const uint32_t base = sb + (uint32_t)P.off_xq * 4u + (uint32_t)(f >> 1) * 4u + (uint32_t)(f & 1) * 2u;
+            if constexpr (G::z % 4 == 0) {
+                // the four bits of a quad sit in one column at consecutive circulant lanes: one address, immediate offsets
+                const uint32_t ad = base + (uint32_t)(j0 * G::LP + a0 * G::Fp) * 4u;
+                const int k1 = k0 + 1;                                             // 1-based index of the quad's first bit
+                const bool allp = P.punct_s > 0 && k1 >= P.punct_s && k1 + 3 <= P.punct_e;
+                const bool alls = P.short_s > 0 && k1 >= P.short_s && k1 + 3 <= P.short_e;
+                if (allp || alls) {                                                // no sample needed: the value is fixed
+                    const unsigned short c = alls ? hneg : (unsigned short)0;
+#pragma unroll
+                    for (int k4 = 0; k4 < 4; ++k4) sts16(ad + (uint32_t)(k4 * G::Fp) * 4u, c);
+                    continue;
+                }
+                float n[4];
+                gen_normal4(P.seed, P.frame_offset + first + (unsigned long long)r, quad, n);
+#pragma unroll
+                for (int k4 = 0; k4 < 4; ++k4) {
+                    const int k = k1 + k4;
+                    unsigned short v = __half_as_ushort(__float2half_rn(llr_from_normal(P, n[k4])));
+                    if (P.punct_s > 0 && k >= P.punct_s && k <= P.punct_e) v = 0;
+                    if (P.short_s > 0 && k >= P.short_s && k <= P.short_e) v = hneg;
+                    sts16(ad + (uint32_t)(k4 * G::Fp) * 4u, v);
+                }
+            } else {
+                float v[4];
+                gen_llr4(P, P.frame_offset + first + (unsigned long long)r, quad, v);
+                int k = k0, j = j0, a = a0;
+#pragma unroll
+                for (int k4 = 0; k4 < 4; ++k4, ++k) {
+                    const float x = fminf(fmaxf(v[k4], -P.qmax), P.qmax);          // shortened: -clip_LLR -> -qmax
+                    if (NZ % 4 == 0 || k < NZ) sts16(base + (uint32_t)(j * G::LP + a * G::Fp) * 4u, __half_as_ushort(__float2half_rn(x)));
+                    if (++a == G::z) { a = 0; ++j; }
+                }
+            }
+        }
+    }
+
+    // ------------------------------------------------------------------------------------------------ VN phase
+    // keep / negkeep: {1, 1} / {-1, -1} as half2, 0 / -0 in the half whose slot was just refilled (or is empty).
+    // freshsel: 0xffff per refilled half.  wv_lo / wv_hi: byte address of the VN weight row of the iteration each half enters.
+    // sh_lo / sh_hi: this lane's bit j*z + a is shortened iff sh_lo <= j*z <= sh_hi (VN weights see the SAMPLE there, -clip_LLR,
+    // not Q(-clip_LLR) = -qmax: Print_Functions.py:59-60 vs Main_Functions.py:168-177)
+    template <int J, bool VNW>
+    static __device__ __forceinline__ void vn_col(const KParams &P, const H2Ctx &h, uint32_t keep, uint32_t negkeep,
+                                                  uint32_t freshsel, uint32_t wv_lo, uint32_t wv_hi, int sh_lo, int sh_hi,
+                                                  uint32_t &cnt) {
+        constexpr int C0 = G::col_ptr[J], DV = G::col_ptr[J + 1] - C0;
+        uint32_t addr[DV], cv[DV];
+        static_for<0, DV>([&](auto u) {
+            constexpr int U = decltype(u)::v;
+            constexpr uint32_t X4 = (uint32_t)G::vn_e[C0 + U] * LP4;
+            constexpr int ROT = G::vn_rot[C0 + U];
+            addr[U] = h.sb + spec_rot<G, ROT>(h) + X4;
+            cv[U] = lds32(addr[U]);
+        });
+        __half2 S = __hmul2(u2h(cv[0]), u2h(keep));
+#pragma unroll
+        for (int u = 1; u < DV; ++u) S = __hfma2(u2h(cv[u]), u2h(keep), S);   // exact: cv * 1 + S, or 0 + S
+        const __half2 xqh = u2h(lds32(h.xq4 + (uint32_t)(J * G::LP) * 4u));
+        __half2 xin = xqh;
+        uint32_t hs = h2u(__hadd2(xqh, S));                                   // unclipped APP (a refilled half: xq itself)
+        if constexpr (VNW) {
+            const float wl = h2_w(wv_lo, J, P.h2_mv), wh = h2_w(wv_hi, J, P.h2_mv);
+            const bool shortened = J * G::z >= sh_lo && J * G::z <= sh_hi;
+            const float xl = shortened ? -P.clip : __low2float(xqh), xh = shortened ? -P.clip : __high2float(xqh);
+            xin = q2(P, __fmul_rn(xl, wl), __fmul_rn(xh, wh));               // Q(xa * w), :168-177
+            hs = (h2u(xin) & freshsel) | (hs & ~freshsel);                    // iteration 0 takes the syndrome of xin_0 (:181-182)
+        }
+        const uint32_t hbw = ~(hs >> 15) & LSB2;                              // bit = (value >= 0)
+        if (J < P.target_n) cnt += hbw;                                       // uniform; 16-bit counters, no carry (<= N per lane)
+        const __half2 SX = __hadd2(xin, S);
+#pragma unroll
+        for (int u = 0; u < DV; ++u) sts32(addr[u], h2u(__hfma2(u2h(cv[u]), u2h(negkeep), SX)) | hbw);   // total - self
+    }
+
+    template <int SLOT, bool VNW>
+    static __device__ __forceinline__ void vn_slot(const KParams &P, const H2Ctx &h, uint32_t keep, uint32_t negkeep,
+                                                   uint32_t freshsel, uint32_t wv_lo, uint32_t wv_hi, int sh_lo, int sh_hi,
+                                                   uint32_t &cnt) {
+        constexpr int NT = (G::N - SLOT + G::R - 1) / G::R;
+        static_for<0, NT>([&](auto n) {
+            constexpr int J = G::vn_order[SLOT + decltype(n)::v * G::R];
+            vn_col<J, VNW>(P, h, keep, negkeep, freshsel, wv_lo, wv_hi, sh_lo, sh_hi, cnt);
+        });
+    }
+
+    // ------------------------------------------------------------------------------------------------ CN phase
+    static __device__ __forceinline__ void cn_phase(const KParams &P, const H2Ctx &h, int slot, int t_lo, int t_hi, uint32_t &bad) {
+        spec_cn_phase<G, true>(P, h, slot, h2_wrow(h, P.h2w_c, t_lo, P.h2_wc), h2_wrow(h, P.h2w_c, t_hi, P.h2_wc),
+                               h2_wrow(h, P.h2w_u, t_lo, P.h2_wu), h2_wrow(h, P.h2w_u, t_hi, P.h2_wu), bad);
+    }
+
+    // ---------------------------------------------------------------------------------------------------- kernel
+    static __device__ __forceinline__ void run(const KParams &P) {
+        const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+        const int chunk = warp % G::C, slot = warp / G::C;
+        const int q = chunk * 32 + lane;
+        const bool act = q < G::L;
+        const int a_lane = act ? q / G::Fp : 0;
+        const int fp = act ? q - a_lane * G::Fp : 0;
+        H2Ctx h;
+        h.sb = smem_base();
+        h.q4 = (uint32_t)q * 4u;
+        h.amask = act ? 0xffffffffu : 0u;
+        h.Lthr4 = act ? (uint32_t)G::L * 4u : 0x40000000u;
+        h.xa8 = 0u;
+        h.xq4 = h.sb + (uint32_t)P.off_xq * 4u + h.q4;
+        uint32_t *misc = nms_smem + P.off_misc;
+        const int T = P.T_run;
+
+        // this CTA's share of the launch's frames
+        const unsigned long long nfr = (unsigned long long)P.n_frames;
+        const unsigned long long lo = nfr * blockIdx.x / gridDim.x, hi = nfr * (blockIdx.x + 1ull) / gridDim.x;
+
+        for (int idx = tid; idx < P.w_words; idx += NTHR) smem_f(P.off_w + idx) = __ldg(P.w_all + idx);
+        for (int idx = tid; idx < P.off_w; idx += NTHR) nms_smem[idx] = 0u;          // messages and channel values: finite
+        for (int idx = tid; idx < MCP_MISC_WORDS; idx += NTHR) misc[idx] = 0u;
+        unsigned long long next = lo;                                                  // first frame not yet in a slot
+        uint32_t fresh = (hi - lo) >= (unsigned long long)FB ? FBMASK : ((1u << (int)(hi - lo)) - 1u);
+        unsigned long long first = next;                                               // frame of the lowest refilled slot
+        next += (unsigned long long)__popc(fresh);
+        uint32_t empty = ~fresh & FBMASK;
+        __syncthreads();
+        if (tid == 0) misc[MCP_ACT] = fresh;
+        // bookkeeping state of slot `lane` (warp 0): iteration index of its frame, "was right at some iteration"
+        int t = 0;
+        bool ever = false;
+        unsigned long long *acc = reinterpret_cast<unsigned long long *>(misc + MCP_ACC) + (lane & 31) * 8;   // this slot's counters
+        if (fresh == 0u) return;
+
+        for (int s = 0;; ++s) {
+            const int p = s & 1;
+            if (fresh != 0u) {
+                generate(P, h.sb, fresh, first);
+                __syncthreads();
+            }
+            // ================================================================ VN phase
+            {
+                const uint32_t kb = ~(fresh | empty) >> (2 * fp);                      // bit 0 / 1: low / high frame goes on
+                const uint32_t keep = ((kb & 1u) ? 0x3c00u : 0u) | ((kb & 2u) ? 0x3c000000u : 0u);
+                const uint32_t freshsel = ((kb & 1u) ? 0u : 0xffffu) | ((kb & 2u) ? 0u : 0xffff0000u);
+                uint32_t cnt = 0;
+                if (P.sharing2 != 0) {
+                    const uint32_t tp = misc[MCP_TP + (p ^ 1) * 16 + fp];              // what the last CN phase ran
+                    const int tl = (kb & 1u) ? min((int)(tp & 0xffffu) + 1, T - 1) : 0;
+                    const int th = (kb & 2u) ? min((int)(tp >> 16) + 1, T - 1) : 0;
+                    const uint32_t wv_lo = h2_wrow(h, P.h2w_v, tl, P.h2_wv), wv_hi = h2_wrow(h, P.h2w_v, th, P.h2_wv);
+                    // shortened bits are k = j*z + a with short_s <= k + 1 <= short_e
+                    const int sh_lo = P.short_s > 0 ? P.short_s - 1 - a_lane : 0x7fffffff, sh_hi = P.short_e - 1 - a_lane;
+                    static_for<0, G::R>([&](auto sl) {
+                        if (slot == decltype(sl)::v)
+                            vn_slot<decltype(sl)::v, true>(P, h, keep, keep ^ SIGN2, freshsel, wv_lo, wv_hi, sh_lo, sh_hi, cnt);
+                    });
+                } else {
+                    static_for<0, G::R>([&](auto sl) {
+                        if (slot == decltype(sl)::v) vn_slot<decltype(sl)::v, false>(P, h, keep, keep ^ SIGN2, freshsel, 0u, 0u, 0, 0, cnt);
+                    });
+                }
+                // ones of this hard decision, per slot pair (skipped by warps that saw none: the common case once
+                // the channel errors are gone)
+                if (!act) cnt = 0u;
+                if (__any_sync(0xffffffffu, cnt != 0u)) {
+#pragma unroll
+                    for (int k = 0; k < G::Fp; ++k) {
+                        const uint32_t r = __reduce_add_sync(0xffffffffu, fp == k ? cnt : 0u);
+                        if (lane == 0 && r) atomicAdd(&misc[MCP_CNT + p * 16 + k], r);
+                    }
+                }
+            }
+            __syncthreads();
+            // ================================================================ CN phase
+            {
+                const uint32_t tp = misc[MCP_TP + p * 16 + fp];
+                uint32_t bad = 0;
+                cn_phase(P, h, slot, min((int)(tp & 0xffffu), T - 1), min((int)(tp >> 16), T - 1), bad);
+                uint32_t m = (bad & 1u) | ((bad >> 15) & 2u);
+                m = act ? m << (2 * fp) : 0u;
+                const uint32_t r = __reduce_or_sync(0xffffffffu, m);
+                if (lane == 0 && r) atomicOr(&misc[MCP_SYND + p], r);
+            }
+            __syncthreads();
+            // ================================================================ who stops, who enters
+            const uint32_t sbad = misc[MCP_SYND + p], actm = misc[MCP_ACT + p];
+            const uint32_t fin = actm & (((P.early_term ? ~sbad : 0u) & misc[MCP_GE1 + p]) | misc[MCP_ATT + p]);
+            const int nfin = __popc(fin);
+            const unsigned long long avail = hi - next;
+            const int nnew = avail >= (unsigned long long)nfin ? nfin : (int)avail;
+            uint32_t enter = fin;                                                      // the lowest nnew of the stopped slots
+            for (int k = nfin; k > nnew; --k) enter &= ~(0x80000000u >> __clz(enter));
+            if (warp == 0) {
+                const bool mine = lane < FB && ((actm >> lane) & 1u);
+                const bool stop = mine && ((fin >> lane) & 1u);
+                const uint32_t cw = misc[MCP_CNT + p * 16 + (lane >> 1 & 15)];
+                const uint32_t ones = (lane & 1) ? cw >> 16 : cw & 0xffffu;            // of APP_{t-1}
+                const bool fbad = (sbad >> lane) & 1u;
+                if (mine && t >= 1 && ones == 0u) ever = true;                         // D9: right at some iteration
+                uint32_t hidx = 0xffffffffu;
+                if (stop) {
+                    const bool synd_ok = !fbad, one = ones != 0u;
+                    acc[0] += 1; acc[1] += one; acc[2] += !ever; acc[3] += ones; acc[4] += (unsigned)t;
+                    acc[5] += !synd_ok; acc[6] += synd_ok && one;
+                    const bool harvest = P.harvest_mode == 0 ? false
+                                         : (P.harvest_mode == 1 ? !ever : (P.harvest_mode == 2 ? one : !synd_ok));
+                    if (harvest) {
+                        acc[7] += 1;
+                        if (P.uncor_count != nullptr) {
+                            hidx = atomicAdd(P.uncor_count, 1u);
+                            if (hidx >= P.uncor_cap || P.uncor_buf == nullptr) hidx = 0xffffffffu;
+                        }
+                    }
+                    t = 0;
+                    ever = false;
+                } else if (mine) {
+                    ++t;
+                }
+                __syncwarp();
+                const bool on = lane < FB && (((actm & ~fin) | enter) >> lane) & 1u;
+                const uint32_t ge1 = __ballot_sync(0xffffffffu, on && t >= 1);
+                const uint32_t att = __ballot_sync(0xffffffffu, on && t >= T);
+                const uint32_t hm = __ballot_sync(0xffffffffu, hidx != 0xffffffffu);
+                const int tn = __shfl_down_sync(0xffffffffu, t, 1);
+                if (lane < FB) misc[MCP_HROW + lane] = hidx;
+                if (lane < FB && !(lane & 1)) {
+                    misc[MCP_TP + (p ^ 1) * 16 + (lane >> 1)] = (uint32_t)t | ((uint32_t)tn << 16);
+                    misc[MCP_CNT + p * 16 + (lane >> 1)] = 0u;                         // both lanes of the pair have read it
+                }
+                if (lane == 0) {
+                    misc[MCP_GE1 + (p ^ 1)] = ge1;
+                    misc[MCP_ATT + (p ^ 1)] = att;
+                    misc[MCP_ACT + (p ^ 1)] = (actm & ~fin) | enter;
+                    misc[MCP_SYND + (p ^ 1)] = 0u;                                     // consumed one step ago
+                    misc[MCP_HMASK] = hm;
+                }
+            }
+            // harvest: the stopped frames' channel values leave before the generator overwrites them
+            if (P.harvest_mode != 0 && fin != 0u && P.uncor_buf != nullptr) {
+                __syncthreads();
+                const uint32_t hm = misc[MCP_HMASK];
+                if (hm != 0u) {
+                    for (int f = 0; f < FB; ++f) {
+                        if (!((hm >> f) & 1u)) continue;
+                        float *row = P.uncor_buf + (size_t)misc[MCP_HROW + f] * NZ;
+                        const __half *xq = reinterpret_cast<const __half *>(nms_smem + P.off_xq) + (f & 1);
+                        for (int k = tid; k < NZ; k += NTHR) {
+                            const int j = k / G::z, a = k - j * G::z;
+                            float v = __half2float(xq[(j * G::LP + a * G::Fp + (f >> 1)) * 2]);
+                            if (P.short_s > 0 && k + 1 >= P.short_s && k + 1 <= P.short_e) v = -P.clip;   // as generated
+                            row[k] = v;
+                        }
+                    }
+                    __syncthreads();
+                }
+            }
+            empty = (empty | fin) & ~enter;
+            first = next;
+            next += (unsigned long long)nnew;
+            fresh = enter;
+            if (((actm & ~fin) | enter) == 0u) break;
+        }
+
+        if (warp == 0 && P.counters != nullptr) {
+            for (int k = 0; k < 8; ++k) {
+                unsigned long long v = lane < FB ? acc[k] : 0ull;
+                for (int o = 16; o > 0; o >>= 1) v += __shfl_down_sync(0xffffffffu, v, o);
+                if (lane == 0 && v) atomicAdd(P.counters + k, v);
+            }
+        }
+    }
+};
+
+}   // namespace nms

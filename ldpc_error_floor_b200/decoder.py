@@ -137,6 +137,16 @@ class NMSDecoder:
         return {"kernel": name.value.decode(), "frames_per_cta": fb.value, "ctas_per_sm": cps.value,
                 "threads_per_cta": thr.value, "smem_bytes": smem.value}
 
+    def mc_info(self) -> Dict:
+        """Kernel and launch geometry of mc_run(early_term=True) (ldpc_decoder_mc_info); 'persistent' = the
+        persistent-slot kernel serves it."""
+        pers, fb, cps, thr, smem = (ctypes.c_int32() for _ in range(5))
+        name = ctypes.create_string_buffer(96)
+        _lib.check(_lib.load().ldpc_decoder_mc_info(self._h, ctypes.byref(pers), ctypes.byref(fb), ctypes.byref(cps),
+                                                    ctypes.byref(thr), ctypes.byref(smem), name, 96))
+        return {"persistent": bool(pers.value), "kernel": name.value.decode(), "frames_per_cta": fb.value,
+                "ctas_per_sm": cps.value, "threads_per_cta": thr.value, "smem_bytes": smem.value}
+
     def __del__(self):
         h = getattr(self, "_h", None)
         if h:
@@ -338,7 +348,8 @@ class NMSDecoder:
             _lib.check(_lib.load().ldpc_mc_run_staged(self._h, float(sigma), int(n_frames), int(seed) & (2**64 - 1),
                                                       int(frame_offset), int(iters), int(stage1_iters), int(harvest),
                                                       _ptr(counters), _ptr(uncor_buf), _ptr(uncor_count), cap,
-                                                      _ptr(self._defer_list), _ptr(self._defer_count), ctypes.c_void_p(stream)))
+                                                      _ptr(self._defer_list), _ptr(self._defer_count),
+                                                      int(self._defer_list.numel()), ctypes.c_void_p(stream)))
             return counters, uncor_buf, uncor_count
         _lib.check(_lib.load().ldpc_mc_run(self._h, float(sigma), int(n_frames), int(seed) & (2**64 - 1),
                                            int(frame_offset), int(iters), 1 if early_term else 0, int(harvest),
@@ -374,6 +385,20 @@ class NMSDecoder:
                                                 1 if early_term else 0, _ptr(counters), _ptr(hard), _ptr(it),
                                                 _ptr(fl), ctypes.c_void_p(stream)))
         return counters, DecodeResult(None, hard, it, fl, torch.empty(0), None)
+
+
+def normal_probe(seed: int, n_frames: int, quads_per_frame: int, frame_offset: int = 0, want_normals: bool = False,
+                 device: int = 0, counts: Optional[torch.Tensor] = None):
+    """The generator's N(0,1) stream on its own (ldpc_normal_probe): returns (counts int64[6] CUDA: samples with
+    |n| > 3, 4, 5, 6, 7 sigma and the total, accumulated into `counts` when given; normals f32 CUDA or None)."""
+    dev = torch.device("cuda", device)
+    if counts is None:
+        counts = torch.zeros((6,), dtype=torch.int64, device=dev)
+    out = torch.empty((n_frames * quads_per_frame * 4,), dtype=torch.float32, device=dev) if want_normals else None
+    stream = torch.cuda.current_stream(dev).cuda_stream
+    _lib.check(_lib.load().ldpc_normal_probe(int(device), int(seed) & (2**64 - 1), int(frame_offset), int(n_frames),
+                                             int(quads_per_frame), _ptr(out), _ptr(counts), ctypes.c_void_p(stream)))
+    return counts, out
 
 
 # ---- PyTorch custom op: torch.ops.ldpc_b200.nms_decode(llr, handle, ...) -> (hard, iters, flags, biterr, app)

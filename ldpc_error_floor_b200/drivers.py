@@ -226,7 +226,12 @@ def evaluate(cfg: RunConfig, weights: Optional[formats.WeightSet] = None, traini
     if rank == 0:
         with open(c.perf_filename, "w") as fh:
             fh.write(perf_header(c, SNR_Matrix, g.M, g.N, g.E, g.rate_ref))
-    dec = NMSDecoder(g, ws, iters=T, decoding_type=c.decoding_type, q_bit=c.q_bit, clip_llr=c.clip_LLR, device=device)
+    if c.opt_result_print == 3:
+        raise NotImplementedError("opt_result_print = 3 selects the best epoch by validation LOSS (Print_Functions.py:151,161, "
+                                  "167-181); compute_results here returns no loss row -- use 0, 1 or 2 (BER / FER_last / FER)")
+    # systematic = 1: metrics over the first N - M proto columns only (main_Base.py:83-86); temporal sharing needs fixed_iter
+    dec = NMSDecoder(g, ws, iters=T, decoding_type=c.decoding_type, q_bit=c.q_bit, clip_llr=c.clip_LLR, device=device,
+                     systematic=c.systematic, fixed_iter=c.fixed_iter)
     seed = 1074 + c.seed_in                                                                # noise_seed, :70
     out = {"SNR_Matrix": SNR_Matrix, "SNR_sigma": SNR_sigma, "iters": T, "decoder": dec}
     opt_valid, opt_flag = 100000, False

@@ -233,7 +233,8 @@ def _pick_stage1(counters: np.ndarray, T: int) -> int:
 def compute_results(decoder, sample_num, input_llr, SNR_sigma, batch_size, sampling_type, seed=2044,
                     uncor_path: Optional[str] = None, iters: int = 0, group=None):
     """Drop-in for Print_Functions.compute_results (:130-165): returns (Results f32[4, nSNR], seconds) with
-    rows BER_last, FER_last, FER, loss (loss is 0: the trainer is out of scope).
+    rows BER_last, FER_last, FER, loss.  The loss row stays 0: the fused Monte-Carlo path has no loss kernel, so
+    `opt_result_print = 3` (best epoch by validation loss) is refused by drivers.evaluate / trainer.train_block.
 
     sampling_type 0/2: `floor(sample_num/batch_size)*batch_size` generated frames per sigma (:135-143);
     2 also appends the never-corrected words to `uncor_path` in the Inputs/[Uncor] format (:155-156).

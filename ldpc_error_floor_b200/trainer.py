@@ -72,6 +72,9 @@ def train_block(cfg: drivers.RunConfig, training_iter_start: int, training_iter_
     from .decoder import NMSDecoder, check_params
     from .montecarlo import compute_results
     c = cfg
+    if c.opt_result_print == 3:
+        raise NotImplementedError("opt_result_print = 3 (best epoch by validation loss, Print_Functions.py:167-181): the "
+                                  "validation pass here has no loss row -- use 0, 1 or 2")
     SNR_Matrix = check_params(c.sampling_type, c.SNR_Matrix, c.sharing, c.iters_max, c.fixed_iter, c.iter_step)
     proto = formats.read_base_graph(c.path(f"./BaseGraph/{c.filename}.txt"))
     g = BaseGraph(proto, c.z_value, (c.punct_start, c.punct_end), (c.short_start, c.short_end), name=c.filename)
@@ -107,7 +110,9 @@ def train_block(cfg: drivers.RunConfig, training_iter_start: int, training_iter_
                     rows = data[0][b * c.batch_size:(b + 1) * c.batch_size]
                     xa = torch.from_numpy(formats.uncor_to_llr(rows, g.N, g.z)).to(dec.device)   # read_uncor_llr (:6-10)
                 else:
-                    xa = make_batch(dec, SNR_sigma, c.batch_size, seed, ((epoch - 1) * nbatch + b) * c.batch_size * 16)
+                    # every batch its own slice of the Philox frame space: make_batch spans len(SNR_sigma) * batch_size indices
+                    xa = make_batch(dec, SNR_sigma, c.batch_size, seed,
+                                    ((epoch - 1) * nbatch + b) * c.batch_size * max(len(SNR_sigma), 1))
                 loss, grads, _ = dec.train_grad(xa, iter_lo=t_lo, loss_type=c.loss_type, etha=etha)
                 for i in tied:
                     # temporal sharing (codes 4 / 5): ONE variable serves every iteration >= fixed_iter (weight_init
@@ -118,7 +123,10 @@ def train_block(cfg: drivers.RunConfig, training_iter_start: int, training_iter_
                 adam.step(params, grads, lr)
                 for i in params:                                                            # clip constraint (:434)
                     np.clip(params[i], c.Min_weight, c.Max_weight, out=params[i])
-                    params[i][:t_lo] = ws.blocks[i][:t_lo]                                  # frozen iterations
+                    # frozen iterations; a tied (temporal) block is ONE variable from fixed_iter on, so only the rows
+                    # before fixed_iter are frozen there -- otherwise the rows [fixed_iter, t_lo) would drift from the rest
+                    lo = min(t_lo, c.fixed_iter) if i in tied else t_lo
+                    params[i][:lo] = ws.blocks[i][:lo]
                 dec.set_weights(formats.WeightSet(list(ws.sharing), {i: p.astype(np.float32) for i, p in params.items()}))
                 avg += loss / nbatch
         t_train = time.time() - t0
@@ -136,7 +144,8 @@ def train_block(cfg: drivers.RunConfig, training_iter_start: int, training_iter_
         t_valid = 0.0
         if c.valid_flag > 0:
             vn = c.valid_num if valid_frames is None else valid_frames
-            r, t_valid = compute_results(dec, vn, data[2], SNR_sigma, c.batch_size, c.sampling_type, seed=seed + 7919)
+            # fresh validation samples every epoch, as the reference's advancing RandomState gives (main_Base.py:176-178)
+            r, t_valid = compute_results(dec, vn, data[2], SNR_sigma, c.batch_size, c.sampling_type, seed=seed + 7919 * (epoch + 1))
             res.valid.append(r)
             res.opt_value, opt_flag = drivers.print_result(r, res.opt_value, c.perf_filename, c.out_filename, T,
                                                            c.opt_result_print, opt_flag, False, root=c.root, quiet=log is None)

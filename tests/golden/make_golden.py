@@ -183,6 +183,9 @@ def make_decode_cases():
     E = int((p != -1).sum())
     make_decode_case("5g_r073_z72_qms_222_t8", "5g_r073_z72", [2, 2, 2],
                      const_weights([2, 2, 2], 8, M, N, E, rng=rng), 8, 2, 5, 2, [3.0, 4.0])
+    # BASELINE config 5 as the campaign runs it: plain 0.8 min-sum, 20 iterations, systematic = 1
+    make_decode_case("5g_r073_z72_qms_300_t20_sys", "5g_r073_z72", [3, 0, 0], const_weights([3, 0, 0], 20, M, N, E), 20, 2, 5,
+                     6, [2.5, 3.0, 3.5], target_node=N - M)
     _, p, z, _, _ = graph_meta("mackay")
     M, N = p.shape
     E = int((p != -1).sum())

@@ -57,6 +57,40 @@ def test_collect_split_post_flow(files):
     assert fer < 1.0                                                     # ten more iterations correct some words
 
 
+def test_evaluate_systematic_counts_information_columns_only(files, codes):
+    """systematic = 1 (main_Base.py:29, 83-86): drivers.evaluate must hand it to the decoder -- BER / FER over the first
+    N - M proto columns, as the performance header says.  Checked against a decoder built directly with systematic = 1 and
+    against the reference's own compute_results run for this configuration (mc_ref_5g_r050_z64.npz)."""
+    import ldpc_error_floor_b200 as L
+    from conftest import golden_path
+    from ldpc_error_floor_b200 import drivers, formats
+    from ldpc_error_floor_b200.montecarlo import SnrPoint, compute_results
+    root, made = files
+    key = "5g_r050_z64"
+    stem = str(codes[f"graph/{key}/stem"])
+    z, ps, pe, ss, se, _ = (int(v) for v in codes[f"graph/{key}/meta"])
+    w = formats.read_weights(made["w:5g_r050_z64_boost50"]).rows(0, 20)
+    out = {}
+    for systematic in (0, 1):
+        cfg = drivers.RunConfig(root=root, filename=stem, sharing=[2, 2, 2], sampling_type=0, systematic=systematic,
+                                z_value=z, punct_start=ps, punct_end=pe, short_start=ss, short_end=se,
+                                SNR_Matrix=np.array([1.5, 2.0]), valid_num=200000)
+        out[systematic] = drivers.evaluate(cfg, weights=w, quiet=True)["valid"]
+        assert f"systematic = {systematic}\n" in open(cfg.perf_filename).read()
+    g = L.BaseGraph(codes[f"graph/{key}/proto"].astype(np.int32), z, (ps, pe), (ss, se))
+    dec = L.NMSDecoder(g, w, iters=20, systematic=1)
+    direct, _ = compute_results(dec, 200000, None, g.sigma([1.5, 2.0]), 20, 0, seed=1074 + cfg.seed_in)
+    assert np.array_equal(out[1], direct)
+    assert (out[1][1] < out[0][1]).all()                 # parity-column errors no longer count
+    ref = np.load(golden_path("mc_ref_5g_r050_z64.npz"))
+    assert int(ref["systematic"]) == 1
+    for k in range(2):
+        pt = SnrPoint(float(ref["snr"][k]), float(ref["sigma"][k]))
+        pt.add([int(ref["frames"]), int(ref[f"uncor_last_{k}"].sum()), int(ref[f"uncor_any_{k}"].sum()), 0, 0, 0, 0, 0])
+        lo, hi = pt.fer_ci95("last")
+        assert lo <= out[1][1, k] <= hi, (k, out[1][1, k], lo, hi)
+
+
 def test_campaign_cli(files, tmp_path):
     import json
     from ldpc_error_floor_b200 import campaign

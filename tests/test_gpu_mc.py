@@ -169,10 +169,12 @@ def test_alu_peak_probe_is_plausible():
 
 
 @pytest.mark.parametrize("key,snr,systematic", [("wimax", 3.0, 0), ("wimax", 4.0, 0), ("5g_r050_z64", 2.5, 1), ("5g_r073_z72", 4.5, 1)])
-def test_two_stage_monte_carlo_equals_single_stage(key, snr, systematic, codes):
+def test_two_stage_monte_carlo_equals_single_stage(key, snr, systematic, codes, monkeypatch):
     """ldpc_mc_run_staged: stage 1 defers the frames without a zero syndrome by frame index, stage 2 regenerates and
-    decodes them in full -- the eight counters and the set of harvested words are those of the one-launch run."""
+    decodes them in full -- the eight counters and the set of harvested words are those of the one-launch run.
+    (The batch kernels' form; graphs with a persistent-slot kernel no longer need it, hence the switch.)"""
     import torch
+    monkeypatch.setenv("LDPC_B200_NO_PERSIST", "1")
     import ldpc_error_floor_b200 as L
     from ldpc_error_floor_b200 import _lib, montecarlo
     proto = codes[f"graph/{key}/proto"].astype(np.int32); meta = codes[f"graph/{key}/meta"]
@@ -199,3 +201,215 @@ def test_two_stage_monte_carlo_equals_single_stage(key, snr, systematic, codes):
     assert c[names.index("frames")] == n
     s1 = montecarlo._pick_stage1(c, 20)
     assert s1 == 0 or 3 <= s1 <= 10
+
+
+# ------------------------------------------------------------------------------------------------------------------
+# persistent-slot Monte-Carlo kernel (csrc/nms_mcp.cuh)
+def _decoder_for(codes, key, systematic, iters=20, weights=None):
+    import ldpc_error_floor_b200 as L
+    proto = codes[f"graph/{key}/proto"].astype(np.int32); meta = codes[f"graph/{key}/meta"]
+    g = L.BaseGraph(proto, int(meta[0]), (int(meta[1]), int(meta[2])), (int(meta[3]), int(meta[4])))
+    wk = {"wimax": "wimax_base20", "wifi": "wifi_boost50", "5g_r050_z64": "5g_r050_z64_boost50",
+          "5g_r073_z32": "5g_r073_z32_boost50", "5g_r033_z32": "5g_r033_z32_boost50",
+          "5g_r050_z32": "5g_r050_z32_boost50"}.get(key) if weights is None else None
+    if wk:
+        ws = L.WeightSet([int(v) for v in codes[f"weights/{wk}/sharing"]], {i: codes[f"weights/{wk}/block{i}"] for i in range(3)})
+    else:
+        ws = weights or L.WeightSet([3, 0, 0], {0: np.full((iters, 1), 0.8, np.float32)})
+    return g, ws, L.NMSDecoder(g, ws, iters=iters, systematic=systematic)
+
+
+def _sorted_rows(a):
+    return a[np.lexsort(a.T[::-1])]
+
+
+@pytest.mark.parametrize("key,snr,systematic,iters,n", [
+    ("wimax", 3.0, 0, 20, 60001), ("wimax", 5.0, 0, 20, 200003), ("wimax", 2.0, 0, 20, 7), ("wimax", 2.0, 0, 20, 1),
+    ("wimax", 3.0, 0, 5, 20011), ("wifi", 3.5, 0, 20, 50000), ("wifi", 3.5, 0, 50, 9000),
+    ("5g_r050_z64", 2.5, 1, 20, 40000), ("5g_r050_z64", 1.5, 0, 50, 6000), ("5g_r073_z72", 4.5, 1, 20, 30011),
+    ("5g_r073_z72", 3.0, 0, 20, 5000), ("5g_r073_z32", 3.0, 1, 20, 30000), ("5g_r033_z32", 0.5, 0, 20, 20000),
+    ("5g_r050_z32", 1.5, 1, 30, 20000)])
+def test_persistent_kernel_counts_like_the_batch_kernel(key, snr, systematic, iters, n, codes, monkeypatch):
+    """ldpc_mc_run with early termination: the persistent-slot kernel (slots refilled frame by frame, frames of one CTA
+    at different iterations) against the batch kernel on the same global frame indices -- the eight counters and the
+    harvested words, for every harvest criterion.  Covers shipped weights with per-iteration / per-check CN, UCN and VN
+    rows, ragged and tiny launches, frames that use up all iterations."""
+    import torch
+    from ldpc_error_floor_b200 import _lib
+    g, ws, dec = _decoder_for(codes, key, systematic, iters)
+    info = dec.mc_info()
+    assert info["persistent"] and info["kernel"].startswith("nms_mcp_spec_"), info
+    sigma = float(g.sigma([snr])[0])
+    cap = 3000
+    for harvest in (_lib.HARVEST_UNCOR_ANY, _lib.HARVEST_UNCOR_LAST, _lib.HARVEST_SYND_FAIL, _lib.HARVEST_NONE):
+        monkeypatch.setenv("LDPC_B200_NO_PERSIST", "1")
+        assert not dec.mc_info()["persistent"]
+        c1, b1, u1 = dec.mc_run(sigma, n, 21, frame_offset=777, early_term=True, harvest=harvest, capacity=cap)
+        torch.cuda.synchronize()
+        monkeypatch.delenv("LDPC_B200_NO_PERSIST")
+        c2, b2, u2 = dec.mc_run(sigma, n, 21, frame_offset=777, early_term=True, harvest=harvest, capacity=cap)
+        torch.cuda.synchronize()
+        assert torch.equal(c1, c2), (harvest, dict(zip(_lib.COUNTER_NAMES, zip(c1.tolist(), c2.tolist()))))
+        k = int(u1.item())
+        assert int(u2.item()) == k == int(c1[7].item())
+        if harvest != _lib.HARVEST_NONE and 0 < k <= cap:
+            assert np.array_equal(_sorted_rows(b1[:k].cpu().numpy()), _sorted_rows(b2[:k].cpu().numpy()))
+    assert int(c1[0].item()) == n
+    # accumulation over calls and offsets: two halves add up to the whole
+    h = n // 2
+    ca, _, _ = dec.mc_run(sigma, h, 21, frame_offset=777, early_term=True)
+    ca, _, _ = dec.mc_run(sigma, n - h, 21, frame_offset=777 + h, early_term=True, counters=ca)
+    assert torch.equal(ca, c2)
+
+
+def _oracle_counters(app, synd, target_bits, early_term):
+    """The eight Monte-Carlo counters from the oracle's per-iteration APPs [T, B, N*z] and syndromes [T, B] (True = some
+    check violated), all-zero codeword, errors counted over the first target_bits bits (calc_ber_fer, Print_Functions.py:
+    100-118, plus the termination-flag mapping of SURVEY.md 8a D9)."""
+    T, B = synd.shape
+    hard = app[:, :, :target_bits] >= 0
+    ones = hard.sum(axis=2)                                  # [T, B]
+    ok = ~synd
+    stop = np.where(ok.any(axis=0), ok.argmax(axis=0), T - 1) if early_term else np.full(B, T - 1)   # iteration whose decision is output
+    executed = np.where(ok.any(axis=0), ok.argmax(axis=0) + 1, T) if early_term else np.full(B, T)
+    idx = np.arange(B)
+    ones_out = ones[stop, idx]
+    ever = np.array([(ones[:stop[b] + 1, b] == 0).any() for b in range(B)])
+    synd_ok = ok[stop, idx]
+    return {"frames": B, "frame_err_last": int((ones_out > 0).sum()), "frame_err_any": int((~ever).sum()),
+            "bit_err_last": int(ones_out.sum()), "iters": int(executed.sum()), "synd_fail": int((~synd_ok).sum()),
+            "undetected": int((synd_ok & (ones_out > 0)).sum())}
+
+
+@pytest.mark.parametrize("key,snrs,systematic,iters,B", [("5g_r073_z72", (2.4, 2.7, 3.0, 3.5), 1, 20, 1600),
+                                                         ("5g_r050_z64", (1.0, 1.5, 2.0), 1, 20, 1200),
+                                                         ("wimax", (2.0, 2.5, 3.0, 3.5), 0, 20, 3000)])
+def test_monte_carlo_counters_against_c_oracle(key, snrs, systematic, iters, B, codes, monkeypatch):
+    """The campaign configurations end to end against oracle/nms_oracle.c: BASELINE config 5 exactly as the campaign runs it
+    (5G R0.73 n2112 z72, plain 0.8 min-sum, sharing [3, 0, 0], 20 iterations, systematic = 1), config 4 and config 1.
+    The fused Monte-Carlo launch (persistent-slot kernel AND batch kernel, with and without early termination) must report
+    the counters computed from the oracle's per-iteration APPs of the very same generated frames; the decode entry point
+    must return the oracle's APPs, flags and iteration counts on them (many CTAs, ragged tail)."""
+    import torch
+    from oracle import c_oracle
+    from ldpc_error_floor_b200 import _lib
+    g, ws, dec = _decoder_for(codes, key, systematic, iters)
+    proto = codes[f"graph/{key}/proto"].astype(np.int32)
+    tb = (g.N - g.M if systematic else g.N) * g.z
+    for k, snr in enumerate(snrs):
+        sigma, off = float(g.sigma([snr])[0]), 1000 * k + 17
+        x = dec.generate(sigma, B, seed=31, frame_offset=off)
+        ref = c_oracle.decode(proto, g.z, x.cpu().numpy(), ws.sharing, ws.blocks, iters, 2, 5, 20.0, want_all=True)
+        r = dec.decode(x, app="last")
+        assert np.array_equal(r.app.cpu().numpy(), ref["app_last"])
+        assert np.array_equal((r.flags.cpu().numpy() & 1) != 0, ~ref["synd"][iters - 1])
+        for et in (True, False):
+            want = _oracle_counters(ref["app"], ref["synd"], tb, et)
+            for persist in (True, False):
+                if persist:
+                    monkeypatch.delenv("LDPC_B200_NO_PERSIST", raising=False)
+                else:
+                    monkeypatch.setenv("LDPC_B200_NO_PERSIST", "1")
+                cnt, _ = dec.mc_run_host(sigma, B, seed=31, frame_offset=off, early_term=et)
+                got = {n: cnt[n] for n in want}
+                assert got == want, (snr, et, persist, got, want)
+        monkeypatch.delenv("LDPC_B200_NO_PERSIST", raising=False)
+        assert want["frame_err_last"] < B       # the points are not degenerate
+    # the float min-sum kernel of the same graph on the last point's frames (float z72 kernel: nms_f32_spec_5g_r073_z72)
+    import ldpc_error_floor_b200 as L
+    fdec = L.NMSDecoder(g, ws, iters=iters, decoding_type=1, systematic=systematic)
+    xf = fdec.generate(sigma, min(B, 1500), seed=32, frame_offset=5)
+    reff = c_oracle.decode(proto, g.z, xf.cpu().numpy(), ws.sharing, ws.blocks, iters, 1, 5, 20.0, want_all=False)
+    rf = fdec.decode(xf, app="last")
+    assert np.array_equal(rf.app.cpu().numpy(), reff["app_last"])
+    assert np.array_equal((rf.flags.cpu().numpy() & 1) != 0, ~reff["synd"][iters - 1])
+    e = fdec.decode(xf, early_term=True)
+    okf = ~reff["synd"]
+    assert np.array_equal(e.iters.cpu().numpy(), np.where(okf.any(axis=0), okf.argmax(axis=0) + 1, iters))
+
+
+# ------------------------------------------------------------------------------------------------------------------
+# reference-side Monte-Carlo fixtures (tests/golden/make_mc_fixtures.py): FER / BER inside the reference's 95 % interval
+REF_MC = ["wimax", "wifi", "5g_r050_z64", "5g_r073_z72", "wimax_float"]
+
+
+@pytest.mark.parametrize("name", REF_MC)
+def test_fer_ber_inside_reference_intervals(name, codes):
+    """north_star: "FER/BER at each Eb/N0 must fall inside the reference's 95 % confidence interval".  The reference side is
+    Print_Functions.compute_results run unmodified (5 000 / 2 000 / 1 000 / 300 frames per point, mc_ref_<name>.npz); ours is
+    2 M frames per point from the fused Monte-Carlo path, so its own sampling error is negligible.  FER and FER_last: Wilson
+    interval of the reference's count.  BER: frames fail in bursts, so the interval comes from the reference's per-frame bit
+    error counts (mean +- 1.96 standard errors), not from a per-bit binomial."""
+    import ldpc_error_floor_b200 as L
+    from ldpc_error_floor_b200.montecarlo import MonteCarlo, SnrPoint
+    path = golden_path(f"mc_ref_{name}.npz")
+    if not os.path.exists(path):
+        pytest.skip(f"{path} not minted")
+    d = np.load(path)
+    key, T, systematic = str(d["graph"]), int(d["T"]), int(d["systematic"])
+    sharing = [int(v) for v in d["sharing"]]
+    ws = L.WeightSet(sharing, {i: d[f"w{i}"] for i in range(3) if f"w{i}" in d})
+    proto = codes[f"graph/{key}/proto"].astype(np.int32); meta = codes[f"graph/{key}/meta"]
+    g = L.BaseGraph(proto, int(meta[0]), (int(meta[1]), int(meta[2])), (int(meta[3]), int(meta[4])))
+    dec = L.NMSDecoder(g, ws, iters=T, decoding_type=int(d["decoding_type"]), q_bit=int(d["q_bit"]), systematic=systematic)
+    mc = MonteCarlo(dec, seed=1234, chunk_frames=1 << 19)
+    nref = int(d["frames"])
+    for k, snr in enumerate(d["snr"]):
+        assert float(g.sigma([snr])[0]) == pytest.approx(float(d["sigma"][k]), rel=1e-12)
+        pt, _ = mc.run_point(float(snr), 1 << 21)                      # no early termination: FER_last needs all iterations
+        ref = SnrPoint(float(snr), float(d["sigma"][k]), bits_per_frame=g.NZ)
+        ref.add([nref, int(d[f"uncor_last_{k}"].sum()), int(d[f"uncor_any_{k}"].sum()), 0, 0, 0, 0, 0])
+        assert ref.fer == pytest.approx(float(d["results"][2, k]), abs=1e-6)        # the fixture is self-consistent
+        lo, hi = ref.fer_ci95("any")
+        assert lo <= pt.fer <= hi, (name, snr, "FER", pt.fer, lo, hi)
+        lo, hi = ref.fer_ci95("last")
+        assert lo <= pt.fer_last <= hi, (name, snr, "FER_last", pt.fer_last, lo, hi)
+        be = d[f"biterr_{k}"].astype(np.float64) / float(d["ber_divisor"])
+        assert be.mean() == pytest.approx(float(d["results"][0, k]), rel=1e-4, abs=1e-9)
+        half = 1.96 * be.std(ddof=1) / np.sqrt(nref)
+        nfail = int((be > 0).sum())
+        if nfail >= 30:
+            lo_b, hi_b = be.mean() - half, be.mean() + half
+        elif nfail > 0:
+            # a handful of failing frames: BER = FER_last x mean burst size; Wilson interval for the first factor, a factor
+            # of two either way for the second
+            burst = be[be > 0].mean()
+            wlo, whi = ref.fer_ci95("last")
+            lo_b, hi_b = 0.5 * wlo * burst, 2.0 * whi * burst
+        else:
+            continue
+        assert lo_b <= pt.ber_last <= hi_b, (name, snr, "BER", pt.ber_last, lo_b, hi_b)
+
+
+# ------------------------------------------------------------------------------------------------------------------
+# generator: the distribution the error-floor estimates rest on
+def test_generator_tails_and_ks():
+    """N(0,1) stream of the fused generator (Philox4x32-10 + Box-Muller on MUFU log2 / rsqrt / sin / cos, u1 refined with a
+    second Philox block below 2^-24): (i) Kolmogorov-Smirnov against the normal CDF on 1e7 samples, (ii) two-sided tail
+    counts beyond 3, 4, 5, 6 and 7 sigma over 1.07e11 samples against erfc within a 4-sigma Poisson band -- the reference
+    draws float64 normals from numpy (Print_Functions.py:45), so this is what "statistically equivalent" has to mean for a
+    1e-9 event."""
+    import math
+    import torch
+    from scipy import stats
+    from ldpc_error_floor_b200.decoder import normal_probe
+    _, x = normal_probe(seed=99, n_frames=10_000, quads_per_frame=250, want_normals=True)
+    x = x.cpu().numpy().astype(np.float64)
+    assert x.size == 10_000_000
+    ks = stats.kstest(x, "norm")
+    assert ks.statistic < 1.63 / math.sqrt(x.size), ks            # 1 % critical value of the KS statistic
+    assert abs(x.mean()) < 4 / math.sqrt(x.size) and abs(x.var() - 1) < 4 * math.sqrt(2 / x.size)
+    # pairs (cos, sin branch) and neighbouring samples are uncorrelated
+    assert abs(np.corrcoef(x[0::2], x[1::2])[0, 1]) < 4 / math.sqrt(x.size / 2)
+    counts = None
+    n_frames, quads = 1 << 20, 1 << 8                             # 2^28 Philox blocks = 1.07e9 samples per launch
+    for rep in range(100):
+        counts, _ = normal_probe(seed=7, n_frames=n_frames, quads_per_frame=quads, frame_offset=rep * n_frames, counts=counts)
+    c = counts.cpu().numpy()
+    total = int(c[5])
+    assert total == 100 * n_frames * quads * 4
+    for k, thr in enumerate((3.0, 4.0, 5.0, 6.0, 7.0)):
+        expect = total * math.erfc(thr / math.sqrt(2.0))
+        band = 4.0 * math.sqrt(expect) + 1.0
+        assert abs(int(c[k]) - expect) <= band + 2e-4 * expect, (thr, int(c[k]), expect)     # 2e-4: MUFU accuracy at 3-4 sigma
+    print("tail counts", dict(zip((3, 4, 5, 6, 7), c[:5].tolist())), "of", total)

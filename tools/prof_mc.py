@@ -1,6 +1,6 @@
 #!/usr/bin/env python
 """One fused Monte-Carlo launch (generate + decode + count, early termination) for ncu captures.
-usage: python tools/prof_mc.py <graph-key> <snr-dB> [frames]"""
+usage: python tools/prof_mc.py <graph-key> <snr-dB> [frames] [systematic]"""
 import os, sys
 import numpy as np, torch
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
@@ -13,7 +13,8 @@ g = L.BaseGraph(proto, int(meta[0]), (int(meta[1]), int(meta[2])), (int(meta[3])
 wk = {"wimax": "wimax_base20"}.get(key)
 ws = (L.WeightSet([int(v) for v in d[f"weights/{wk}/sharing"]], {i: d[f"weights/{wk}/block{i}"] for i in range(3)}) if wk
       else L.WeightSet([3, 0, 0], {0: np.full((20, 1), 0.8, np.float32)}))
-dec = L.NMSDecoder(g, ws, iters=20)
+dec = L.NMSDecoder(g, ws, iters=20, systematic=int(sys.argv[4]) if len(sys.argv) > 4 else 0)
+print(dec.mc_info())
 sigma = float(g.sigma([snr])[0])
 dec.mc_run(sigma, n, 3, early_term=True); torch.cuda.synchronize()
 e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
