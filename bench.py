@@ -7,9 +7,11 @@
 Workload (BASELINE.json configs[0]): WiMAX N576 R3/4 z24, quantised NMS (q_bit 5),
 20 iterations, weights C0_wman_N0576_R34_z24_Opt_Weight_End20 (sharing 3 3 3), decoding the
 Inputs/[Uncor]_wman_N0576_R34_z24_Test set.  That file is missing from the reference checkout
-(.MISSING_LARGE_BLOBS), so the set is regenerated through the same criterion: words the 20-iteration
-base decoder never corrects (Print_Functions.py:105-111, 120-126), harvested on the GPU at a recorded
-Eb/N0 and tiled to the batch size.  Worst case for throughput: no frame converges, no early stop.
+(.MISSING_LARGE_BLOBS), so the set was regenerated through the same criterion: words the 20-iteration
+base decoder never corrects (Print_Functions.py:105-111, 120-126), harvested at 3.5 dB with a recorded
+seed (tools/make_uncor_fixture.py -> tests/golden/uncor_wimax_3.5dB.q8) and tiled to the batch size.
+BOTH arms (`--impl ours`, `--impl reference`) decode this same set.  Worst case for throughput: no frame
+converges, no early stop.
 
 One "step" = one pass of the hot path over one batch of B frames per GPU (+ the 8-counter
 all-reduce when N > 1).  `value` = decoded information Gbit/s with LLRs resident in HBM;
@@ -33,6 +35,27 @@ OPS_PER_EDGE_UPDATE_FLOAT = 20   # same table, float min-sum (no quantisers)
 SM_COUNT, LANES_PER_SM = 148, 128
 HARVEST_SNR_DB = 3.5
 HARVEST_SEED = 20261018
+WORDS_FIXTURE = os.path.join("tests", "golden", "uncor_wimax_3.5dB.q8")
+WORKLOAD = ("WiMAX N576 R3/4 z24 QMS(q_bit=5) NMS 20-iter, shipped End20 weights (3 3 3), no early stop, decode of the "
+            "regenerated Inputs/[Uncor]_wman_N0576_R34_z24_Test words")
+# the reference's OWN Python (Main_Functions.build_neural_network, unmodified, on oracle/tf_shim's numpy stand-in for TensorFlow 1.x,
+# which is not installable) cannot run on the GPU box (/root/reference is absent there): measured once in the development container
+REFERENCE_PYTHON = {"frames_per_s": 7.7, "batch": 20, "where": "development container, 8 vCPU, numpy 2.3 + OpenBLAS, "
+                    "oracle/ref_runner.py (DESIGN.md section 6); batch 200: 6.6 frames/s", "static": True}
+
+
+def load_words():
+    """The shared workload of both arms: int8 words [n, N*z] in units of 0.5 (LDPCQ8 sidecar of the [Uncor] text format)."""
+    from ldpc_error_floor_b200 import formats
+    words, meta = formats.read_uncor_q8(os.path.join(ROOT, WORDS_FIXTURE))
+    return np.ascontiguousarray(words), meta
+
+
+def workload_config(n_words, frames_per_step_per_gpu, world):
+    return {"workload": WORKLOAD, "frames_per_step_per_gpu": frames_per_step_per_gpu, "uncor_words": int(n_words),
+            "words_file": WORDS_FIXTURE,
+            "harvest": {"ebn0_db": HARVEST_SNR_DB, "seed": HARVEST_SEED, "criterion": "never correct at any of 20 iterations"},
+            "l2": "inputs 2.4 GB per step > 126 MB L2", "parallelism": f"frames sharded over {world} GPU(s)"}
 
 
 def load_config():
@@ -124,14 +147,6 @@ def host_threads():
         return max(1, os.cpu_count() or 1)
 
 
-def synth_words_cpu(n, N, z, seed=1):
-    """Noisy WiMAX words at the harvest SNR for the CPU-only reference arm (no GPU needed)."""
-    rng = np.random.RandomState(seed)
-    sigma = float(np.sqrt(1.0 / (2.0 * (431.0 / 574.0) * 10 ** (HARVEST_SNR_DB / 10))))
-    x = 2.0 * (rng.normal(size=(n, N, z)) * sigma - 1.0) / sigma ** 2
-    return np.clip(np.rint(x * 2) / 2, -7.5, 7.5).astype(np.float32)
-
-
 def run_reference(args, rank, emit=print):
     if rank != 0:
         return
@@ -139,7 +154,8 @@ def run_reference(args, rank, emit=print):
     M, N = proto.shape
     E = int((proto != -1).sum())
     k_info = (N - M) * z
-    words = synth_words_cpu(512, N, z)
+    w8, _ = load_words()
+    words = (w8.astype(np.float32) * 0.5).reshape(-1, N, z)      # the same set the GPU arm decodes
     # warm-up + K timed steps, each a bounded sample sized so the whole run stays within minutes
     per_step_budget = min(15.0, 120.0 / max(1, args.steps + args.warmup))
     fps_probe, cores, n, _ = cpu_baseline(proto, z, sharing, blocks, words, budget_s=per_step_budget)
@@ -157,33 +173,39 @@ def run_reference(args, rank, emit=print):
         "impl": "reference", "metric": "decoded_info_gbit_per_s", "value": val, "unit": "Gbit/s",
         "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * dt / args.steps,
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": {"workload": "WiMAX N576 R3/4 z24 QMS(q_bit=5) NMS 20-iter, shipped End20 weights, no early stop",
-                   "frames_per_step": n},
+        "config": workload_config(w8.shape[0], args.frames, max(1, args.gpus)),
         "frames_per_s": fps, "edge_updates_per_s": fps * E * z * 20,
         "cpu_baseline": {"value": val, "unit": "Gbit/s", "cores": cores, "kind": "port",
-                         "sample": f"{n} noisy WiMAX frames at {HARVEST_SNR_DB} dB per step, oracle/nms_oracle.c "
-                                   f"(C port of the reference arithmetic, OpenMP over frames); the reference's own "
-                                   f"TensorFlow graph cannot run here (TF not installable)"},
+                         "sample": f"{n} frames per step: the workload's {w8.shape[0]} uncorrected words, tiled; "
+                                   f"oracle/nms_oracle.c (C port of the reference arithmetic, OpenMP over frames); the "
+                                   f"reference's own TensorFlow graph cannot run here (TF not installable)",
+                         "sample_frames_per_step": n},
+        "reference_python": REFERENCE_PYTHON,
         "e2e": {"value": val, "unit": "Gbit/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     }
     emit(json.dumps(line))
 
 
-def harvest_uncorrected(dec, g, sigma, want, torch):
-    """Regenerate the [Uncor] test set: words the base decoder never corrects (criterion D9)."""
-    import ldpc_error_floor_b200 as L
-    buf = cnt = ucount = None
-    offset = 0
-    chunk = 1 << 21
-    while True:
-        cnt, buf, ucount = dec.mc_run(sigma, chunk, HARVEST_SEED, frame_offset=offset, harvest=L.HARVEST_UNCOR_ANY,
-                                      capacity=want, counters=cnt, uncor_buf=buf, uncor_count=ucount)
-        offset += chunk
-        n = int(ucount.item())
-        if n >= want or offset >= (1 << 26):
-            break
-    n = min(n, want)
-    return buf[:n].clone(), cnt.cpu().numpy(), offset
+def h2d_ceiling(torch, dist, dev, world, seconds=0.4):
+    """What the box can move host -> device with every rank copying at once (pinned 256 MiB blocks, one stream per rank,
+    barrier on both sides): the roof of any end-to-end number that ships float32 words."""
+    blk = torch.empty(256 << 20, dtype=torch.uint8).pin_memory()
+    dst = torch.empty_like(blk, device=dev)
+    dst.copy_(blk, non_blocking=True)
+    torch.cuda.synchronize()
+    if world > 1:
+        dist.barrier()
+    t0 = time.perf_counter()
+    n = 0
+    while time.perf_counter() - t0 < seconds:
+        dst.copy_(blk, non_blocking=True)
+        torch.cuda.synchronize()
+        n += 1
+    dt = time.perf_counter() - t0
+    t = torch.tensor([n * blk.numel() / dt / 1e9], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(t)
+    return float(t.item())
 
 
 def _claim_stdout():
@@ -238,8 +260,9 @@ def main():
     k_info = g.k_true
     sigma = float(g.sigma([HARVEST_SNR_DB])[0])
 
-    # ---- the workload: harvested uncorrected words, tiled to B frames (2.4 GB > L2, no flush needed)
-    words, hcnt, hframes = harvest_uncorrected(dec, g, sigma, 5000, torch)
+    # ---- the workload: the regenerated [Uncor] words, tiled to B frames (2.4 GB > L2, no flush needed)
+    w8, wmeta = load_words()
+    words = (torch.from_numpy(w8).to(dev).to(torch.float32) * float(wmeta["step"])).contiguous()
     B = args.frames
     reps = (B + words.shape[0] - 1) // words.shape[0]
     llr = words.repeat(reps, 1)[:B].contiguous()
@@ -330,6 +353,21 @@ def main():
     e2e_q8_fps = world * Be * e_steps / float(ttq.item())
     q8_same = bool(np.array_equal(hq["flags"], he["flags"]) and np.array_equal(hq["hard_packed"], he["hard_packed"]))
 
+    # ---- the float32 leg again from PAGEABLE caller memory (what a numpy caller passes): the copies are
+    # staged by the driver and no longer overlap
+    page_llr = np.array(host_llr.numpy(), copy=True)
+    dec.decode_host(page_llr)
+    sync_all()
+    tp0 = time.perf_counter()
+    for _ in range(3):
+        dec.decode_host(page_llr)
+    torch.cuda.synchronize()
+    ttp = torch.tensor([time.perf_counter() - tp0], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(ttp, op=dist.ReduceOp.MAX)
+    e2e_page_fps = world * Be * 3 / float(ttp.item())
+    h2d_roof = h2d_ceiling(torch, dist, dev, world)
+
     # ---- secondary: fused Monte-Carlo (in-kernel Philox LLRs, counters only), same decoder
     mc_frames = 1 << 21
     mcnt = torch.zeros(_lib.NUM_COUNTERS, dtype=torch.int64, device=dev)
@@ -348,6 +386,35 @@ def main():
         if world > 1:
             dist.destroy_process_group()
         return
+
+    # ---- secondary (rank 0): BASELINE config 5 as the error-floor campaign runs it -- 5G NR R0.73 n2112 z72, normalised
+    # min-sum 0.8, quantised, 20 iterations, systematic, per-frame early termination, at 5.5 dB (persistent-slot kernel)
+    cfg5 = None
+    try:
+        cd = dict(np.load(os.path.join(ROOT, "tests", "golden", "codes.npz")))
+        m5 = cd["graph/5g_r073_z72/meta"]
+        g5 = L.BaseGraph(cd["graph/5g_r073_z72/proto"].astype(np.int32), int(m5[0]), (int(m5[1]), int(m5[2])), (int(m5[3]), int(m5[4])))
+        d5 = L.NMSDecoder(g5, L.WeightSet([3, 0, 0], {0: np.full((20, 1), 0.8, np.float32)}), iters=20, systematic=1, device=local_rank)
+        s5 = float(g5.sigma([5.5])[0])
+        c5 = torch.zeros(_lib.NUM_COUNTERS, dtype=torch.int64, device=dev)
+        d5.mc_run(s5, 1 << 21, 7, early_term=True, counters=c5)
+        torch.cuda.synchronize()
+        c5.zero_()
+        q0, q1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        q0.record()
+        d5.mc_run(s5, 1 << 22, 8, frame_offset=1 << 21, early_term=True, counters=c5)
+        q1.record()
+        torch.cuda.synchronize()
+        f5 = (1 << 22) / (q0.elapsed_time(q1) / 1e3)
+        c5n = c5.cpu().numpy()
+        it5 = float(c5n[4]) / float(c5n[0])
+        cfg5 = {"workload": "5G NR R0.73 n2112 z72, NMS 0.8 QMS 20-iter, systematic, early termination, Eb/N0 5.5 dB (fused "
+                            "Monte-Carlo: in-kernel Philox samples, counters only)",
+                "kernel": d5.mc_info(), "frames_per_s": f5, "avg_iterations": it5, "info_gbit_per_s": f5 * g5.k_true / 1e9,
+                "edge_updates_per_s": f5 * g5.E * g5.z * it5,
+                "note": "edge updates counted over the iterations the early-terminated frames executed"}
+    except Exception as exc:          # secondary leg: never costs the headline line
+        cfg5 = {"error": repr(exc)}
 
     # ---- secondary (rank 0): the float min-sum path (decoding_type 1, SURVEY.md 8d "and also decoding_type=1") on the
     # same words and weights -- one frame per 32-bit lane instead of two, reference-ordered float32 arithmetic
@@ -402,6 +469,7 @@ def main():
         "ncu": ncu_info,
         "ops_per_edge_update": OPS_PER_EDGE_UPDATE_QMS, "edge_updates_per_launch": eu_per_launch,
         "kernel_ms": k_ms, "traffic": traffic, "traffic_source": traffic_src,
+        "traffic_is": "committed ncu capture scaled to this launch's frames, not measured in this run",
         "hbm": {"achieved": hbm_bytes / (k_ms / 1e3) / 1e9, "peak": pk["hbm_gbs"], "unit": "GB/s",
                 "frac": hbm_bytes / (k_ms / 1e3) / 1e9 / pk["hbm_gbs"], "peak_source": pk_src,
                 "algorithmic_bytes_per_launch": hbm_bytes},
@@ -410,15 +478,16 @@ def main():
         "metric": "decoded_info_gbit_per_s", "value": fps * k_info / 1e9, "unit": "Gbit/s", "n_gpus": world,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms / args.steps, "higher_is_better": True,
         "scaling": "weak", "vs_baseline": None, "dtype": "f16x2" if dec.packed else "f32", "data": "synthetic",
-        "config": {"workload": "WiMAX N576 R3/4 z24 QMS(q_bit=5) NMS 20-iter, shipped End20 weights (3 3 3), no early "
-                               "stop, decode of regenerated [Uncor] words",
-                   "frames_per_step_per_gpu": B, "uncor_words": int(words.shape[0]),
-                   "harvest": {"ebn0_db": HARVEST_SNR_DB, "seed": HARVEST_SEED, "frames_drawn": int(hframes),
-                               "criterion": "never correct at any of 20 iterations"},
-                   "l2": "inputs 2.4 GB per step > 126 MB L2", "parallelism": f"frames sharded over {world} GPU(s)"},
+        "config": workload_config(words.shape[0], B, world),
         "frames_per_s": fps, "edge_updates_per_s": fps * E * z * T,
         "e2e": {"value": e2e_fps * k_info / 1e9, "unit": "Gbit/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
-                "frames_per_s": e2e_fps, "frames_per_step_per_gpu": Be, "api": "ldpc_decode_host (pinned host buffers)"},
+                "frames_per_s": e2e_fps, "frames_per_step_per_gpu": Be, "api": "ldpc_decode_host (pinned host buffers)",
+                "h2d_gbs": e2e_fps * NZ * 4 / 1e9,
+                "h2d_ceiling_gbs": h2d_roof,
+                "h2d_ceiling_how": f"all {world} rank(s) copying pinned 256 MiB blocks host -> device at once, same run: "
+                                   f"the roof of a float32 transport on this box"},
+        "e2e_pageable": {"value": e2e_page_fps * k_info / 1e9, "unit": "Gbit/s", "frames_per_s": e2e_page_fps,
+                         "api": "ldpc_decode_host on pageable numpy memory (driver-staged copies)"},
         "e2e_q8": {"value": e2e_q8_fps * k_info / 1e9, "unit": "Gbit/s", "h2d_bytes_per_step": Be * NZ,
                    "d2h_bytes_per_step": d2h, "frames_per_s": e2e_q8_fps, "same_results_as_f32": q8_same,
                    "api": "ldpc_decode_q8_host: the same words as int8 multiples of the quantiser step (pinned host)"},
@@ -429,7 +498,8 @@ def main():
                "frames_per_s_early_stop": mc_frames / (mc_et_ms / 1e3),
                "note": f"fused Philox generate+decode+count at {HARVEST_SNR_DB} dB (ldpc_mc_run), 20 iterations fixed / "
                        f"with per-frame early termination",
-               "fer_any": float(mcnt[2].item()) / float(mcnt[0].item())},
+               "fer_any": float(mcnt[2].item()) / float(mcnt[0].item()), "early_stop_kernel": dec.mc_info()},
+        "mc_config5": cfg5,
         "float_min_sum": {"kernel": fdec.kernel_name, "frames_per_launch": Bf, "kernel_ms": f_ms,
                           "frames_per_s": Bf / (f_ms / 1e3), "value": Bf / (f_ms / 1e3) * k_info / 1e9, "unit": "Gbit/s",
                           "edge_updates_per_s": Bf / (f_ms / 1e3) * E * z * T, "ops_per_edge_update": OPS_PER_EDGE_UPDATE_FLOAT,
@@ -440,8 +510,9 @@ def main():
                      "threads_per_cta": li["threads_per_cta"], "smem_bytes": li["smem_bytes"],
                      "early_termination_launches": dec.launch_info(early_term=True)},
     }
+    line["reference_python"] = REFERENCE_PYTHON
     if world == 1 and not args.skip_cpu:
-        wcpu = words[:512].reshape(-1, g.N, g.z).cpu().numpy()
+        wcpu = words.reshape(-1, g.N, g.z).cpu().numpy()
         cfps, cores, n, dt = cpu_baseline(proto, z, sharing, blocks, wcpu)
         line["cpu_baseline"] = {"value": cfps * k_info / 1e9, "unit": "Gbit/s", "cores": cores, "kind": "port",
                                 "frames_per_s": cfps,

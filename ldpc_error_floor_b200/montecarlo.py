@@ -44,6 +44,7 @@ class SnrPoint:
     harvested: int = 0
     bits_per_frame: int = 0
     seconds: float = 0.0
+    chunks_done: int = 0           # chunks of the point's frame index space decoded so far (resume granularity)
 
     @property
     def fer(self) -> float:        # Results[2]: never correct at any iteration (Print_Functions.py:105-111)
@@ -132,12 +133,18 @@ class MonteCarlo:
     def run_point(self, snr_db: float, n_frames: int, *, sigma: Optional[float] = None, iters: int = 0,
                   early_term: bool = False, harvest: int = _lib.HARVEST_NONE, max_uncor: int = 0,
                   min_frame_errors: Optional[int] = None, frame_base: int = 0, round_chunks: int = 4,
-                  stage1_iters: Optional[int] = None):
+                  stage1_iters: Optional[int] = None, start_chunk: int = 0, init_counters=None, init_rows=None,
+                  on_checkpoint=None, checkpoint_rounds: int = 0):
         """Decode frames [frame_base, frame_base + n_frames) of this point's global index space.
         Stops early once `min_frame_errors` frame errors (any-iteration criterion) are seen, checked once
         per round of `round_chunks` chunks per rank.  Returns (SnrPoint, harvested LLR rows [n, N*z]).
         stage1_iters: with early termination, split each launch in two (NMSDecoder.mc_run): None = decide after the
-        first chunk from its statistics (see _pick_stage1), 0 = never.  The counters do not depend on it."""
+        first chunk from its statistics (see _pick_stage1), 0 = never.  The counters do not depend on it.
+
+        Resume / checkpoint (campaign.py): the point continues at chunk `start_chunk` with the counters (`init_counters`,
+        int64[8]) and harvested rows (`init_rows`) of the chunks before it; every `checkpoint_rounds` rounds
+        `on_checkpoint(chunks_done, counters, rows)` is called on every rank with the all-reduced state of chunks
+        [0, chunks_done).  Chunks are keyed by global frame indices, so a point may be resumed with another number of ranks."""
         g = self.dec.graph
         if sigma is None:
             sigma = float(g.sigma([snr_db])[0])
@@ -146,7 +153,22 @@ class MonteCarlo:
         n_chunks = (n_frames + self.chunk - 1) // self.chunk
         counters = ubuf = ucnt = None
         stage1 = stage1_iters if early_term and _takes_stage1(self.dec) else 0
-        done_chunks = 0
+        base = np.zeros(_lib.NUM_COUNTERS, dtype=np.int64) if init_counters is None else np.asarray(init_counters, dtype=np.int64)
+        want_rows = harvest != _lib.HARVEST_NONE and max_uncor > 0
+        acc_rows = [np.asarray(init_rows, dtype=np.float32).reshape(-1, g.NZ)] if (init_rows is not None and want_rows) else []
+        sent = 0                                  # local harvested rows already gathered into acc_rows
+
+        def collect_rows():
+            nonlocal sent
+            if not want_rows:
+                return np.zeros((0, g.NZ), dtype=np.float32)
+            n = min(int(self._to_numpy(ucnt)[0]), max_uncor) if ubuf is not None else 0
+            new = self._rows(ubuf, n)[sent:] if n > sent else np.zeros((0, g.NZ), dtype=np.float32)
+            sent = max(sent, n)
+            acc_rows.append(_all_gather_rows(np.ascontiguousarray(new), self.dec.device, self.group))
+            return np.concatenate(acc_rows, axis=0)[:max_uncor]          # the cap is global, not per rank
+
+        done_chunks, rounds = int(start_chunk), 0
         while done_chunks < n_chunks:
             hi = min(n_chunks, done_chunks + round_chunks * self.world)
             for c in range(done_chunks, hi):
@@ -161,20 +183,18 @@ class MonteCarlo:
                     sigma, n, self.seed, frame_offset=frame_base + off, iters=iters, early_term=early_term,
                     harvest=harvest, capacity=max_uncor, counters=counters, uncor_buf=ubuf, uncor_count=ucnt, **extra)
             done_chunks = hi
-            if min_frame_errors is not None and done_chunks < n_chunks:
-                local = self._to_numpy(counters)
-                tot = _all_reduce_sum(local, self.dec.device, self.group)
-                if tot[_lib.COUNTER_NAMES.index("frame_err_any")] >= min_frame_errors:
+            rounds += 1
+            ckpt = on_checkpoint is not None and checkpoint_rounds > 0 and rounds % checkpoint_rounds == 0
+            if (min_frame_errors is not None or ckpt) and done_chunks < n_chunks:
+                tot = base + _all_reduce_sum(self._to_numpy(counters), self.dec.device, self.group)
+                if ckpt:
+                    on_checkpoint(done_chunks, tot, collect_rows())
+                if min_frame_errors is not None and tot[_lib.COUNTER_NAMES.index("frame_err_any")] >= min_frame_errors:
                     break
-        local = self._to_numpy(counters)
-        pt.add(_all_reduce_sum(local, self.dec.device, self.group))
-        rows = np.zeros((0, g.NZ), dtype=np.float32)
-        if harvest != _lib.HARVEST_NONE and max_uncor > 0:
-            if ubuf is not None:
-                n = min(int(self._to_numpy(ucnt)[0]), max_uncor)
-                rows = self._rows(ubuf, n)
-            rows = _all_gather_rows(rows, self.dec.device, self.group)[:max_uncor]   # the cap is global, not per rank
+        pt.add(base + _all_reduce_sum(self._to_numpy(counters), self.dec.device, self.group))
+        rows = collect_rows()
         pt.seconds = time.time() - t0
+        pt.chunks_done = done_chunks
         return pt, rows
 
     def sweep(self, snr_db_list: Sequence[float], n_frames: int, **kw) -> List[SnrPoint]:
@@ -247,7 +267,16 @@ def compute_results(decoder, sample_num, input_llr, SNR_sigma, batch_size, sampl
     n = int(math.floor(sample_num / batch_size)) * int(batch_size)
     if sampling_type == 1:
         xa = formats.uncor_to_llr(np.asarray(input_llr, dtype=np.float32)[:n], g.N, g.z)
-        r = decoder.decode_host(xa, iters=iters)
+        # stored words of a quantised decoder sit on its grid ('%.1f' of 0.5-steps, Print_Functions.py:124): ship them as
+        # int8 -- a quarter of the bytes over PCIe, same results (tests/test_gpu_parity.py::test_q8_words_...)
+        step = float(getattr(decoder, "q8_step", 0.0) or 0.0)
+        words = None
+        if step > 0 and hasattr(decoder, "decode_q8_host"):
+            try:
+                words = formats.llr_to_q8(xa.reshape(xa.shape[0], -1), step)
+            except ValueError:
+                words = None                      # off-grid rows (a float decoder's file): float32 transport
+        r = decoder.decode_q8_host(words, iters=iters) if words is not None else decoder.decode_host(xa, iters=iters)
         flags = r["flags"]
         res[0, :] = r["biterr"].sum() / max(n * g.NZ, 1)
         res[1, :] = ((flags & _lib.FLAG_UNCOR_LAST) != 0).mean() if n else 0.0

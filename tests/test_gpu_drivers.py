@@ -102,7 +102,7 @@ def test_campaign_cli(files, tmp_path):
                         "--harvest", harvest, "--max-uncor", "5000", "--post-weights", made["w:5g_r050_z64_boost50"],
                         "--json", js])
     assert rc == 0
-    recs = json.load(open(js))
+    recs = json.load(open(js))["points"]
     assert [r["snr_db"] for r in recs] == [1.5, 2.5]
     assert recs[0]["fer"] > recs[1]["fer"] > 0 and recs[0]["frames"] < 200000     # stopped on the error target
     for r in recs:
