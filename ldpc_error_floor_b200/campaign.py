@@ -239,7 +239,8 @@ def main(argv=None) -> int:
         post = NMSDecoder(g, pws, iters=args.post_iters or None, decoding_type=args.decoding_type, q_bit=args.q_bit,
                           device=local_rank, systematic=1 if args.systematic else 0)
     if rank == 0:
-        print(f"# {g.name or args.graph}: M={g.M} N={g.N} z={g.z} E={g.E} k={g.k_true} n={g.n_true}  kernel {dec.kernel_name}  "
+        mk = dec.mc_info()["kernel"] if not args.no_early_term else dec.launch_info(False)["kernel"]
+        print(f"# {g.name or args.graph}: M={g.M} N={g.N} z={g.z} E={g.E} k={g.k_true} n={g.n_true}  kernel {mk}  "
               f"{world} GPU(s)", flush=True)
     recs = run_campaign(dec, args.snr, int(args.frames), args.min_errors, early_term=not args.no_early_term,
                         seed=args.seed, chunk_frames=args.chunk, harvest=args.harvest is not None,

@@ -45,9 +45,11 @@ GEOMETRIES_F32 = {
     "5g_r033_z32": [(4, 2)], "5g_r073_z32": [(4, 2)], "mackay": [(32, 8)], "bch": [(32, 4)],
 }
 # persistent-slot Monte-Carlo kernels (nms_mcp.cuh: no float channel array, no ballots -> smaller CTAs, more of them per SM).
-# First entry = default; LDPC_B200_MCP_FP / LDPC_B200_MCP_R select another compiled one at run time.
+# First entry = default; LDPC_B200_MCP_FP / LDPC_B200_MCP_R select another compiled one at run time.  z72 on B200 at 5.5 dB
+# (profiles/r02_mc_sweep.txt): (4,2) 28.4, (2,2) 27.7, (3,2) 26.9, (4,3) 25.9 M frames/s -- 288 = 9 x 32 lanes: no padding
+# lanes, no bank conflicts at the rotation wrap.
 GEOMETRIES_MCP = {
-    "wimax": [(4, 2), (2, 2)], "wifi": [(7, 2), (3, 2)], "5g_r073_z72": [(2, 2), (3, 2), (3, 3)], "5g_r050_z64": [(2, 2), (1, 2)],
+    "wimax": [(4, 2), (2, 2)], "wifi": [(7, 2), (3, 2)], "5g_r073_z72": [(4, 2), (2, 2)], "5g_r050_z64": [(2, 2), (1, 2)],
     "5g_r050_z32": [(4, 2)], "5g_r033_z32": [(4, 2)], "5g_r073_z32": [(4, 2)],
 }
 MCP_MISC_WORDS = 112 + 32 * 8 * 2

@@ -364,7 +364,7 @@ int launch(const ldpc_decoder *d, const KParams &Pin, cudaStream_t st) {
         Q = mc ? d->base_mc : d->base_alt;
         Q.T_run = Pin.T_run; Q.early_term = Pin.early_term;
         Q.llr = Pin.llr; Q.llr_q8 = Pin.llr_q8; Q.q8_step = Pin.q8_step; Q.n_frames = Pin.n_frames;
-        Q.sigma = Pin.sigma; Q.two_over_s2 = Pin.two_over_s2; Q.two_over_s = Pin.two_over_s; Q.seed = Pin.seed; Q.frame_offset = Pin.frame_offset;
+        Q.sigma = Pin.sigma; Q.two_over_s2 = Pin.two_over_s2; Q.two_over_s = Pin.two_over_s; std::memcpy(Q.pkeys, Pin.pkeys, sizeof Q.pkeys); Q.seed = Pin.seed; Q.frame_offset = Pin.frame_offset;
         Q.app = Pin.app; Q.app_all = Pin.app_all; Q.app_stride_t = Pin.app_stride_t;
         Q.hard = Pin.hard; Q.iters = Pin.iters; Q.flags = Pin.flags; Q.biterr = Pin.biterr; Q.counters = Pin.counters;
         Q.uncor_buf = Pin.uncor_buf; Q.uncor_count = Pin.uncor_count; Q.uncor_cap = Pin.uncor_cap; Q.harvest_mode = Pin.harvest_mode;
@@ -875,6 +875,10 @@ void fill_channel(KParams &P, double sigma, uint64_t seed, uint64_t frame_offset
     P.sigma = (float)sigma;
     P.two_over_s2 = (float)(2.0 / (sigma * sigma));
     P.two_over_s = (float)(2.0 / sigma);
+    for (int r = 0; r < 10; ++r) {
+        P.pkeys[2 * r] = (uint32_t)seed + (uint32_t)r * 0x9E3779B9u;
+        P.pkeys[2 * r + 1] = (uint32_t)(seed >> 32) + (uint32_t)r * 0xBB67AE85u;
+    }
     P.seed = seed; P.frame_offset = frame_offset;
 }
 }   // namespace

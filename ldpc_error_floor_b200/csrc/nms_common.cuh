@@ -59,6 +59,7 @@ struct KParams {
     long long n_frames;
     float sigma, two_over_s2, two_over_s;   // channel: llr = (2/sigma) * n - 2/sigma^2
     unsigned long long seed, frame_offset;
+    uint32_t pkeys[20];   // the ten Philox round keys of `seed` (k0, k1 per round): constant-bank operands instead of a key schedule per block
     // two-stage Monte-Carlo (ldpc_mc_run_staged): stage 1 decodes T_run < T iterations with early termination and, instead
     // of counting a frame that has not reached a zero syndrome, appends its global frame index to defer_list; stage 2
     // regenerates exactly those frames (frame_list[k] instead of frame_offset + k: the Philox counter is the global index)
@@ -120,6 +121,20 @@ __host__ __device__ __forceinline__ void philox4x32_10(uint32_t c0, uint32_t c1,
         const uint32_t n2 = (uint32_t)(p0 >> 32) ^ c3 ^ k1;
         c1 = (uint32_t)p1; c3 = (uint32_t)p0; c0 = n0; c2 = n2;
         k0 += 0x9E3779B9u; k1 += 0xBB67AE85u;
+    }
+    out[0] = c0; out[1] = c1; out[2] = c2; out[3] = c3;
+}
+
+// same function with the round keys precomputed (KParams::pkeys)
+__device__ __forceinline__ void philox4x32_10_keyed(uint32_t c0, uint32_t c1, uint32_t c2, uint32_t c3, const uint32_t (&k)[20],
+                                                    uint32_t out[4]) {
+#pragma unroll
+    for (int r = 0; r < 10; ++r) {
+        const uint64_t p0 = (uint64_t)0xD2511F53u * c0;
+        const uint64_t p1 = (uint64_t)0xCD9E8D57u * c2;
+        const uint32_t n0 = (uint32_t)(p1 >> 32) ^ c1 ^ k[2 * r];
+        const uint32_t n2 = (uint32_t)(p0 >> 32) ^ c3 ^ k[2 * r + 1];
+        c1 = (uint32_t)p1; c3 = (uint32_t)p0; c0 = n0; c2 = n2;
     }
     out[0] = c0; out[1] = c1; out[2] = c2; out[3] = c3;
 }

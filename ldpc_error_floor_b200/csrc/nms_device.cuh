@@ -43,6 +43,10 @@ __device__ __forceinline__ float &smem_f(int w) { return reinterpret_cast<float 
 // round x half-to-even to the quantiser step (== rint(x*qk)/qk of Main_Functions.py:483-492; exact for
 // |x| < 2^21/qk): floats in [2^23/qk, 2^24/qk) are spaced exactly one step apart
 __device__ __forceinline__ float qround(float x, float magic) { return __fsub_rn(__fadd_rn(x, magic), magic); }
+// two values at once with Blackwell's packed fp32x2 adds (FADD2: one issue slot for both) -- same IEEE results
+__device__ __forceinline__ float2 qround2(float2 x, float magic) {
+    return __fadd2_rn(__fadd2_rn(x, make_float2(magic, magic)), make_float2(-magic, -magic));
+}
 __device__ __forceinline__ float qf(const KParams &P, float x) {   // full float quantiser
     return fminf(fmaxf(qround(x, P.qmagic), -P.qmax), P.qmax);
 }
@@ -100,10 +104,8 @@ static __device__ __noinline__ float gen_tail_u1(unsigned long long F, int quad,
     return ((float)r + lowbits) * 2.3283064365386963e-10f;
 }
 
-// One Philox4x32-10 block -> four N(0,1) via Box-Muller (frame F, bits 4*quad..4*quad+3)
-__device__ __forceinline__ void gen_normal4(unsigned long long seed, unsigned long long F, int quad, float n[4]) {
-    uint32_t r[4];
-    philox4x32_10((uint32_t)F, (uint32_t)(F >> 32), (uint32_t)quad, 0u, (uint32_t)seed, (uint32_t)(seed >> 32), r);
+// four Philox words -> four N(0,1) via Box-Muller
+__device__ __forceinline__ void box_muller4(const uint32_t (&r)[4], unsigned long long seed, unsigned long long F, int quad, float n[4]) {
 #pragma unroll
     for (int h = 0; h < 2; ++h) {
         float u1 = fmaf((float)r[2 * h], 2.3283064365386963e-10f, 1.1641532182693481e-10f);   // (r+0.5)/2^32
@@ -120,6 +122,19 @@ __device__ __forceinline__ void gen_normal4(unsigned long long seed, unsigned lo
     }
 }
 
+// One Philox4x32-10 block -> four N(0,1) (frame F, bits 4*quad..4*quad+3)
+__device__ __forceinline__ void gen_normal4(unsigned long long seed, unsigned long long F, int quad, float n[4]) {
+    uint32_t r[4];
+    philox4x32_10((uint32_t)F, (uint32_t)(F >> 32), (uint32_t)quad, 0u, (uint32_t)seed, (uint32_t)(seed >> 32), r);
+    box_muller4(r, seed, F, quad, n);
+}
+// the same block with the round keys taken from the kernel parameters
+__device__ __forceinline__ void gen_normal4(const KParams &P, unsigned long long F, int quad, float n[4]) {
+    uint32_t r[4];
+    philox4x32_10_keyed((uint32_t)F, (uint32_t)(F >> 32), (uint32_t)quad, 0u, P.pkeys, r);
+    box_muller4(r, P.seed, F, quad, n);
+}
+
 // N(0,1) sample -> channel LLR of a zero bit.  Print_Functions.py:45-50: x = n*sigma - 1 (all-zero word), llr = 2x/sigma^2
 // (float64 there), quantised on the QMS path.  Here llr = fma(n, 2/sigma, -2/sigma^2): one rounding.
 __device__ __forceinline__ float llr_from_normal(const KParams &P, float n) {
@@ -130,7 +145,7 @@ __device__ __forceinline__ float llr_from_normal(const KParams &P, float n) {
 // One Philox block -> four channel LLRs (bits 4*quad .. 4*quad+3 of frame F), punctured and shortened (:53-60)
 __device__ __forceinline__ void gen_llr4(const KParams &P, unsigned long long F, int quad, float out[4]) {
     float n[4];
-    gen_normal4(P.seed, F, quad, n);
+    gen_normal4(P, F, quad, n);
 #pragma unroll
     for (int k4 = 0; k4 < 4; ++k4) {
         const int k = 4 * quad + k4 + 1;   // 1-based bit index

@@ -92,7 +92,8 @@ __device__ __forceinline__ uint32_t h2_rot(const H2Ctx &h, uint32_t rot4, uint32
 // Q() of two float32 values -> half2 (round to step in fp32, saturate after packing; +-inf saturate too)
 __device__ __forceinline__ __half2 q2(const KParams &P, float lo, float hi) {
     const __half2 qm = __float2half2_rn(P.qmax);
-    const __half2 r = __floats2half2_rn(qround(lo, P.qmagic), qround(hi, P.qmagic));
+    const float2 q = qround2(make_float2(lo, hi), P.qmagic);
+    const __half2 r = __floats2half2_rn(q.x, q.y);
     return __hmax2(__hmin2(r, qm), __hneg2(qm));
 }
 
@@ -108,10 +109,11 @@ __device__ __forceinline__ void h2_row_mags(const KParams &P, float w0lo, float 
     const float wlo = (par & 1u) ? w1lo : w0lo;     // unsatisfied check -> UCN weight (:275,:285,:295)
     const float whi = (par & 0x10000u) ? w1hi : w0hi;
     // Q(relu(min * w)) (:308-311)
-    __half2 magA = __floats2half2_rn(qround(__fmul_rn(__low2float(m1c), wlo), P.qmagic),
-                                     qround(__fmul_rn(__high2float(m1c), whi), P.qmagic));
-    __half2 magB = __floats2half2_rn(qround(__fmul_rn(__low2float(m2c), wlo), P.qmagic),
-                                     qround(__fmul_rn(__high2float(m2c), whi), P.qmagic));
+    const float2 w2 = make_float2(wlo, whi);
+    const float2 qa = qround2(__fmul2_rn(__half22float2(m1c), w2), P.qmagic);
+    const float2 qb = qround2(__fmul2_rn(__half22float2(m2c), w2), P.qmagic);
+    __half2 magA = __floats2half2_rn(qa.x, qa.y);
+    __half2 magB = __floats2half2_rn(qb.x, qb.y);
     magA = __hmax2(__hmin2(magA, qm), zero);
     magB = __hmax2(__hmin2(magB, qm), zero);
     // C->V is negative iff (dc + #negative others) is odd (:251-254; a zero V->C counts as positive, :230)

@@ -59,41 +59,44 @@ struct McpKernel {
     // channel values of the frames entering the slots in `fresh` (rank r in the mask -> global frame first + r), written
     // as halves into the xq array; same samples, same order as gen_llr4 draws them for everyone else
     static __device__ __forceinline__ void generate(const KParams &P, uint32_t sb, uint32_t fresh, unsigned long long first) {
-        const int total = __popc(fresh) * NQUADS;
         const unsigned short hneg = __half_as_ushort(__float2half_rn(-P.qmax));   // a shortened bit: Q(-clip_LLR) to the decoder
-        for (int it = threadIdx.x; it < total; it += NTHR) {
-            const int r = it / NQUADS, quad = it - r * NQUADS;
-            uint32_t m = fresh;
-            for (int i = 0; i < r; ++i) m &= m - 1u;
-            const int f = __ffs(m) - 1;                                            // the r-th lowest refilled slot
-            const int k0 = 4 * quad, j0 = k0 / G::z, a0 = k0 - j0 * G::z;
+        unsigned long long F = P.frame_offset + first;
+        for (uint32_t m = fresh; m != 0u; m &= m - 1u, ++F) {                      // uniform: one refilled slot after the other
+            const int f = __ffs(m) - 1;
             const uint32_t base = sb + (uint32_t)P.off_xq * 4u + (uint32_t)(f >> 1) * 4u + (uint32_t)(f & 1) * 2u;
-            if constexpr (G::z % 4 == 0) {
-                // the four bits of a quad sit in one column at consecutive circulant lanes: one address, immediate offsets
-                const uint32_t ad = base + (uint32_t)(j0 * G::LP + a0 * G::Fp) * 4u;
-                const int k1 = k0 + 1;                                             // 1-based index of the quad's first bit
-                const bool allp = P.punct_s > 0 && k1 >= P.punct_s && k1 + 3 <= P.punct_e;
-                const bool alls = P.short_s > 0 && k1 >= P.short_s && k1 + 3 <= P.short_e;
-                if (allp || alls) {                                                // no sample needed: the value is fixed
-                    const unsigned short c = alls ? hneg : (unsigned short)0;
+            for (int quad = threadIdx.x; quad < NQUADS; quad += NTHR) {
+                const int k1 = 4 * quad + 1;                                       // 1-based index of the quad's first bit
+                if constexpr (G::z % 4 == 0) {
+                    // the four bits of a quad sit in one column at consecutive circulant lanes: one address, immediate offsets
+                    constexpr int QPC = G::z / 4;
+                    const int j0 = quad / QPC, a0 = (quad - j0 * QPC) * 4;
+                    const uint32_t ad = base + (uint32_t)(j0 * G::LP + a0 * G::Fp) * 4u;
+                    const bool inp = P.punct_s > 0 && k1 + 3 >= P.punct_s && k1 <= P.punct_e;   // touches the punctured range
+                    const bool ins = P.short_s > 0 && k1 + 3 >= P.short_s && k1 <= P.short_e;   // ... the shortened range
+                    if (!(inp || ins)) {                                           // the common case: four plain samples
+                        float n[4];
+                        gen_normal4(P, F, quad, n);
+                        const __half2 lo = __floats2half2_rn(llr_from_normal(P, n[0]), llr_from_normal(P, n[1]));
+                        const __half2 hi = __floats2half2_rn(llr_from_normal(P, n[2]), llr_from_normal(P, n[3]));
+                        sts16(ad, (unsigned short)(h2u(lo) & 0xffffu));
+                        sts16(ad + (uint32_t)G::Fp * 4u, (unsigned short)(h2u(lo) >> 16));
+                        sts16(ad + (uint32_t)G::Fp * 8u, (unsigned short)(h2u(hi) & 0xffffu));
+                        sts16(ad + (uint32_t)G::Fp * 12u, (unsigned short)(h2u(hi) >> 16));
+                        continue;
+                    }
+                    const bool allp = P.punct_s > 0 && k1 >= P.punct_s && k1 + 3 <= P.punct_e;
+                    const bool alls = P.short_s > 0 && k1 >= P.short_s && k1 + 3 <= P.short_e;
+                    if (allp || alls) {                                            // no sample needed: the value is fixed
+                        const unsigned short c = alls ? hneg : (unsigned short)0;
 #pragma unroll
-                    for (int k4 = 0; k4 < 4; ++k4) sts16(ad + (uint32_t)(k4 * G::Fp) * 4u, c);
-                    continue;
+                        for (int k4 = 0; k4 < 4; ++k4) sts16(ad + (uint32_t)(k4 * G::Fp) * 4u, c);
+                        continue;
+                    }
                 }
-                float n[4];
-                gen_normal4(P.seed, P.frame_offset + first + (unsigned long long)r, quad, n);
-#pragma unroll
-                for (int k4 = 0; k4 < 4; ++k4) {
-                    const int k = k1 + k4;
-                    unsigned short v = __half_as_ushort(__float2half_rn(llr_from_normal(P, n[k4])));
-                    if (P.punct_s > 0 && k >= P.punct_s && k <= P.punct_e) v = 0;
-                    if (P.short_s > 0 && k >= P.short_s && k <= P.short_e) v = hneg;
-                    sts16(ad + (uint32_t)(k4 * G::Fp) * 4u, v);
-                }
-            } else {
+                // a quad that straddles a range boundary or a column boundary: the general code
                 float v[4];
-                gen_llr4(P, P.frame_offset + first + (unsigned long long)r, quad, v);
-                int k = k0, j = j0, a = a0;
+                gen_llr4(P, F, quad, v);
+                int k = k1 - 1, j = k / G::z, a = k - j * G::z;
 #pragma unroll
                 for (int k4 = 0; k4 < 4; ++k4, ++k) {
                     const float x = fminf(fmaxf(v[k4], -P.qmax), P.qmax);          // shortened: -clip_LLR -> -qmax
