@@ -131,6 +131,15 @@ int ldpc_decoder_geometry(const ldpc_decoder_t *d, int32_t *frames_per_cta, int3
 int ldpc_decoder_launch_info(const ldpc_decoder_t *d, int32_t early_term, int32_t *frames_per_cta, int32_t *ctas_per_sm,
                              int32_t *threads_per_cta, int32_t *smem_bytes, char *kernel_name, int32_t name_cap);
 
+/* ---- run-time graph specialisation ------------------------------------------------------
+ * Main_Functions.init_connecting_matrix (:46-150) accepts any proto matrix at run time.  Base graphs the build knows
+ * have unrolled kernels compiled in; for any other graph ldpc_decoder_create generates the same kernel source for it,
+ * compiles it with NVRTC (sm_100a) and keeps the cubin in an on-disk cache (<library dir>/jit_cache, or
+ * $LDPC_B200_JIT_CACHE), so user graphs get the fast path too -- bit-identical to the table-driven generic kernels,
+ * which stay the fallback (LDPC_B200_NO_JIT=1, or no libnvrtc).  ldpc_jit_prebuild fills the cache ahead of time and
+ * needs no GPU; returns the number of kernels cached (>= 0) or an error code. */
+int ldpc_jit_prebuild(const int32_t *proto, int32_t M, int32_t N, int32_t z);
+
 /* ---- decode --------------------------------------------------------------------------
  * Replaces sess.run(ya_output_all / ya_output{t}) (Print_Functions.py:148-151, main_Base.py:160).
  *   llr_dev      f32 [B, N*z]  channel LLRs log(p1/p0), bit index j*z+c (== xa[B,N,z] flattened)
@@ -144,7 +153,8 @@ int ldpc_decoder_launch_info(const ldpc_decoder_t *d, int32_t early_term, int32_
  *   iters_dev    i32 [B]  iterations until the first zero syndrome (also reported when
  *                early_term == 0), or `iters` if none
  *   flags_dev    u8  [B]  LDPC_FLAG_*
- *   biterr_dev   i32 [B]  ones in the output hard decision (bit errors vs the all-zero word)
+ *   biterr_dev   i32 [B]  ones in the output hard decision (bit errors vs the all-zero word; other codewords:
+ *                ldpc_decode_cw)
  * Any output pointer may be NULL. */
 int ldpc_decode(const ldpc_decoder_t *d, const float *llr_dev, int64_t B, int32_t iters,
                 int32_t early_term, float *app_dev, int32_t app_all_iters, uint32_t *hard_dev,
@@ -156,6 +166,26 @@ int ldpc_decode_host(const ldpc_decoder_t *d, const float *llr_host, int64_t B, 
                      int32_t early_term, float *app_host, int32_t app_all_iters,
                      uint32_t *hard_host, int32_t *iters_host, uint8_t *flags_host,
                      int32_t *biterr_host);
+
+/* ---- non-zero codewords ("next" row N3 of SURVEY.md 8f) ----------------------------------------
+ * The reference can train / evaluate on random codewords Y = infoWord . code_GM mod 2 (Print_Functions.py:40-46 with
+ * is_zeros_word = False; main_Base.py hard-codes the all-zero word) and counts errors against Y (:100-118).
+ * codeword_bits_dev: packed bits, bit k of a frame at word k / 32, bit k % 32; cw_stride_words = words between the
+ * codewords of consecutive frames (ceil(N*z/32) for one word per frame, 0 = every frame carries the same codeword).
+ *
+ * ldpc_llr_generate_cw: the samples of ldpc_llr_generate (same Philox stream) around +-1 per bit:
+ *   llr = 2 (sigma n + (2 y - 1)) / sigma^2, then quantise / puncture / shorten as there.
+ * ldpc_decode_cw: ldpc_decode with the error metrics taken against the codeword -- flags UNCOR_ANY / UNCOR_LAST,
+ *   biterr_dev (Hamming distance of the output decision), biterr_signed_dev (sum over bits of decision - y: what
+ *   calc_ber_fer sums, :112-113 -- its BER lets 0->1 and 1->0 errors cancel) and counters_dev as in ldpc_mc_run
+ *   (accumulated).  Implemented as the decode kernel writing the per-iteration APPs of a chunk of frames plus a
+ *   metrics kernel over them (the reference's own order of work, Print_Functions.py:148-154); any output may be NULL. */
+int ldpc_llr_generate_cw(const ldpc_decoder_t *d, double sigma, int64_t n_frames, uint64_t seed, uint64_t frame_offset,
+                         const uint32_t *codeword_bits_dev, int64_t cw_stride_words, float *llr_dev, void *stream);
+int ldpc_decode_cw(const ldpc_decoder_t *d, const float *llr_dev, const uint32_t *codeword_bits_dev,
+                   int64_t cw_stride_words, int64_t B, int32_t iters, int32_t early_term, uint32_t *hard_dev,
+                   int32_t *iters_dev, uint8_t *flags_dev, int32_t *biterr_dev, int32_t *biterr_signed_dev,
+                   uint64_t *counters_dev, void *stream);
 
 /* ---- compact (int8) words ---------------------------------------------------------------
  * On the quantised path every decoder input of Print_Functions.create_mix_epoch (:49-50) and every

@@ -13,7 +13,7 @@ def __getattr__(name):
     if name in ("NMSDecoder", "DecodeResult", "check_params", "unpack_bits"):
         from . import decoder
         return getattr(decoder, name)
-    if name in ("MonteCarlo", "compute_results", "SnrPoint"):
+    if name in ("MonteCarlo", "compute_results", "create_mix_epoch", "SnrPoint"):
         from . import montecarlo
         return getattr(montecarlo, name)
     raise AttributeError(name)

@@ -62,6 +62,8 @@ SYMBOLS = {
                                             ctypes.POINTER(_I32), ctypes.POINTER(_I32), ctypes.c_char_p, _I32]),
     "ldpc_decode": (ctypes.c_int, [_P, _P, _I64, _I32, _I32, _P, _I32, _P, _P, _P, _P, _P]),
     "ldpc_decode_host": (ctypes.c_int, [_P, _P, _I64, _I32, _I32, _P, _I32, _P, _P, _P, _P]),
+    "ldpc_llr_generate_cw": (ctypes.c_int, [_P, ctypes.c_double, _I64, _U64, _U64, _P, _I64, _P, _P]),
+    "ldpc_decode_cw": (ctypes.c_int, [_P, _P, _P, _I64, _I64, _I32, _I32, _P, _P, _P, _P, _P, _P, _P]),
     "ldpc_decoder_q8_step": (ctypes.c_float, [_P]),
     "ldpc_decode_q8": (ctypes.c_int, [_P, _P, ctypes.c_float, _I64, _I32, _I32, _P, _P, _P, _P, _P, _P]),
     "ldpc_decode_q8_host": (ctypes.c_int, [_P, _P, ctypes.c_float, _I64, _I32, _I32, _P, _P, _P, _P]),
@@ -75,6 +77,7 @@ SYMBOLS = {
     "ldpc_decoder_set_weights": (ctypes.c_int, [_P, _P, _P, _P]),
     "ldpc_train_grad": (ctypes.c_int, [_P, _P, _I64, _I32, _I32, _I32, ctypes.c_double, ctypes.POINTER(ctypes.c_double),
                                        _P, _P, _P, _P]),
+    "ldpc_jit_prebuild": (ctypes.c_int, [_P, _I32, _I32, _I32]),
     "ldpc_alu_peak_probe": (ctypes.c_int, [_I32, _I32, ctypes.POINTER(ctypes.c_double)]),
     "ldpc_launch_count": (ctypes.c_uint64, []),
 }
@@ -113,6 +116,16 @@ def check(rc: int) -> None:
 
 
 ALU_PROBE_KINDS = {"ffma": 0, "fmnmx": 1, "lop3": 2, "iadd": 3, "hfma2": 4, "hmnmx2": 5, "fadd": 6}
+
+
+def jit_prebuild(proto, z: int) -> int:
+    """Compile the run-time specialised kernels of a base graph into the on-disk cache (no GPU needed)."""
+    import numpy as np
+    p = np.ascontiguousarray(proto, dtype=np.int32)
+    rc = load().ldpc_jit_prebuild(p.ctypes.data, p.shape[0], p.shape[1], int(z))
+    if rc < 0:
+        check(rc)
+    return rc
 
 
 def alu_peak_probe(device: int = 0, kinds=("ffma", "fmnmx", "lop3", "hfma2", "hmnmx2")) -> dict:

@@ -7,6 +7,7 @@
 #include "../../include/ldpc_b200.h"
 #include "nms_common.cuh"
 #include "nms_train.cuh"
+#include "nms_jit.h"
 
 #include <algorithm>
 #include <cmath>
@@ -119,9 +120,15 @@ struct ldpc_decoder {
     // persistent-slot Monte-Carlo kernel (nms_mcp.cuh) of the same graph: serves ldpc_mc_run with early termination
     const void *func_mc = nullptr;
     const char *mc_name = nullptr;
+    // run-time specialised kernels (nms_jit.cu) are driver-API functions: launched / queried through nms_jit_*
+    bool func_cu = false, func_mc_cu = false;
+    char jit_name[48] = {0}, jit_mc_name[48] = {0};
     LaunchGeom geom_mc{};
     KParams base_mc{};
     float *d_w = nullptr;
+    // ldpc_decode_cw: per-iteration APPs of one chunk of frames + their flags / iteration counts
+    float *d_cw_app = nullptr; size_t cw_app_cap = 0;
+    int *d_cw_iters = nullptr; uint8_t *d_cw_flags = nullptr; size_t cw_frames_cap = 0;
     // training step (nms_train.cu): the weights as given ([T*wc | T*wu | T*wv], no "effective" rows), graph tables,
     // per-call workspace -- all created on first use
     int wc_raw = 0, wu_raw = 0, wv_raw = 0;
@@ -378,6 +385,12 @@ int launch(const ldpc_decoder *d, const KParams &Pin, cudaStream_t st) {
     const int grid = (int)std::min<long long>(nb, (long long)d->sm_count * geo.ctas_per_sm);
     void *args[] = {(void *)&P};
     const void *func = mc ? d->func_mc : (alt ? d->func_alt : d->func);
+    if (mc ? d->func_mc_cu : (!alt && d->func_cu)) {
+        if (nms_jit_launch(const_cast<void *>(func), grid, geo.threads, geo.smem_bytes, st, &P) != 0)
+            return fail(LDPC_E_CUDA, "launch of the run-time specialised kernel failed");
+        nms_note_launch();
+        return LDPC_OK;
+    }
     CUDA_TRY(cudaLaunchKernel(func, dim3(grid), dim3(geo.threads), args, (size_t)geo.smem_bytes, st));
     nms_note_launch();
     return LDPC_OK;
@@ -521,6 +534,50 @@ extern "C" int ldpc_decoder_create2(const ldpc_graph_t *g, const int32_t sharing
             d->func_mc = f; d->geom_mc = geo; d->mc_name = tab[k].name;
         }
     }
+    // a graph the build does not know: specialise it now (NVRTC, cached on disk) -- packed decode kernel and, for lifted
+    // graphs, the persistent-slot Monte-Carlo kernel.  Any failure leaves the generic degree-bucketed kernels in charge.
+    bool no_empty_node = true;       // the unrolled code has no body for a node without edges
+    for (int i = 0; i < g->M; ++i) no_empty_node = no_empty_node && g->row_ptr[i + 1] > g->row_ptr[i];
+    for (int j = 0; j < g->N; ++j) no_empty_node = no_empty_node && g->col_ptr[j + 1] > g->col_ptr[j];
+    if (d->packed && d->func == nullptr && !env_on("LDPC_B200_NO_SPEC") && !env_on("LDPC_B200_NO_JIT") && g->info.max_dc <= 64 &&
+        no_empty_node && nms_jit_available()) {
+        char err[512] = {0};
+        const unsigned long long h = graph_hash(d->g);
+        for (int kind = NMS_JIT_DECODE; kind <= NMS_JIT_MCP; ++kind) {
+            if (kind == NMS_JIT_MCP && (g->z < 2 || g->N * g->z >= 65536 || env_on("LDPC_B200_NO_JIT_MCP"))) continue;
+            int Fp = 0, R = 0;
+            nms_jit_pick_geometry(g->M, g->N, g->E, g->z, kind, g->info.max_dc, &Fp, &R);
+            const char *efp = getenv(kind == NMS_JIT_MCP ? "LDPC_B200_MCP_FP" : "LDPC_B200_FP");
+            const char *er = getenv(kind == NMS_JIT_MCP ? "LDPC_B200_MCP_R" : "LDPC_B200_R");
+            if (efp && atoi(efp) > 0) Fp = atoi(efp);
+            if (er && atoi(er) > 0) R = atoi(er);
+            LaunchGeom geo{};
+            geo.Fp = Fp; geo.FB = 2 * Fp; geo.L = g->z * Fp; geo.LP = (geo.L + 31) & ~31; geo.C = geo.LP / 32; geo.R = R;
+            geo.threads = geo.C * R * 32;
+            if (geo.C > 16 || geo.threads > 1024 || geo.FB > LDPC_MAX_FB || (kind == NMS_JIT_MCP && geo.FB > 32)) continue;
+            KParams tmp{};
+            tmp.E = g->E; tmp.N = g->N; tmp.L = geo.L; tmp.LP = geo.LP; tmp.C = geo.C; tmp.qms = 1; tmp.no_xq = no_xq;
+            tmp.w_words = w_words; tmp.w_staged = w_words > 0 && w_words <= NMS_WSTAGE_MAX_WORDS;
+            if (kind == NMS_JIT_MCP) fill_smem_layout_mc(&tmp); else fill_smem_layout(&tmp, true, false);
+            geo.smem_bytes = tmp.smem_words * 4;
+            if (geo.smem_bytes > 227 * 1024) continue;
+            void *fn = nullptr;
+            if (nms_jit_build(d->g.proto.data(), g->M, g->N, g->z, Fp, R, kind, &fn, err, (int)sizeof err) != 0 ||
+                nms_jit_set_smem(fn, geo.smem_bytes) != 0 ||
+                nms_jit_occupancy(fn, geo.threads, geo.smem_bytes, &geo.ctas_per_sm) != 0 || geo.ctas_per_sm < 1) {
+                if (env_on("LDPC_B200_JIT_VERBOSE")) fprintf(stderr, "ldpc_b200: run-time specialisation failed: %s\n", err);
+                cudaGetLastError();
+                continue;
+            }
+            if (kind == NMS_JIT_DECODE) {
+                snprintf(d->jit_name, sizeof d->jit_name, "jit%016llx_fp%d_r%d", h, Fp, R);
+                d->func = fn; d->func_cu = true; d->geom = geo; d->spec_name = d->jit_name; rc = LDPC_OK;
+            } else if (d->func_cu) {
+                snprintf(d->jit_mc_name, sizeof d->jit_mc_name, "jit%016llx_fp%d_r%d", h, Fp, R);
+                d->func_mc = fn; d->func_mc_cu = true; d->geom_mc = geo; d->mc_name = d->jit_mc_name;
+            }
+        }
+    }
     // graph-specialised float32 kernel (float / quantised twin); it reads its weights from shared memory
     if (!d->packed && w_words <= NMS_WSTAGE_MAX_WORDS && !env_on("LDPC_B200_NO_SPEC")) {
         int n = 0;
@@ -644,6 +701,7 @@ extern "C" int ldpc_decoder_destroy(ldpc_decoder_t *d) {
     {
         DeviceGuard guard(d->device);
         free_scratch(d->hs);
+        cudaFree(d->d_cw_app); cudaFree(d->d_cw_iters); cudaFree(d->d_cw_flags);
         cudaFree(d->d_w); cudaFree(d->d_w_raw); cudaFree(d->d_tab); cudaFree(d->d_hist); cudaFree(d->d_coef);
         cudaFree(d->d_grad); cudaFree(d->d_loss);
     }
@@ -740,6 +798,68 @@ extern "C" int ldpc_decode(const ldpc_decoder_t *d, const float *llr_dev, int64_
     if (!llr_dev && B > 0) return fail(LDPC_E_INVALID, "decode: bad arguments");
     return decode_dev(d, llr_dev, nullptr, 0.0f, B, iters, early_term, app_dev, app_all_iters, hard_dev, iters_dev,
                       flags_dev, biterr_dev, nullptr, stream);
+}
+
+namespace { void fill_channel(KParams &P, double sigma, uint64_t seed, uint64_t frame_offset); }
+
+// ---- non-zero codewords ("next" row N3: Print_Functions.py:40-46, 100-118 with Y != 0)
+extern "C" int ldpc_llr_generate_cw(const ldpc_decoder_t *d, double sigma, int64_t n_frames, uint64_t seed, uint64_t frame_offset,
+                                    const uint32_t *codeword_bits_dev, int64_t cw_stride_words, float *llr_dev, void *stream) {
+    if (!d || !llr_dev || !codeword_bits_dev || n_frames < 0 || cw_stride_words < 0 || !(sigma > 0.0))
+        return fail(LDPC_E_INVALID, "llr_generate_cw: bad arguments");
+    if (n_frames == 0) return LDPC_OK;
+    DeviceGuard guard(d->device);
+    if (!guard.ok) return fail(LDPC_E_CUDA, "cudaSetDevice(%d) failed", d->device);
+    KParams P = d->base;
+    fill_channel(P, sigma, seed, frame_offset);
+    CUDA_TRY(nms_launch_generate_cw(P, codeword_bits_dev, cw_stride_words, llr_dev, n_frames, (cudaStream_t)stream));
+    return LDPC_OK;
+}
+
+extern "C" int ldpc_decode_cw(const ldpc_decoder_t *dc, const float *llr_dev, const uint32_t *codeword_bits_dev,
+                              int64_t cw_stride_words, int64_t B, int32_t iters, int32_t early_term, uint32_t *hard_dev,
+                              int32_t *iters_dev, uint8_t *flags_dev, int32_t *biterr_dev, int32_t *biterr_signed_dev,
+                              uint64_t *counters_dev, void *stream) {
+    ldpc_decoder *d = const_cast<ldpc_decoder *>(dc);
+    if (!d || (!llr_dev && B > 0) || !codeword_bits_dev || B < 0 || cw_stride_words < 0)
+        return fail(LDPC_E_INVALID, "decode_cw: bad arguments");
+    if (iters < 0 || iters > d->T) return fail(LDPC_E_INVALID, "decode_cw: iters %d outside 0..%d", iters, d->T);
+    if (B == 0) return LDPC_OK;
+    DeviceGuard guard(d->device);
+    if (!guard.ok) return fail(LDPC_E_CUDA, "cudaSetDevice(%d) failed", d->device);
+    std::lock_guard<std::mutex> lock(d->mu);
+    const KParams &P0 = d->base;
+    const int T_run = iters == 0 ? d->T : iters;
+    cudaStream_t st = (cudaStream_t)stream;
+    // chunks of frames whose [T_run, chunk, N*z] APP tensor stays below 1 GiB
+    const size_t per_frame = (size_t)T_run * P0.NZ * sizeof(float);
+    const int64_t chunk = std::max<int64_t>(1, std::min<int64_t>(B, (int64_t)((1ull << 30) / per_frame)));
+    if (d->cw_app_cap < (size_t)chunk * per_frame) {
+        CUDA_TRY(cudaStreamSynchronize(st));
+        cudaFree(d->d_cw_app); d->d_cw_app = nullptr; d->cw_app_cap = 0;
+        CUDA_TRY(cudaMalloc(&d->d_cw_app, (size_t)chunk * per_frame));
+        d->cw_app_cap = (size_t)chunk * per_frame;
+    }
+    if (d->cw_frames_cap < (size_t)chunk) {
+        CUDA_TRY(cudaStreamSynchronize(st));
+        cudaFree(d->d_cw_iters); cudaFree(d->d_cw_flags); d->d_cw_iters = nullptr; d->d_cw_flags = nullptr; d->cw_frames_cap = 0;
+        CUDA_TRY(cudaMalloc(&d->d_cw_iters, (size_t)chunk * sizeof(int)));
+        CUDA_TRY(cudaMalloc(&d->d_cw_flags, (size_t)chunk));
+        d->cw_frames_cap = (size_t)chunk;
+    }
+    for (int64_t off = 0; off < B; off += chunk) {
+        const int64_t nb = std::min<int64_t>(chunk, B - off);
+        int32_t *it = iters_dev ? iters_dev + off : d->d_cw_iters;
+        uint8_t *fl = flags_dev ? flags_dev + off : d->d_cw_flags;
+        int rc = decode_dev(d, llr_dev + off * P0.NZ, nullptr, 0.0f, nb, iters, early_term, d->d_cw_app, 1,
+                            hard_dev ? hard_dev + off * P0.HW : nullptr, it, fl, nullptr, nullptr, st);
+        if (rc != LDPC_OK) return rc;
+        CUDA_TRY(nms_launch_cw_metrics(d->d_cw_app, nb, T_run, P0.NZ, P0.target_n * P0.z,
+                                       codeword_bits_dev + off * cw_stride_words, cw_stride_words, it, early_term ? 1 : 0, fl,
+                                       biterr_dev ? biterr_dev + off : nullptr, biterr_signed_dev ? biterr_signed_dev + off : nullptr,
+                                       (unsigned long long *)counters_dev, st));
+    }
+    return LDPC_OK;
 }
 
 extern "C" float ldpc_decoder_q8_step(const ldpc_decoder_t *d) { return d ? quantiser_step(d) : 0.0f; }
@@ -1118,6 +1238,36 @@ extern "C" int ldpc_train_grad(const ldpc_decoder_t *dc, const float *llr_dev, i
     if (g_ucn_host && P.wu) std::memcpy(g_ucn_host, gh.data() + Tw * P.wc, Tw * P.wu * sizeof(float));
     if (g_vn_host && P.wv) std::memcpy(g_vn_host, gh.data() + Tw * (P.wc + P.wu), Tw * P.wv * sizeof(float));
     return LDPC_OK;
+}
+
+// Run-time specialisation without a device: make sure the cubins a decoder for this graph would ask for are in the on-disk
+// cache (NVRTC cross-compiles for sm_100a).  Returns the number of kernels now cached, or a negative error code.
+extern "C" int ldpc_jit_prebuild(const int32_t *proto, int32_t M, int32_t N, int32_t z) {
+    if (!proto || M <= 0 || N <= 0 || z <= 0) return fail(LDPC_E_INVALID, "jit_prebuild: bad arguments");
+    if (!nms_jit_available()) return fail(LDPC_E_UNSUPPORTED, "jit_prebuild: libnvrtc not available");
+    int E = 0, max_dc = 0;
+    for (int i = 0; i < M; ++i) {
+        int dc = 0;
+        for (int j = 0; j < N; ++j) dc += proto[(size_t)i * N + j] != -1;
+        if (dc == 0) return fail(LDPC_E_LIMIT, "jit_prebuild: row %d has no edge", i);
+        E += dc; max_dc = std::max(max_dc, dc);
+    }
+    for (int j = 0; j < N; ++j) {
+        int dv = 0;
+        for (int i = 0; i < M; ++i) dv += proto[(size_t)i * N + j] != -1;
+        if (dv == 0) return fail(LDPC_E_LIMIT, "jit_prebuild: column %d has no edge", j);
+    }
+    if (max_dc > 64 || M > LDPC_MAX_M || N > LDPC_MAX_N || E > LDPC_MAX_E) return fail(LDPC_E_LIMIT, "jit_prebuild: graph outside the specialised kernels' limits");
+    int built = 0;
+    char err[512] = {0};
+    for (int kind = NMS_JIT_DECODE; kind <= NMS_JIT_MCP; ++kind) {
+        if (kind == NMS_JIT_MCP && (z < 2 || N * z >= 65536)) continue;
+        int Fp = 0, R = 0;
+        nms_jit_pick_geometry(M, N, E, z, kind, max_dc, &Fp, &R);
+        if (nms_jit_build(proto, M, N, z, Fp, R, kind, nullptr, err, (int)sizeof err) != 0) return fail(LDPC_E_UNSUPPORTED, "jit_prebuild: %s", err);
+        ++built;
+    }
+    return built;
 }
 
 extern "C" int nms_alu_probe(int device, int kind, double *lane_ops_per_s);

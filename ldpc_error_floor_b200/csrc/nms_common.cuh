@@ -9,8 +9,19 @@
 // both sides of every rotation (conflict-free up to the single wrap point).
 #pragma once
 #include <cuda_fp16.h>
+#ifndef __CUDACC_RTC__
 #include <cuda_runtime.h>
 #include <stdint.h>
+#else
+// run-time specialisation (nms_jit.cu) compiles the kernel headers with NVRTC: no host headers there
+typedef unsigned char uint8_t;
+typedef signed char int8_t;
+typedef unsigned short uint16_t;
+typedef unsigned int uint32_t;
+typedef int int32_t;
+typedef unsigned long long uint64_t;
+typedef long long int64_t;
+#endif
 
 #define LDPC_MAX_M 256
 #define LDPC_MAX_N 256
@@ -104,10 +115,12 @@ struct NmsSpecEntry {
     const void *(*func)();
     int noet;   // 1: the variant for launches without early termination (never the default geometry)
 };
+#ifndef __CUDACC_RTC__
 extern "C" const NmsSpecEntry *nms_spec_table(int *count);
 extern "C" const NmsSpecEntry *nms_spec_f32_table(int *count);    // float path (decoding_type 1)
 extern "C" const NmsSpecEntry *nms_spec_f32q_table(int *count);   // quantised twin (q_bit 6, per-edge weights)
 extern "C" const NmsSpecEntry *nms_spec_mcp_table(int *count);    // persistent-slot Monte-Carlo kernels (nms_mcp.cuh)
+#endif
 #define NMS_MCP_MISC_WORDS (112 + 32 * 8 * 2)   // their per-CTA state words (== nms::MCP_MISC_WORDS)
 
 // ---- Philox4x32-10 (Salmon et al., SC'11), written out so the host tests can restate it
@@ -139,8 +152,15 @@ __device__ __forceinline__ void philox4x32_10_keyed(uint32_t c0, uint32_t c1, ui
     out[0] = c0; out[1] = c1; out[2] = c2; out[3] = c3;
 }
 
+#ifndef __CUDACC_RTC__
 cudaError_t nms_launch_generate(const KParams &P, float *out, long long n_frames, cudaStream_t st);
 cudaError_t nms_launch_normal_probe(unsigned long long seed, unsigned long long frame_offset, long long n_frames, int nquads,
                                     float *out, unsigned long long *counts, cudaStream_t st);
+cudaError_t nms_launch_generate_cw(const KParams &P, const uint32_t *cw, long long cw_stride, float *out, long long n_frames,
+                                   cudaStream_t st);
+cudaError_t nms_launch_cw_metrics(const float *app, long long B, int T, int NZ, int target_bits, const uint32_t *cw, long long cw_stride,
+                                  const int *iters, int early_term, uint8_t *flags, int *biterr, int *biterr_signed,
+                                  unsigned long long *counters, cudaStream_t st);
 void nms_note_launch();
 unsigned long long nms_launch_count();
+#endif

@@ -61,6 +61,21 @@ class DecodeResult:
         return (self.flags & _lib.FLAG_UNCOR_LAST) != 0
 
 
+def pack_codewords(y, nbits: int, device) -> "tuple[torch.Tensor, int]":
+    """Codeword bits [nbits] (shared by all frames) or [B, nbits] (0/1, any integer / bool type, numpy or torch) ->
+    (int32 CUDA tensor of packed words, stride in words): bit k at word k // 32, bit k % 32 (include/ldpc_b200.h)."""
+    a = y.detach().cpu().numpy() if isinstance(y, torch.Tensor) else np.asarray(y)
+    shared = a.ndim == 1
+    a = np.ascontiguousarray(a.reshape(1 if shared else a.shape[0], -1) != 0)
+    if a.shape[1] != nbits:
+        raise ValueError(f"codeword has {a.shape[1]} bits, expected {nbits}")
+    words = (nbits + 31) // 32
+    pad = np.zeros((a.shape[0], words * 32), dtype=bool)
+    pad[:, :nbits] = a
+    packed = np.packbits(pad, axis=1, bitorder="little").view(np.uint32).reshape(a.shape[0], words)
+    return torch.from_numpy(packed.view(np.int32).copy()).to(device), (0 if shared else words)
+
+
 def _ptr(t: Optional[torch.Tensor]):
     return ctypes.c_void_p(t.data_ptr()) if t is not None else None
 
@@ -193,6 +208,36 @@ class NMSDecoder:
                                            ctypes.c_void_p(stream)))
         return DecodeResult(unpack_bits(hard, g.NZ) if (unpack and hard is not None) else None, hard, it, fl, be, app_t)
 
+    def decode_cw(self, llr: torch.Tensor, codeword, iters: int = 0, early_term: bool = False,
+                  counters: Optional[torch.Tensor] = None):
+        """decode() with the error metrics taken against `codeword` (bits [N*z] or [B, N*z]) instead of the all-zero word
+        (ldpc_decode_cw; calc_ber_fer with Y != 0, Print_Functions.py:100-118).  Returns (DecodeResult, biterr_signed int32 [B],
+        counters int64[8]); DecodeResult.biterr is the Hamming distance of the output decision."""
+        g = self.graph
+        if not llr.is_cuda or llr.dtype != torch.float32:
+            raise ValueError("decode_cw: llr must be a CUDA float32 tensor")
+        B = llr.shape[0]
+        if llr.numel() != B * g.NZ:
+            raise ValueError(f"decode_cw: llr has {llr.numel()} elements, expected {B}x{g.NZ}")
+        llr = llr.contiguous()
+        cw, stride = pack_codewords(codeword, g.NZ, self.device)
+        if stride and cw.shape[0] != B:
+            raise ValueError("decode_cw: one codeword per frame, or one for all")
+        dev = self.device
+        hard = torch.empty((B, self.hard_words), dtype=torch.int32, device=dev)
+        it = torch.empty((B,), dtype=torch.int32, device=dev)
+        fl = torch.empty((B,), dtype=torch.uint8, device=dev)
+        be = torch.empty((B,), dtype=torch.int32, device=dev)
+        bs = torch.empty((B,), dtype=torch.int32, device=dev)
+        if counters is None:
+            counters = torch.zeros((_lib.NUM_COUNTERS,), dtype=torch.int64, device=dev)
+        stream = torch.cuda.current_stream(dev).cuda_stream
+        _lib.check(_lib.load().ldpc_decode_cw(self._h, _ptr(llr), _ptr(cw), stride, B, int(iters), 1 if early_term else 0,
+                                              _ptr(hard), _ptr(it), _ptr(fl), _ptr(be), _ptr(bs), _ptr(counters),
+                                              ctypes.c_void_p(stream)))
+        torch.cuda.current_stream(dev).synchronize()                  # cw is a temporary
+        return DecodeResult(None, hard, it, fl, be, None), bs, counters
+
     def ya_output_all(self, xa: torch.Tensor, iters: int = 0) -> torch.Tensor:
         """net_dict["ya_output_all"] of the reference: [T*B, N*z] float32 (Main_Functions.py:380-383)."""
         r = self.decode(xa, iters=iters, early_term=False, app="all", want_hard=False)
@@ -313,11 +358,20 @@ class NMSDecoder:
         return {"hard_packed": hard, "iters": it, "flags": fl, "biterr": be, "app": None}
 
     # --------------------------------------------------------------------- generator / MC / post
-    def generate(self, sigma: float, n_frames: int, seed: int, frame_offset: int = 0) -> torch.Tensor:
+    def generate(self, sigma: float, n_frames: int, seed: int, frame_offset: int = 0, codeword=None) -> torch.Tensor:
         """BPSK/AWGN LLRs of the all-zero codeword, CUDA float32 [n_frames, N, z]
-        (replaces Print_Functions.create_mix_epoch, :29-72; Philox instead of MT19937)."""
+        (replaces Print_Functions.create_mix_epoch, :29-72; Philox instead of MT19937).
+        codeword: bits [N*z] (every frame) or [n_frames, N*z]: the samples of those words instead (is_zeros_word = False, :40-46)."""
         out = torch.empty((n_frames, self.graph.N, self.graph.z), dtype=torch.float32, device=self.device)
         stream = torch.cuda.current_stream(self.device).cuda_stream
+        if codeword is not None:
+            cw, stride = pack_codewords(codeword, self.graph.NZ, self.device)
+            if stride and cw.shape[0] != n_frames:
+                raise ValueError("generate: one codeword per frame, or one for all")
+            _lib.check(_lib.load().ldpc_llr_generate_cw(self._h, float(sigma), int(n_frames), int(seed) & (2**64 - 1),
+                                                        int(frame_offset), _ptr(cw), stride, _ptr(out), ctypes.c_void_p(stream)))
+            torch.cuda.current_stream(self.device).synchronize()      # cw is a temporary
+            return out
         _lib.check(_lib.load().ldpc_llr_generate(self._h, float(sigma), int(n_frames), int(seed) & (2**64 - 1),
                                                  int(frame_offset), _ptr(out), ctypes.c_void_p(stream)))
         return out

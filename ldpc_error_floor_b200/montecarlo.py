@@ -250,15 +250,45 @@ def _pick_stage1(counters: np.ndarray, T: int) -> int:
     return s1
 
 
+def create_mix_epoch(decoder, scaling_factor, word_random, seed: int, batch_size: int, code_GM=None,
+                     is_zeros_word: bool = True, frame_offset: int = 0):
+    """Drop-in for Print_Functions.create_mix_epoch (:29-72): one batch, frame k drawn at scaling_factor[k % len] (:36).
+    Returns (X CUDA float32 [B, N, z], Y int64 numpy [B, N*z]).  The noise comes from the device generator (Philox key
+    `seed`, global frame indices from `frame_offset`); the codewords -- when `is_zeros_word` is False -- from the caller's
+    numpy RandomState exactly as in the reference: infoWord = word_random.randint(0, 2, (1, k*z)), Y = infoWord . code_GM mod 2
+    (:40-42), one draw per frame in frame order."""
+    g = decoder.graph
+    sf = np.atleast_1d(np.asarray(scaling_factor, dtype=np.float64))
+    B, n = int(batch_size), sf.size
+    Y = np.zeros((B, g.NZ), dtype=np.int64)
+    if not is_zeros_word:
+        GM = np.asarray(code_GM)
+        for k in range(B):
+            info = word_random.randint(0, 2, size=(1, GM.shape[0]))
+            Y[k] = (np.dot(info, GM) % 2)[0]
+    else:
+        for k in range(B):
+            word_random.randint(0, 2, size=(1, g.NZ))                  # the reference draws and discards (:39)
+    X = torch.empty((B, g.N, g.z), dtype=torch.float32, device=decoder.device)
+    for s, sg in enumerate(sf):
+        idx = np.arange(s, B, n)
+        if idx.size:
+            X[s::n] = decoder.generate(float(sg), idx.size, seed, frame_offset + s * B,
+                                       codeword=None if is_zeros_word else Y[idx])
+    return X, Y
+
+
 def compute_results(decoder, sample_num, input_llr, SNR_sigma, batch_size, sampling_type, seed=2044,
-                    uncor_path: Optional[str] = None, iters: int = 0, group=None):
+                    uncor_path: Optional[str] = None, iters: int = 0, group=None, input_codeword=None):
     """Drop-in for Print_Functions.compute_results (:130-165): returns (Results f32[4, nSNR], seconds) with
     rows BER_last, FER_last, FER, loss.  The loss row stays 0: the fused Monte-Carlo path has no loss kernel, so
     `opt_result_print = 3` (best epoch by validation loss) is refused by drivers.evaluate / trainer.train_block.
 
     sampling_type 0/2: `floor(sample_num/batch_size)*batch_size` generated frames per sigma (:135-143);
     2 also appends the never-corrected words to `uncor_path` in the Inputs/[Uncor] format (:155-156).
-    sampling_type 1: decodes the stored rows `input_llr` (file sign convention, :145 / :6-10)."""
+    sampling_type 1: decodes the stored rows `input_llr` (file sign convention, :145 / :6-10); with `input_codeword`
+    (labels [n, N*z], Main_Functions.process_data) the metrics are taken against those words (ldpc_decode_cw), BER with the
+    reference's signed sum (:112-113)."""
     from . import formats
     t0 = time.time()
     g = decoder.graph
@@ -269,6 +299,16 @@ def compute_results(decoder, sample_num, input_llr, SNR_sigma, batch_size, sampl
         xa = formats.uncor_to_llr(np.asarray(input_llr, dtype=np.float32)[:n], g.N, g.z)
         # stored words of a quantised decoder sit on its grid ('%.1f' of 0.5-steps, Print_Functions.py:124): ship them as
         # int8 -- a quarter of the bytes over PCIe, same results (tests/test_gpu_parity.py::test_q8_words_...)
+        if input_codeword is not None and np.any(np.asarray(input_codeword)[:n]):
+            Y = np.asarray(input_codeword)[:n].reshape(n, -1)
+            r, signed, cnt = decoder.decode_cw(torch.from_numpy(xa).to(decoder.device), Y, iters=iters)
+            c = cnt.cpu().numpy()
+            nb = max(int(batch_size), 1)
+            sg = signed.cpu().numpy().astype(np.int64)[:(n // nb) * nb].reshape(-1, nb)
+            res[0, :] = np.abs(sg.sum(axis=1)).sum() / max(n * g.NZ, 1)          # |sum of signed errors| per batch (:112-113, 158)
+            res[1, :] = c[1] / max(n, 1)
+            res[2, :] = c[2] / max(n, 1)
+            return res, time.time() - t0
         step = float(getattr(decoder, "q8_step", 0.0) or 0.0)
         words = None
         if step > 0 and hasattr(decoder, "decode_q8_host"):

@@ -232,6 +232,83 @@ def make_decode_cases():
     make_decode_case("5g_r050_z64_qms_222_t12_sys", "5g_r050_z64", sh, w, 12, 2, 5, 12, [0.5, 1.5, 2.5], target_node=N - M)
 
 
+def lifted_H(proto, z):
+    M, N = proto.shape
+    H = np.zeros((M * z, N * z), dtype=np.uint8)
+    for i in range(M):
+        for j in range(N):
+            if proto[i, j] != -1:
+                s_ = int(proto[i, j]) % z
+                for a in range(z):
+                    H[i * z + a, j * z + (a + s_) % z] = 1          # check (i, a) -- variable (j, (a + s) mod z)
+    return H
+
+
+def generator_matrix(H, k):
+    """k rows of a basis of the null space of H over GF(2): a code_GM for create_mix_epoch (Print_Functions.py:41-42)."""
+    Hm = H.copy() % 2
+    m, n = Hm.shape
+    piv, r = [], 0
+    for c in range(n):
+        rows = np.nonzero(Hm[r:, c])[0]
+        if rows.size == 0:
+            continue
+        Hm[[r, r + rows[0]]] = Hm[[r + rows[0], r]]
+        for rr in np.nonzero(Hm[:, c])[0]:
+            if rr != r:
+                Hm[rr] ^= Hm[r]
+        piv.append(c)
+        r += 1
+        if r == m:
+            break
+    free = [c for c in range(n) if c not in piv]
+    G = np.zeros((len(free), n), dtype=np.int64)
+    for gi, fc in enumerate(free):
+        G[gi, fc] = 1
+        for ri, pc in enumerate(piv):
+            G[gi, pc] = Hm[ri, fc]
+    assert not ((G @ H.T) % 2).any()
+    return G[:k]
+
+
+def make_cw_case(name, gkey, sharing, weights, T, decoding_type, q_bit, B, snr_db, seed=5, clip=20.0):
+    """Non-zero codewords ("next" row N3): create_mix_epoch with is_zeros_word = False and a generator matrix, the decode, and
+    calc_ber_fer against Y -- all by the reference's own code."""
+    if ONLY and not any(o in name for o in ONLY):
+        return
+    stem, proto, z, punct, short = graph_meta(gkey)
+    rd = ref_runner.ReferenceDecoder(proto.astype(int), z, sharing, weights, T, decoding_type, q_bit, clip, punct, short, snr_db)
+    M, N = proto.shape
+    GM = generator_matrix(lifted_H(proto, z), (N - M) * z)
+    word = np.random.RandomState(2042 + seed)
+    noise = np.random.RandomState(1074 + seed)
+    X, Y = rd.pf.create_mix_epoch(np.asarray(rd.snr_sigma), word, noise, B, N, N - M, z, GM, False, decoding_type,
+                                  punct[0], punct[1], short[0], short[1], q_bit, clip)
+    X = np.asarray(X, dtype=np.float32)
+    res = rd.decode(X, ya=Y.astype(np.float32))
+    ber_last, fer_last, fer, uncor, error_num = rd.pf.calc_ber_fer(res["ya_output_all"], T, Y, B)
+    out = {"proto": proto.astype(np.int16), "meta": np.array([z, punct[0], punct[1], short[0], short[1]]),
+           "sharing": np.array(sharing), "T": np.array(T), "decoding_type": np.array(decoding_type),
+           "q_bit": np.array(q_bit), "clip": np.array(clip, dtype=np.float32), "xa": X, "app": res["app"].astype(np.float32),
+           "sigma": np.asarray(rd.snr_sigma), "codeword": Y.astype(np.uint8), "uncor_flag": np.asarray(uncor),
+           "error_num": np.asarray(error_num), "metrics": np.array([ber_last, fer_last, fer])}
+    for i in range(3):
+        if sharing[i] > 0:
+            out[f"w{i}"] = np.asarray(weights[i], dtype=np.float32)[:T]
+    np.savez_compressed(os.path.join(OUT, f"decode_{name}.npz"), **out)
+    print(f"decode_{name}.npz  B={B} T={T}  ones per codeword {Y.sum(axis=1)[:4]}  FER {fer:.3f} FER_last {fer_last:.3f} BER_last {ber_last:.3e}")
+
+
+def make_cw_cases():
+    _, p, z, _, _ = graph_meta("mackay")
+    M, N = p.shape
+    E = int((p != -1).sum())
+    make_cw_case("mackay_qms_300_t20_cw", "mackay", [3, 0, 0], const_weights([3, 0, 0], 20, M, N, E), 20, 2, 5, 16, [1.0, 2.0, 3.0, 4.0])
+    sh, w = shipped("wimax_base20")
+    make_cw_case("wimax_qms_333_t20_cw", "wimax", sh, w, 20, 2, 5, 8, [2.0, 2.5, 3.0, 3.5])
+    make_cw_case("wimax_float_333_t10_cw", "wimax", sh, w, 10, 1, 5, 6, [2.0, 3.0])
+
+
 def make_mc():
     """compute_results exactly as main_Base.py:177 calls it at epoch 0 with sampling_type=2."""
     sh, w = shipped("wimax_base20")
@@ -317,11 +394,13 @@ if __name__ == "__main__":
         raise SystemExit("needs /root/reference (development container only)")
     # `make_golden.py decode only=sys,fixed` re-mints just the decode cases whose name contains one of the keys
     ONLY[:] = [k for a in sys.argv[1:] if a.startswith("only=") for k in a[5:].split(",")]
-    what = [a for a in sys.argv[1:] if not a.startswith("only=")] or ["codes", "decode", "mc", "grad"]
+    what = [a for a in sys.argv[1:] if not a.startswith("only=")] or ["codes", "decode", "cw", "mc", "grad"]
     if "codes" in what:
         make_codes()
     if "decode" in what:
         make_decode_cases()
+    if "cw" in what:
+        make_cw_cases()
     if "mc" in what:
         make_mc()
     if "grad" in what:

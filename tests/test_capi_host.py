@@ -160,3 +160,18 @@ def test_two_stage_heuristic():
     assert montecarlo._pick_stage1(cnt(.0002, 3.18), 20) == 0         # WiMAX 4 dB
     assert montecarlo._pick_stage1(cnt(.7, 18.0), 20) == 0            # waterfall: most frames fail
     assert montecarlo._pick_stage1(np.zeros(8), 20) == 0
+
+
+def test_jit_prebuild_needs_no_gpu(tmp_path, monkeypatch):
+    """Run-time specialisation cross-compiles with NVRTC: the cubin of an unknown graph lands in the on-disk cache
+    without a device (ldpc_jit_prebuild); a second call is a cache hit."""
+    import time
+    monkeypatch.setenv("LDPC_B200_JIT_CACHE", str(tmp_path))
+    proto = -np.ones((3, 6), dtype=np.int32)
+    proto[0, [0, 1, 3]] = [1, 2, 0]; proto[1, [1, 2, 3, 4]] = [3, 0, 5, 0]; proto[2, [0, 2, 4, 5]] = [4, 6, 1, 0]
+    n = _lib.jit_prebuild(proto, 8)
+    assert n == 2                                                  # packed decode kernel + persistent-slot Monte-Carlo kernel
+    files = sorted(os.listdir(tmp_path))
+    assert len(files) == 2 and all(f.endswith(".cubin") for f in files)
+    t0 = time.time()
+    assert _lib.jit_prebuild(proto, 8) == 2 and time.time() - t0 < 2.0

@@ -413,3 +413,30 @@ def test_generator_tails_and_ks():
         band = 4.0 * math.sqrt(expect) + 1.0
         assert abs(int(c[k]) - expect) <= band + 2e-4 * expect, (thr, int(c[k]), expect)     # 2e-4: MUFU accuracy at 3-4 sigma
     print("tail counts", dict(zip((3, 4, 5, 6, 7), c[:5].tolist())), "of", total)
+
+
+def test_create_mix_epoch_and_compute_results_with_codewords():
+    """create_mix_epoch drop-in with a generator matrix (is_zeros_word = False) and compute_results(sampling_type 1) on labelled
+    words: Y is a codeword, the decoder brings most frames back to it, and the metrics are taken against it."""
+    import torch
+    from ldpc_error_floor_b200 import formats
+    from ldpc_error_floor_b200.montecarlo import compute_results, create_mix_epoch
+    d = np.load(golden_path("decode_mackay_qms_300_t20_cw.npz"))
+    case, g, dec = make("mackay_qms_300_t20_cw")
+    H = np.zeros((g.M, g.N), np.int64); H[case["proto"] != -1] = 1         # z = 1: the proto matrix is H
+    Yg = d["codeword"].astype(np.int64)
+    assert not ((Yg @ H.T) % 2).any()
+    GM = Yg[:8]                                                            # eight codewords span a small subcode
+    rs = np.random.RandomState(4)
+    X, Y = create_mix_epoch(dec, g.sigma([4.0, 5.0]), rs, seed=12, batch_size=600, code_GM=GM, is_zeros_word=False)
+    assert X.shape == (600, g.N, g.z) and Y.shape == (600, g.NZ) and not ((Y @ H.T) % 2).any() and Y.any()
+    r, signed, cnt = dec.decode_cw(X, Y)
+    c = cnt.cpu().numpy()
+    assert c[0] == 600 and c[2] <= c[1] < 60                               # 4-5 dB: nearly every frame is brought back to Y
+    z, _, _ = dec.decode_cw(X, np.zeros_like(Y))                           # against the wrong word: (almost) all frames "fail"
+    assert int(((z.flags.cpu().numpy() & 4) != 0).sum()) > 500
+    rows = -X.reshape(600, -1).cpu().numpy()                               # the [Uncor] file sign convention
+    res, _ = compute_results(dec, 600, rows, np.array([0.0]), 20, 1, input_codeword=Y)
+    assert res[1, 0] == pytest.approx(c[1] / 600) and res[2, 0] == pytest.approx(c[2] / 600)
+    Xz, Yz = create_mix_epoch(dec, g.sigma([4.0]), np.random.RandomState(4), seed=12, batch_size=64)
+    assert not Yz.any() and torch.equal(Xz, dec.generate(float(g.sigma([4.0])[0]), 64, 12).reshape(64, g.N, g.z))

@@ -3,6 +3,8 @@ reference's own code, and against the C oracle on larger seeded batches.
 
 Pass criteria (BASELINE.json north_star): quantised path bit-exact (APP, hard decisions, syndrome
 flags); float path: hard decisions identical, APP within 1e-5 relative."""
+import os
+
 import numpy as np
 import pytest
 
@@ -443,3 +445,133 @@ def test_partial_iterations_and_ragged_batches(name):
             assert torch.equal(r.flags, want.flags[:n]) and torch.equal(r.biterr, want.biterr[:n])
     h = dec.decode_host(big[:5].cpu().numpy())
     assert np.array_equal(h["flags"], full.flags[:5].cpu().numpy())
+
+
+# ------------------------------------------------------------------------------------------------------------------
+# "next" row N3: non-zero codewords (Print_Functions.py:40-46 with is_zeros_word = False, metrics against Y :100-118)
+@pytest.mark.parametrize("name", ["mackay_qms_300_t20_cw", "wimax_qms_333_t20_cw", "wimax_float_333_t10_cw"])
+def test_nonzero_codeword_golden(name):
+    """Goldens minted by the reference itself: create_mix_epoch with a generator matrix, build_neural_network,
+    calc_ber_fer(ya_output_all, T, Y, B).  ldpc_decode_cw must report the reference's uncor_flag (never equal to Y at any
+    iteration), its per-frame signed error sums, FER_last and -- with the reference's cancelling sum -- BER_last."""
+    import torch
+    from ldpc_error_floor_b200 import _lib
+    case = load_case(name)
+    d = np.load(os.path.join(os.path.dirname(__file__), "golden", f"decode_{name}.npz"))
+    Y, T = d["codeword"], case["T"]
+    g, dec = build_decoder(case)
+    xa = torch.from_numpy(case["xa"]).cuda()
+    B = xa.shape[0]
+    r, signed, cnt = dec.decode_cw(xa, Y)
+    flags = r.flags.cpu().numpy()
+    hard_ref = case["app"] >= 0                                           # [T, B, NZ]
+    wrong = (hard_ref != Y[None].astype(bool)).any(axis=2)                # [T, B]
+    assert np.array_equal((flags & _lib.FLAG_UNCOR_ANY) != 0, d["uncor_flag"].astype(bool))
+    assert np.array_equal((flags & _lib.FLAG_UNCOR_ANY) != 0, wrong.all(axis=0))
+    assert np.array_equal((flags & _lib.FLAG_UNCOR_LAST) != 0, wrong[-1])
+    assert np.array_equal(signed.cpu().numpy(), d["error_num"].astype(np.int64))
+    assert np.array_equal(r.biterr.cpu().numpy(), (hard_ref[-1] != Y.astype(bool)).sum(axis=1))
+    ber_last, fer_last, fer = (float(v) for v in d["metrics"])
+    assert abs(abs(int(signed.sum().item())) / (B * g.NZ) - ber_last) < 1e-12        # :112-113
+    c = cnt.cpu().numpy()
+    assert c[0] == B and c[1] == round(fer_last * B) and c[2] == round(fer * B) and c[4] == B * T
+    assert c[3] == int(r.biterr.sum().item())
+    # the decode itself does not know about Y: same hard decisions / syndromes as the plain entry point
+    plain = dec.decode(xa)
+    assert torch.equal(plain.hard_packed, r.hard_packed) and torch.equal(plain.iters, r.iters)
+    assert torch.equal(plain.flags & 9, r.flags & 9)
+    # one shared codeword == that codeword repeated; early termination stops at the first zero syndrome
+    r1, s1, _ = dec.decode_cw(xa[:1].repeat(3, 1, 1), Y[0])
+    assert torch.equal(r1.flags, r.flags[:1].repeat(3)) and int(s1[0].item()) == int(signed[0].item())
+    e, es, ec = dec.decode_cw(xa, Y, early_term=True)
+    hard_e = np.stack([hard_ref[int(it) - 1, b] for b, it in enumerate(e.iters.cpu().numpy())])
+    assert np.array_equal(e.biterr.cpu().numpy(), (hard_e != Y.astype(bool)).sum(axis=1))
+    assert int(ec[4].item()) == int(np.where((e.flags.cpu().numpy() & 1) != 0, e.iters.cpu().numpy(), T).sum())
+
+
+def test_generator_with_codeword(codes):
+    """ldpc_llr_generate_cw: the all-zero codeword gives ldpc_llr_generate's samples bit for bit; a random codeword moves
+    the mean to +-2/sigma^2 per bit (Print_Functions.py:45-46) and leaves punctured / shortened positions alone."""
+    import torch
+    case = load_case("5g_r050_z64_qms_222_t50")
+    g, dec = build_decoder(case)
+    import ldpc_error_floor_b200 as L
+    fdec = L.NMSDecoder(g, L.WeightSet(case["sharing"], dict(case["weights"])), iters=case["T"], decoding_type=1)
+    sigma = float(g.sigma([2.0])[0])
+    zero = np.zeros(g.NZ, np.uint8)
+    a = fdec.generate(sigma, 300, seed=5, frame_offset=9)
+    b = fdec.generate(sigma, 300, seed=5, frame_offset=9, codeword=zero)
+    assert torch.equal(a, b)
+    assert torch.equal(dec.generate(sigma, 300, seed=5), dec.generate(sigma, 300, seed=5, codeword=np.zeros((300, g.NZ), np.uint8)))
+    rng = np.random.RandomState(3)
+    Y = rng.randint(0, 2, size=(4000, g.NZ)).astype(np.uint8)
+    x = fdec.generate(sigma, 4000, seed=6, codeword=Y).cpu().numpy().reshape(4000, -1)
+    ps, pe = case["punct"]; ss, se = case["short"]
+    assert np.all(x[:, ps - 1:pe] == 0) and np.all(x[:, ss - 1:se] == -case["clip"])
+    mask = np.ones(g.NZ, bool); mask[ps - 1:pe] = False; mask[ss - 1:se] = False
+    s = (x * (2.0 * Y - 1.0))[:, mask]
+    assert abs(s.mean() - 2 / sigma ** 2) < 5 * (2 / sigma) / np.sqrt(s.size)
+    assert abs(s.std() / (2 / sigma) - 1) < 0.01
+    # shared codeword
+    xs = fdec.generate(sigma, 16, seed=6, codeword=Y[0]).cpu().numpy().reshape(16, -1)
+    assert np.array_equal(xs[0], x[0])
+
+
+# ------------------------------------------------------------------------------------------------------------------
+# run-time graph specialisation (csrc/nms_jit.cu): a graph the build has never seen gets NVRTC-compiled unrolled kernels
+def _random_qc_graph(seed=17, M=5, N=15, z=40):
+    rng = np.random.RandomState(seed)
+    proto = -np.ones((M, N), dtype=np.int32)
+    for i in range(M):
+        cols = rng.choice(N - M, size=6, replace=False)
+        proto[i, cols] = rng.randint(0, z, size=6)
+        proto[i, N - M + i] = 0                              # a staircase over the parity columns
+        if i:
+            proto[i, N - M + i - 1] = rng.randint(0, z)
+    for j in range(N - M):                                   # no unconnected column
+        if (proto[:, j] == -1).all():
+            proto[rng.randint(M), j] = rng.randint(0, z)
+    return proto, z
+
+
+def test_runtime_specialised_kernels_match_generic_and_oracle(monkeypatch):
+    import torch
+    import ldpc_error_floor_b200 as L
+    from oracle import c_oracle
+    proto, z = _random_qc_graph()
+    M, N = proto.shape
+    rng = np.random.RandomState(3)
+    T = 12
+    ws = L.WeightSet([2, 2, 2], {0: rng.uniform(0.5, 1.0, (T, M)).astype(np.float32), 1: rng.uniform(0.3, 0.9, (T, M)).astype(np.float32),
+                                 2: rng.uniform(0.8, 1.1, (T, N)).astype(np.float32)})
+    g = L.BaseGraph(proto, z)
+    dec = L.NMSDecoder(g, ws, iters=T)
+    assert "jit" in dec.kernel_name and dec.packed, dec.kernel_name
+    info = dec.mc_info()
+    assert info["persistent"] and "jit" in info["kernel"], info
+    monkeypatch.setenv("LDPC_B200_NO_JIT", "1")
+    gen = L.NMSDecoder(g, ws, iters=T)                        # the table-driven generic kernels
+    monkeypatch.delenv("LDPC_B200_NO_JIT")
+    assert "jit" not in gen.kernel_name and not gen.mc_info()["persistent"]
+    sigma = float(g.sigma([2.5])[0])
+    x = dec.generate(sigma, 2500, seed=8)
+    for et in (False, True):
+        a, b = dec.decode(x, early_term=et), gen.decode(x, early_term=et)
+        assert torch.equal(a.hard_packed, b.hard_packed) and torch.equal(a.flags, b.flags)
+        assert torch.equal(a.iters, b.iters) and torch.equal(a.biterr, b.biterr)
+    ref = c_oracle.decode(proto, z, x.cpu().numpy(), ws.sharing, ws.blocks, T, 2, 5, 20.0, want_all=False)
+    r = dec.decode(x, app="last")
+    assert np.array_equal(r.app.cpu().numpy(), ref["app_last"])
+    assert 0 < int(((r.flags.cpu().numpy() & 1) == 0).sum()) < 2500          # some frames fail, some converge
+    for et in (True, False):
+        c1, _ = dec.mc_run_host(sigma, 40001, seed=2, frame_offset=5, early_term=et, harvest=L.HARVEST_UNCOR_ANY, capacity=10)
+        c2, _ = gen.mc_run_host(sigma, 40001, seed=2, frame_offset=5, early_term=et, harvest=L.HARVEST_UNCOR_ANY, capacity=10)
+        assert c1 == c2, (et, c1, c2)
+
+
+def test_polar_runs_on_a_runtime_specialised_kernel():
+    """Polar(64, 48) has row degree 64 and no compiled-in unrolled kernel: it is specialised at run time (its cubin is
+    prebuilt by __graft_entry__.build()); the goldens above already hold it to the reference."""
+    case = load_case("polar_qms_223_t6")
+    g, dec = build_decoder(case)
+    assert "jit" in dec.kernel_name, dec.kernel_name
