@@ -200,6 +200,7 @@ struct GF_{name} {{
 {arr('vn_rot', vn_rot)}
     static constexpr int NDEG = {len(sorted(set(dc)))}, DVMAX = {max(dv)};
 {arr('cn_degs', sorted(set(dc)))}
+{cn_tables}
 }};
 
 __global__ void __launch_bounds__({threads}, {mb[0]}) nms_f32_spec_{name}(const __grid_constant__ KParams P) {{

@@ -39,7 +39,7 @@ struct F32Ctx {
 
 __device__ __forceinline__ F32Ctx f32_ctx(const KParams &P, const Ctx &c) {
     F32Ctx h;
-    h.sb = (uint32_t)__cvta_generic_to_shared(nms_smem);
+    h.sb = smem_base();
     h.q4 = (uint32_t)c.q * 4u;
     h.amask = c.act ? 0xffffffffu : 0u;
     h.Lthr4 = c.act ? (uint32_t)P.L * 4u : 0x40000000u;

@@ -68,6 +68,41 @@ struct F32SpecPolicy {
     }
 
     // ------------------------------------------------------------------------------ CN phase
+    // min-sum rows with one weight per row or per iteration: one counted loop per degree class (a slot's rows come sorted by
+    // degree, G::cn_cls_cnt[slot][class] of them), the row list read one entry ahead, weights that do not vary per row loaded
+    // once per phase (WROW = false) -- the structure of spec_cn_rows in nms_h2_spec.cuh
+    template <bool WROW>
+    static __device__ __forceinline__ void cn_rows(const KParams &P, const Ctx &c, uint32_t a00, uint32_t hb4, uint32_t et2c,
+                                                   uint32_t w0row, int m0, uint32_t w1row, int m1, uint32_t &bad) {
+        constexpr int NT = (G::M + G::R - 1) / G::R;
+        float w0 = 1.0f, w1 = 1.0f;
+        if constexpr (!WROW) { w0 = ldsf(w0row); w1 = ldsf(w1row); }
+        const uint2 *task = P.cn_task + c.slot * NT;
+        uint2 tk = task[0];
+        static_for<0, G::NDEG>([&](auto k) {
+            constexpr int K = decltype(k)::v;
+            constexpr int DC = G::cn_degs_desc[K];
+            int nk = 0;
+            static_for<0, G::R>([&](auto sl) {
+                constexpr int CNT = G::cn_cls_cnt[decltype(sl)::v * G::NDEG + K];
+                if (c.slot == decltype(sl)::v) nk = CNT;
+            });
+#pragma unroll 1
+            for (int n = 0; n < nk; ++n) {
+                const uint2 cur = tk;
+                tk = *++task;
+                const uint32_t par = row_syndrome(et2c, hb4, (int)(cur.x / LP4), DC);
+                bad |= par;
+                if constexpr (WROW) {
+                    const int i = (int)(cur.y >> 16);
+                    w0 = ldsf(w0row + (uint32_t)((i & m0) * 4));
+                    w1 = ldsf(w1row + (uint32_t)((i & m1) * 4));
+                }
+                cn_row_f32<DC, QM>(P, a00 + cur.x, LP4, w0, w1, par);
+            }
+        });
+    }
+
     static __device__ __forceinline__ void cn_phase(const KParams &P, const Ctx &c, int t, uint32_t &bad) {
         const F32Ctx h = f32_ctx(P, c);
         const uint32_t a00 = h.sb + h.q4;
@@ -80,6 +115,11 @@ struct F32SpecPolicy {
         const int m0 = (P.sharing0 != 0 && P.wc > 1) ? -1 : 0;
         const uint32_t w1row = P.sharing1 != 0 ? h.sb + (uint32_t)(P.off_w + P.w_off_ucn + t * P.wu) * 4u : w0row;
         const int m1 = P.sharing1 != 0 ? (P.wu > 1 ? -1 : 0) : m0;
+        if (!(QM == 0 && P.sp) && P.sharing0 != 1) {   // uniform
+            if ((m0 | m1) != 0) cn_rows<true>(P, c, a00, hb4, et2c, w0row, m0, w1row, m1, bad);
+            else cn_rows<false>(P, c, a00, hb4, et2c, w0row, m0, w1row, m1, bad);
+            return;
+        }
         constexpr int NT = (G::M + G::R - 1) / G::R;
         const uint2 *task = P.cn_task + c.slot * NT;   // host-built: {row offset in bytes, degree | row index << 16}
 #pragma unroll 1
@@ -90,19 +130,8 @@ struct F32SpecPolicy {
             const uint32_t a0 = a00 + tk.x;
             const uint32_t par = row_syndrome(et2c, hb4, (int)(tk.x / LP4), dc);
             bad |= par;
-            if (QM == 0 && P.sp) {   // sum-product check update (decoding_type 0)
-                cn_row_f32_sp(P, a0, LP4, dc, t, i, (int)(tk.x / LP4), par);
-                continue;
-            }
-            if (P.sharing0 == 1) {   // per-edge weights: the compact two-pass code
-                cn_row_f32_generic<QM>(P, a0, LP4, dc, t, i, (int)(tk.x / LP4), par);
-                continue;
-            }
-            const float w0 = ldsf(w0row + (uint32_t)((i & m0) * 4)), w1 = ldsf(w1row + (uint32_t)((i & m1) * 4));
-            static_for<0, G::NDEG>([&](auto k) {
-                constexpr int DC = G::cn_degs[decltype(k)::v];
-                if (dc == DC) cn_row_f32<DC, QM>(P, a0, LP4, w0, w1, par);
-            });
+            if (QM == 0 && P.sp) cn_row_f32_sp(P, a0, LP4, dc, t, i, (int)(tk.x / LP4), par);        // sum-product (decoding_type 0)
+            else cn_row_f32_generic<QM>(P, a0, LP4, dc, t, i, (int)(tk.x / LP4), par);              // per-edge weights
         }
     }
 
