@@ -608,6 +608,12 @@ extern "C" int ldpc_decoder_create2(const ldpc_graph_t *g, const int32_t sharing
     P.M = g->M; P.N = g->N; P.E = g->E; P.z = g->z; P.NZ = g->N * g->z;
     P.Fp = geom.Fp; P.FB = geom.FB; P.L = geom.L; P.LP = geom.LP; P.C = geom.C; P.R = geom.R;
     P.qms = qms; P.sp = decoding_type == 0; P.qmagic = 12582912.0f / qk; P.qmax = qmax; P.clip = clip_llr;
+    {
+        const __half hq = __float2half_rn(qmax);
+        unsigned short bits;
+        std::memcpy(&bits, &hq, sizeof bits);
+        P.qmax_h2 = (uint32_t)bits | ((uint32_t)bits << 16);
+    }
     P.sat_magic = qms ? P.qmagic : 0.0f; P.sat_bound = qms ? qmax : clip_llr;
     P.sharing0 = sharing[0]; P.sharing1 = sharing[1]; P.sharing2 = sharing[2];
     P.wc = wc; P.wu = wu; P.wv = wv;

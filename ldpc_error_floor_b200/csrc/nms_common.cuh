@@ -46,6 +46,7 @@ struct KParams {
     int sp;            // 1: sum-product check update (decoding_type 0, Main_Functions.py:238-245), float kernels only
     float qmagic;      // 1.5*2^23/qk: (x + qmagic) - qmagic rounds x half-to-even to the quantiser step 1/qk
     float qmax;        // Q(x) = clamp(round_to_step(x), +-qmax)            (Main_Functions.py:483-492)
+    uint32_t qmax_h2;  // {qmax, qmax} as half2 bits: the packed kernels' clamp operand, converted once on the host
     float clip;        // clip_LLR (main_Base.py:69)
     // message saturation without a mode branch: sat(x) = clamp((x + sat_magic) - sat_magic, +-sat_bound) is Q(x) on the
     // quantised path (qmagic, qmax) and clip(x, +-clip_LLR) on the float path (0, clip)

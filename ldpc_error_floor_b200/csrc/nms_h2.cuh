@@ -91,7 +91,7 @@ __device__ __forceinline__ uint32_t h2_rot(const H2Ctx &h, uint32_t rot4, uint32
 
 // Q() of two float32 values -> half2 (round to step in fp32, saturate after packing; +-inf saturate too)
 __device__ __forceinline__ __half2 q2(const KParams &P, float lo, float hi) {
-    const __half2 qm = __float2half2_rn(P.qmax);
+    const __half2 qm = u2h(P.qmax_h2);
     const float2 q = qround2(make_float2(lo, hi), P.qmagic);
     const __half2 r = __floats2half2_rn(q.x, q.y);
     return __hmax2(__hmin2(r, qm), __hneg2(qm));
@@ -103,7 +103,7 @@ __device__ __forceinline__ __half2 q2(const KParams &P, float lo, float hi) {
 // (CN, UCN) weight pair per half.
 __device__ __forceinline__ void h2_row_mags(const KParams &P, float w0lo, float w0hi, float w1lo, float w1hi, bool dc_odd,
                                             uint32_t par, __half2 m1, __half2 m2, uint32_t &A, uint32_t &B) {
-    const __half2 qm = __float2half2_rn(P.qmax), zero = __float2half2_rn(0.0f);
+    const __half2 qm = u2h(P.qmax_h2), zero = __float2half2_rn(0.0f);
     // drop the piggy-backed hard bits; V->C saturation (:223-224) applied to the two minima
     const __half2 m1c = __hmin2(u2h(h2u(m1) & ~LSB2), qm), m2c = __hmin2(u2h(h2u(m2) & ~LSB2), qm);
     const float wlo = (par & 1u) ? w1lo : w0lo;     // unsatisfied check -> UCN weight (:275,:285,:295)

@@ -112,8 +112,10 @@ struct H2SpecPolicy {
     //        VN_INIT_SMEM   pass before iteration 0 (C->V = 0), channel values already in the xa array
     //        VN_INIT_GLOBAL same, channel values `xg` just loaded from global memory (also fills the xa array)
     //   VNW: VN weights present.  HB: publish the hard decisions as ballots (a copy-out may follow).
+    // wvs: the VN weight when it does not vary per column (sharing code 3: loaded once per phase), NaN-free sentinel < 0
+    // otherwise (sharing code 2: fetched per column from wvrow)
     template <int J, int MODE, bool VNW, bool HB>
-    static __device__ __forceinline__ void vn_col(const KParams &P, const H2Ctx &h, uint32_t wvrow, uint32_t hbrow,
+    static __device__ __forceinline__ void vn_col(const KParams &P, const H2Ctx &h, uint32_t wvrow, float wvs, uint32_t hbrow,
                                                   float2 xg, uint32_t &ones) {
         constexpr int C0 = G::col_ptr[J], DV = G::col_ptr[J + 1] - C0;
         constexpr bool INIT = MODE != VN_ITER;
@@ -150,8 +152,9 @@ struct H2SpecPolicy {
         }
         __half2 xin = xqh;
         if constexpr (VNW) {
-            const float w = h2_w(wvrow, J, P.h2_mv);
-            xin = q2(P, __fmul_rn(x.x, w), __fmul_rn(x.y, w));   // Q(xa * w), :168-177
+            const float w = P.h2_mv != 0 ? h2_w(wvrow, J, -1) : wvs;       // uniform branch
+            const float2 xw = __fmul2_rn(x, make_float2(w, w));
+            xin = q2(P, xw.x, xw.y);                             // Q(xa * w), :168-177
         }
         // hard bit = (value >= 0): of xin_0 before iteration 0 (:181-182), of the APP afterwards (a zero is +0)
         const __half2 hsrc = INIT ? xin : __hadd2(xqh, S);
@@ -177,7 +180,7 @@ struct H2SpecPolicy {
     }
 
     template <int SLOT, int MODE, bool VNW, bool HB>
-    static __device__ __forceinline__ void vn_slot(const KParams &P, const Ctx &c, const H2Ctx &h, uint32_t wvrow,
+    static __device__ __forceinline__ void vn_slot(const KParams &P, const Ctx &c, const H2Ctx &h, uint32_t wvrow, float wvs,
                                                    uint32_t hbrow, uint32_t &ones) {
         constexpr int NT = (G::N - SLOT + G::R - 1) / G::R;
         if constexpr (MODE == VN_INIT_GLOBAL) {
@@ -203,12 +206,12 @@ struct H2SpecPolicy {
             }
             static_for<0, NT>([&](auto n) {
                 constexpr int J = G::vn_order[SLOT + decltype(n)::v * G::R];
-                vn_col<J, MODE, VNW, HB>(P, h, wvrow, hbrow, x[decltype(n)::v], ones);
+                vn_col<J, MODE, VNW, HB>(P, h, wvrow, wvs, hbrow, x[decltype(n)::v], ones);
             });
         } else {
             static_for<0, NT>([&](auto n) {
                 constexpr int J = G::vn_order[SLOT + decltype(n)::v * G::R];
-                vn_col<J, MODE, VNW, HB>(P, h, wvrow, hbrow, make_float2(0.0f, 0.0f), ones);
+                vn_col<J, MODE, VNW, HB>(P, h, wvrow, wvs, hbrow, make_float2(0.0f, 0.0f), ones);
             });
         }
     }
@@ -220,12 +223,13 @@ struct H2SpecPolicy {
         // ballots go to hb[buf][half][j][chunk]
         const uint32_t hbrow = h.sb + (uint32_t)(P.off_hb + tbuf * 2 * G::N * G::C + c.chunk) * 4u;
         if (P.sharing2 != 0) {
+            const float wvs = ldsf(wvrow);                       // element 0 of the row: THE weight when sharing code is 3
             static_for<0, G::R>([&](auto s) {
-                if (c.slot == decltype(s)::v) vn_slot<decltype(s)::v, MODE, true, HB>(P, c, h, wvrow, hbrow, ones);
+                if (c.slot == decltype(s)::v) vn_slot<decltype(s)::v, MODE, true, HB>(P, c, h, wvrow, wvs, hbrow, ones);
             });
         } else {
             static_for<0, G::R>([&](auto s) {
-                if (c.slot == decltype(s)::v) vn_slot<decltype(s)::v, MODE, false, HB>(P, c, h, wvrow, hbrow, ones);
+                if (c.slot == decltype(s)::v) vn_slot<decltype(s)::v, MODE, false, HB>(P, c, h, wvrow, 1.0f, hbrow, ones);
             });
         }
     }

@@ -114,8 +114,8 @@ struct McpKernel {
     // not Q(-clip_LLR) = -qmax: Print_Functions.py:59-60 vs Main_Functions.py:168-177)
     template <int J, bool VNW>
     static __device__ __forceinline__ void vn_col(const KParams &P, const H2Ctx &h, uint32_t keep, uint32_t negkeep,
-                                                  uint32_t freshsel, uint32_t wv_lo, uint32_t wv_hi, int sh_lo, int sh_hi,
-                                                  uint32_t &cnt) {
+                                                  uint32_t freshsel, uint32_t wv_lo, uint32_t wv_hi, float wsl, float wsh,
+                                                  int sh_lo, int sh_hi, uint32_t &cnt) {
         constexpr int C0 = G::col_ptr[J], DV = G::col_ptr[J + 1] - C0;
         uint32_t addr[DV], cv[DV];
         static_for<0, DV>([&](auto u) {
@@ -132,7 +132,8 @@ struct McpKernel {
         __half2 xin = xqh;
         uint32_t hs = h2u(__hadd2(xqh, S));                                   // unclipped APP (a refilled half: xq itself)
         if constexpr (VNW) {
-            const float wl = h2_w(wv_lo, J, P.h2_mv), wh = h2_w(wv_hi, J, P.h2_mv);
+            // per-column rows (sharing code 2) are fetched here, a per-iteration scalar (code 3) came in with the phase
+            const float wl = P.h2_mv != 0 ? h2_w(wv_lo, J, -1) : wsl, wh = P.h2_mv != 0 ? h2_w(wv_hi, J, -1) : wsh;
             const bool shortened = J * G::z >= sh_lo && J * G::z <= sh_hi;
             const float xl = shortened ? -P.clip : __low2float(xqh), xh = shortened ? -P.clip : __high2float(xqh);
             xin = q2(P, __fmul_rn(xl, wl), __fmul_rn(xh, wh));               // Q(xa * w), :168-177
@@ -147,12 +148,12 @@ struct McpKernel {
 
     template <int SLOT, bool VNW>
     static __device__ __forceinline__ void vn_slot(const KParams &P, const H2Ctx &h, uint32_t keep, uint32_t negkeep,
-                                                   uint32_t freshsel, uint32_t wv_lo, uint32_t wv_hi, int sh_lo, int sh_hi,
-                                                   uint32_t &cnt) {
+                                                   uint32_t freshsel, uint32_t wv_lo, uint32_t wv_hi, float wsl, float wsh,
+                                                   int sh_lo, int sh_hi, uint32_t &cnt) {
         constexpr int NT = (G::N - SLOT + G::R - 1) / G::R;
         static_for<0, NT>([&](auto n) {
             constexpr int J = G::vn_order[SLOT + decltype(n)::v * G::R];
-            vn_col<J, VNW>(P, h, keep, negkeep, freshsel, wv_lo, wv_hi, sh_lo, sh_hi, cnt);
+            vn_col<J, VNW>(P, h, keep, negkeep, freshsel, wv_lo, wv_hi, wsl, wsh, sh_lo, sh_hi, cnt);
         });
     }
 
@@ -219,13 +220,14 @@ struct McpKernel {
                     const uint32_t wv_lo = h2_wrow(h, P.h2w_v, tl, P.h2_wv), wv_hi = h2_wrow(h, P.h2w_v, th, P.h2_wv);
                     // shortened bits are k = j*z + a with short_s <= k + 1 <= short_e
                     const int sh_lo = P.short_s > 0 ? P.short_s - 1 - a_lane : 0x7fffffff, sh_hi = P.short_e - 1 - a_lane;
+                    const float wsl = ldsf(wv_lo), wsh = ldsf(wv_hi);
                     static_for<0, G::R>([&](auto sl) {
                         if (slot == decltype(sl)::v)
-                            vn_slot<decltype(sl)::v, true>(P, h, keep, keep ^ SIGN2, freshsel, wv_lo, wv_hi, sh_lo, sh_hi, cnt);
+                            vn_slot<decltype(sl)::v, true>(P, h, keep, keep ^ SIGN2, freshsel, wv_lo, wv_hi, wsl, wsh, sh_lo, sh_hi, cnt);
                     });
                 } else {
                     static_for<0, G::R>([&](auto sl) {
-                        if (slot == decltype(sl)::v) vn_slot<decltype(sl)::v, false>(P, h, keep, keep ^ SIGN2, freshsel, 0u, 0u, 0, 0, cnt);
+                        if (slot == decltype(sl)::v) vn_slot<decltype(sl)::v, false>(P, h, keep, keep ^ SIGN2, freshsel, 0u, 0u, 1.0f, 1.0f, 0, 0, cnt);
                     });
                 }
                 // ones of this hard decision, per slot pair (skipped by warps that saw none: the common case once
