@@ -41,7 +41,7 @@ GEOMETRIES = {
 GEOMETRIES_NOET = {"wimax": (8, 2)}
 # float32 kernels (one frame per lane): same lanes as the packed choice
 GEOMETRIES_F32 = {
-    "wimax": [(4, 2), (8, 2)], "wifi": [(7, 2)], "5g_r073_z72": [(4, 2), (3, 2)], "5g_r050_z64": [(2, 2)], "5g_r050_z32": [(4, 2)],
+    "wimax": [(4, 2)], "wifi": [(7, 2)], "5g_r073_z72": [(4, 2)], "5g_r050_z64": [(2, 2)], "5g_r050_z32": [(4, 2)],
     "5g_r033_z32": [(4, 2)], "5g_r073_z32": [(4, 2)], "mackay": [(32, 8)], "bch": [(32, 4)],
 }
 # persistent-slot Monte-Carlo kernels (nms_mcp.cuh: no float channel array, no ballots -> smaller CTAs, more of them per SM).
@@ -49,7 +49,7 @@ GEOMETRIES_F32 = {
 # (profiles/r02_mc_sweep.txt): (4,2) 28.4, (2,2) 27.7, (3,2) 26.9, (4,3) 25.9 M frames/s -- 288 = 9 x 32 lanes: no padding
 # lanes, no bank conflicts at the rotation wrap.
 GEOMETRIES_MCP = {
-    "wimax": [(4, 2), (2, 2)], "wifi": [(7, 2), (3, 2)], "5g_r073_z72": [(4, 2), (2, 2)], "5g_r050_z64": [(2, 2), (1, 2)],
+    "wimax": [(4, 2)], "wifi": [(7, 2)], "5g_r073_z72": [(4, 2), (2, 2)], "5g_r050_z64": [(2, 2)],
     "5g_r050_z32": [(4, 2)], "5g_r033_z32": [(4, 2)], "5g_r073_z32": [(4, 2)],
 }
 MCP_MISC_WORDS = 112 + 32 * 8 * 2

@@ -19,6 +19,7 @@
 #include <new>
 #include <numeric>
 #include <string>
+#include <thread>
 #include <vector>
 
 // kernel address getters, one per compiled degree bucket (nms_h2.cu / nms_f32.cu)
@@ -94,6 +95,10 @@ struct HostScratch {
     uint8_t *h_flags[2] = {nullptr, nullptr};
     int *h_biterr[2] = {nullptr, nullptr};
     cudaStream_t st[2] = {nullptr, nullptr};
+    // pinned staging of the INPUT words for callers that pass pageable memory (numpy arrays): a few host threads copy the
+    // next chunk in while the device works on the current one, instead of the driver's synchronous staged copy
+    char *h_in[2] = {nullptr, nullptr};
+    size_t h_in_bytes = 0;
     unsigned long long *counters = nullptr;
     unsigned int *ucount = nullptr;
     float *ubuf = nullptr;
@@ -695,6 +700,7 @@ void free_scratch(HostScratch &h) {
         cudaFree(h.llr[i]); cudaFree(h.app[i]); cudaFree(h.hard[i]); cudaFree(h.iters[i]);
         cudaFree(h.flags[i]); cudaFree(h.biterr[i]);
         cudaFreeHost(h.h_hard[i]); cudaFreeHost(h.h_iters[i]); cudaFreeHost(h.h_flags[i]); cudaFreeHost(h.h_biterr[i]);
+        cudaFreeHost(h.h_in[i]);
         if (h.st[i]) cudaStreamDestroy(h.st[i]);
     }
     cudaFree(h.counters); cudaFree(h.ucount); cudaFree(h.ubuf);
@@ -947,14 +953,44 @@ int decode_host_impl(const ldpc_decoder_t *dc, const void *src_host, bool q8, fl
         pend_n[k] = 0;
         return LDPC_OK;
     };
+    // pageable caller memory?  (cudaMemcpyAsync from it is staged by the driver and blocks: stage it ourselves, in parallel)
+    bool pageable = false;
+    {
+        cudaPointerAttributes attr;
+        if (cudaPointerGetAttributes(&attr, src_host) != cudaSuccess) { cudaGetLastError(); pageable = true; }
+        else pageable = attr.type == cudaMemoryTypeUnregistered;
+    }
+    if (pageable && h.h_in_bytes < chunk * P0.NZ * elem) {
+        for (int i = 0; i < 2; ++i) { cudaFreeHost(h.h_in[i]); h.h_in[i] = nullptr; }
+        h.h_in_bytes = 0;
+        for (int i = 0; i < 2; ++i) CUDA_TRY(cudaMallocHost(&h.h_in[i], chunk * P0.NZ * elem));
+        h.h_in_bytes = chunk * P0.NZ * elem;
+    }
+    const unsigned hw = std::max(1u, std::thread::hardware_concurrency());
+    const int n_copy = (int)std::min(8u, std::max(1u, hw / 2));
+    auto stage_in = [&](char *dst, const char *src, size_t bytes) {
+        if (bytes < (4u << 20) || n_copy == 1) { std::memcpy(dst, src, bytes); return; }
+        std::vector<std::thread> th;
+        const size_t per = ((bytes + n_copy - 1) / n_copy + 4095) & ~(size_t)4095;
+        for (int t = 1; t < n_copy; ++t) {
+            const size_t lo = std::min(bytes, per * t), hi = std::min(bytes, per * (t + 1));
+            if (hi > lo) th.emplace_back([=] { std::memcpy(dst + lo, src + lo, hi - lo); });
+        }
+        std::memcpy(dst, src, std::min(bytes, per));
+        for (auto &t : th) t.join();
+    };
     int k = 0;
     for (int64_t off = 0; off < B; off += (int64_t)chunk, k ^= 1) {
         const int64_t nb = std::min<int64_t>((int64_t)chunk, B - off);
         cudaStream_t st = h.st[k];
         rc = drain(k);
         if (rc != LDPC_OK) return rc;
-        CUDA_TRY(cudaMemcpyAsync(h.llr[k], (const char *)src_host + (size_t)off * P0.NZ * elem, (size_t)nb * P0.NZ * elem,
-                                 cudaMemcpyHostToDevice, st));
+        const char *src = (const char *)src_host + (size_t)off * P0.NZ * elem;
+        if (pageable) {
+            stage_in(h.h_in[k], src, (size_t)nb * P0.NZ * elem);      // stream k has drained: its staging buffer is free
+            src = h.h_in[k];
+        }
+        CUDA_TRY(cudaMemcpyAsync(h.llr[k], src, (size_t)nb * P0.NZ * elem, cudaMemcpyHostToDevice, st));
         KParams P = P0;
         P.T_run = T_run; P.early_term = early_term ? 1 : 0;
         P.llr = q8 ? nullptr : h.llr[k]; P.llr_q8 = q8 ? (const signed char *)h.llr[k] : nullptr; P.q8_step = step;

@@ -456,12 +456,35 @@ def normal_probe(seed: int, n_frames: int, quads_per_frame: int, frame_offset: i
 
 
 # ---- PyTorch custom op: torch.ops.ldpc_b200.nms_decode(llr, handle, ...) -> (hard, iters, flags, biterr, app)
-_REGISTRY: Dict[int, "NMSDecoder"] = {}
+# `handle` is a small integer the decoder owns for its whole life (weak registry below), so a traced / exported graph that
+# captured the op keeps referring to a live decoder; it is not the C pointer and not id().
+import itertools
+import weakref
+
+_REGISTRY: "weakref.WeakValueDictionary[int, NMSDecoder]" = weakref.WeakValueDictionary()
+_NEXT_HANDLE = itertools.count(1)
+
+
+def op_handle(dec: NMSDecoder) -> int:
+    """The integer that names `dec` in torch.ops.ldpc_b200.nms_decode calls (assigned once, valid while `dec` lives)."""
+    h = getattr(dec, "_op_handle", None)
+    if h is None:
+        h = next(_NEXT_HANDLE)
+        dec._op_handle = h
+        _REGISTRY[h] = dec
+    return h
+
+
+def _lookup(handle: int) -> NMSDecoder:
+    dec = _REGISTRY.get(int(handle))
+    if dec is None:
+        raise RuntimeError(f"ldpc_b200::nms_decode: decoder handle {handle} is not alive")
+    return dec
 
 
 @torch.library.custom_op("ldpc_b200::nms_decode", mutates_args=(), device_types="cuda")
 def _nms_decode_op(llr: torch.Tensor, handle: int, iters: int, early_term: bool, app_mode: int) -> List[torch.Tensor]:
-    dec = _REGISTRY[handle]
+    dec = _lookup(handle)
     app = {0: None, 1: "last", 2: "all"}[app_mode]
     r = dec._decode_impl(llr, iters, early_term, app, True, False)
     app_t = r.app if r.app is not None else torch.empty(0, device=llr.device)
@@ -470,7 +493,7 @@ def _nms_decode_op(llr: torch.Tensor, handle: int, iters: int, early_term: bool,
 
 @_nms_decode_op.register_fake
 def _(llr, handle, iters, early_term, app_mode):
-    dec = _REGISTRY[handle]
+    dec = _lookup(handle)
     B = llr.shape[0]
     T_run = dec.T if iters == 0 else iters
     app = (torch.empty(0, device=llr.device) if app_mode == 0 else
@@ -481,11 +504,7 @@ def _(llr, handle, iters, early_term, app_mode):
 
 def _decode_via_op(dec: NMSDecoder, llr, iters, early_term, app, want_hard, unpack) -> DecodeResult:
     """Routes NMSDecoder.decode through torch.ops.ldpc_b200.nms_decode and re-wraps the outputs."""
-    _REGISTRY[id(dec)] = dec
-    try:
-        hard, it, fl, be, app_t = torch.ops.ldpc_b200.nms_decode(
-            llr, id(dec), int(iters), bool(early_term), {None: 0, "last": 1, "all": 2}[app])
-    finally:
-        _REGISTRY.pop(id(dec), None)
+    hard, it, fl, be, app_t = torch.ops.ldpc_b200.nms_decode(
+        llr, op_handle(dec), int(iters), bool(early_term), {None: 0, "last": 1, "all": 2}[app])
     return DecodeResult(unpack_bits(hard, dec.graph.NZ) if unpack else None, hard if want_hard else None, it, fl,
                         be, app_t if app is not None else None)

@@ -575,3 +575,25 @@ def test_polar_runs_on_a_runtime_specialised_kernel():
     case = load_case("polar_qms_223_t6")
     g, dec = build_decoder(case)
     assert "jit" in dec.kernel_name, dec.kernel_name
+
+
+def test_custom_op_handle_is_stable():
+    """torch.ops.ldpc_b200.nms_decode names its decoder by a small integer the decoder keeps for life (not id(), not a pointer
+    popped after the call), so a captured call site stays valid while other decoders come and go."""
+    import gc
+    import torch
+    from ldpc_error_floor_b200.decoder import op_handle
+    case = load_case("wimax_qms_333_t20")
+    g, dec = build_decoder(case)
+    xa = torch.from_numpy(case["xa"]).cuda()
+    h = op_handle(dec)
+    a = torch.ops.ldpc_b200.nms_decode(xa, h, 0, False, 0)
+    _, other = build_decoder(load_case("mackay_qms_300_t20"))
+    assert op_handle(other) != h
+    del other
+    gc.collect()
+    b = torch.ops.ldpc_b200.nms_decode(xa, h, 0, False, 0)
+    assert op_handle(dec) == h and torch.equal(a[0], b[0]) and torch.equal(a[2], b[2])
+    assert torch.equal(dec.decode(xa).hard_packed, a[0])
+    with pytest.raises(RuntimeError):
+        torch.ops.ldpc_b200.nms_decode(xa, 10 ** 9, 0, False, 0)
