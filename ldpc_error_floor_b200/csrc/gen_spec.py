@@ -50,9 +50,12 @@ GEOMETRIES_F32 = {
 # lanes, no bank conflicts at the rotation wrap.
 GEOMETRIES_MCP = {
     "wimax": [(4, 2)], "wifi": [(7, 2)], "5g_r073_z72": [(4, 2), (2, 2)], "5g_r050_z64": [(2, 2)],
-    "5g_r050_z32": [(4, 2)], "5g_r033_z32": [(4, 2)], "5g_r073_z32": [(4, 2)],
+    "5g_r050_z32": [(4, 2)], "5g_r033_z32": [(4, 2)], "5g_r073_z32": [(4, 2)], "mackay": [(32, 8)], "bch": [(32, 4)],
 }
-MCP_MISC_WORDS = 112 + 32 * 8 * 2
+
+
+def mcp_misc_words(FB):
+    return 224 + FB * 16
 SKIP = {"polar"}   # row degree 64 > 32: generic two-pass kernel
 
 
@@ -149,9 +152,9 @@ def emit(key, proto, z, Fp, R, outdir, f32=False, mcp=False):
     cls_cnt = [sum(1 for p in range(s_, M, R) if dc[cn_order[p]] == dg) for s_ in range(R) for dg in degs_desc]
     cn_tables = arr('cn_degs_desc', degs_desc) + "\n" + arr('cn_cls_cnt', cls_cnt)
     if mcp:
-        if 2 * Fp > 32:
+        if 2 * Fp > 64:
             return None
-        words = ((E * LP + 3) & ~3) + N * LP + 256 + MCP_MISC_WORDS
+        words = ((E * LP + 3) & ~3) + N * LP + 256 + mcp_misc_words(2 * Fp)
         minb = max(1, min(MAX_SMEM // (words * 4 + 1024), 2048 // threads, 65536 // (threads * 56)))
         src = f"""// GENERATED by gen_spec.py -- do not edit.  Graph "{key}": {M}x{N}, z={z}, E={E}; persistent-slot Monte-Carlo geometry Fp={Fp} R={R}.
 #include "../nms_mcp.cuh"

@@ -297,7 +297,7 @@ void fill_smem_layout_mc(KParams *P) {
     P->off_xa = off; P->off_xq = off; off += P->N * P->LP;
     P->off_hb = off; P->off_et = off; P->off_et2 = off;
     P->off_w = off; off += (P->w_words + 3) & ~3;      // the state block holds 64-bit counters
-    P->off_misc = off; off += NMS_MCP_MISC_WORDS;
+    P->off_misc = off; off += NMS_MCP_MISC_WORDS(P->FB);
     P->smem_words = off;
 }
 
@@ -511,7 +511,7 @@ extern "C" int ldpc_decoder_create2(const ldpc_graph_t *g, const int32_t sharing
             }
         }
     }
-    // persistent-slot Monte-Carlo kernel of the same graph (slot masks are one word: at most 32 frames per CTA)
+    // persistent-slot Monte-Carlo kernel of the same graph
     if (d->packed && d->spec_name != nullptr && g->N * g->z < 65536 && !env_on("LDPC_B200_NO_SPEC")) {
         int n = 0;
         const NmsSpecEntry *tab = nms_spec_mcp_table(&n);
@@ -526,7 +526,7 @@ extern "C" int ldpc_decoder_create2(const ldpc_graph_t *g, const int32_t sharing
             geo.Fp = tab[k].Fp; geo.FB = 2 * geo.Fp; geo.L = g->z * geo.Fp; geo.LP = (geo.L + 31) & ~31; geo.C = geo.LP / 32;
             geo.R = tab[k].R; geo.threads = geo.C * geo.R * 32;
             KParams tmp{};
-            tmp.E = g->E; tmp.N = g->N; tmp.LP = geo.LP; tmp.w_words = w_words;
+            tmp.E = g->E; tmp.N = g->N; tmp.LP = geo.LP; tmp.w_words = w_words; tmp.FB = geo.FB;
             fill_smem_layout_mc(&tmp);
             geo.smem_bytes = tmp.smem_words * 4;
             if (geo.smem_bytes > 227 * 1024) continue;
@@ -549,7 +549,7 @@ extern "C" int ldpc_decoder_create2(const ldpc_graph_t *g, const int32_t sharing
         char err[512] = {0};
         const unsigned long long h = graph_hash(d->g);
         for (int kind = NMS_JIT_DECODE; kind <= NMS_JIT_MCP; ++kind) {
-            if (kind == NMS_JIT_MCP && (g->z < 2 || g->N * g->z >= 65536 || env_on("LDPC_B200_NO_JIT_MCP"))) continue;
+            if (kind == NMS_JIT_MCP && (g->N * g->z >= 65536 || env_on("LDPC_B200_NO_JIT_MCP"))) continue;
             int Fp = 0, R = 0;
             nms_jit_pick_geometry(g->M, g->N, g->E, g->z, kind, g->info.max_dc, &Fp, &R);
             const char *efp = getenv(kind == NMS_JIT_MCP ? "LDPC_B200_MCP_FP" : "LDPC_B200_FP");
@@ -559,9 +559,9 @@ extern "C" int ldpc_decoder_create2(const ldpc_graph_t *g, const int32_t sharing
             LaunchGeom geo{};
             geo.Fp = Fp; geo.FB = 2 * Fp; geo.L = g->z * Fp; geo.LP = (geo.L + 31) & ~31; geo.C = geo.LP / 32; geo.R = R;
             geo.threads = geo.C * R * 32;
-            if (geo.C > 16 || geo.threads > 1024 || geo.FB > LDPC_MAX_FB || (kind == NMS_JIT_MCP && geo.FB > 32)) continue;
+            if (geo.C > 16 || geo.threads > 1024 || geo.FB > LDPC_MAX_FB) continue;
             KParams tmp{};
-            tmp.E = g->E; tmp.N = g->N; tmp.L = geo.L; tmp.LP = geo.LP; tmp.C = geo.C; tmp.qms = 1; tmp.no_xq = no_xq;
+            tmp.E = g->E; tmp.N = g->N; tmp.L = geo.L; tmp.LP = geo.LP; tmp.C = geo.C; tmp.qms = 1; tmp.no_xq = no_xq; tmp.FB = geo.FB;
             tmp.w_words = w_words; tmp.w_staged = w_words > 0 && w_words <= NMS_WSTAGE_MAX_WORDS;
             if (kind == NMS_JIT_MCP) fill_smem_layout_mc(&tmp); else fill_smem_layout(&tmp, true, false);
             geo.smem_bytes = tmp.smem_words * 4;
@@ -1303,7 +1303,7 @@ extern "C" int ldpc_jit_prebuild(const int32_t *proto, int32_t M, int32_t N, int
     int built = 0;
     char err[512] = {0};
     for (int kind = NMS_JIT_DECODE; kind <= NMS_JIT_MCP; ++kind) {
-        if (kind == NMS_JIT_MCP && (z < 2 || N * z >= 65536)) continue;
+        if (kind == NMS_JIT_MCP && N * z >= 65536) continue;
         int Fp = 0, R = 0;
         nms_jit_pick_geometry(M, N, E, z, kind, max_dc, &Fp, &R);
         if (nms_jit_build(proto, M, N, z, Fp, R, kind, nullptr, err, (int)sizeof err) != 0) return fail(LDPC_E_UNSUPPORTED, "jit_prebuild: %s", err);

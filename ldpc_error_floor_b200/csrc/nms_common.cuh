@@ -122,7 +122,7 @@ extern "C" const NmsSpecEntry *nms_spec_f32_table(int *count);    // float path 
 extern "C" const NmsSpecEntry *nms_spec_f32q_table(int *count);   // quantised twin (q_bit 6, per-edge weights)
 extern "C" const NmsSpecEntry *nms_spec_mcp_table(int *count);    // persistent-slot Monte-Carlo kernels (nms_mcp.cuh)
 #endif
-#define NMS_MCP_MISC_WORDS (112 + 32 * 8 * 2)   // their per-CTA state words (== nms::MCP_MISC_WORDS)
+#define NMS_MCP_MISC_WORDS(FB) (224 + (FB) * 16)   // their per-CTA state words: masks / per-pair words + 8 uint64 counters per slot
 
 // ---- Philox4x32-10 (Salmon et al., SC'11), written out so the host tests can restate it
 __host__ __device__ __forceinline__ void philox4x32_10(uint32_t c0, uint32_t c1, uint32_t c2, uint32_t c3,

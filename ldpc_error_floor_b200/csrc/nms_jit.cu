@@ -130,10 +130,10 @@ extern "C" int nms_jit_available(void) { return nvrtc().ok ? 1 : 0; }
 // lanes (z * Fp close to a multiple of 32) while enough warps stay resident; z = 1 graphs interleave as many frames as
 // the kernel family allows and split the rows over about E / (1.5 max_dc) slots (the longest row bounds a phase).
 void nms_jit_pick_geometry(int M, int N, int E, int z, int kind, int max_dc, int *Fp_out, int *R_out) {
-    const int max_smem = 227 * 1024, fp_max = kind == NMS_JIT_MCP ? 16 : 32;
+    const int max_smem = 227 * 1024, fp_max = 32;
     const int regs = std::min(128, std::max(56, (2 * max_dc + 40 + 7) & ~7));
     auto smem_of = [&](int LP, int C) {
-        const int words = kind == NMS_JIT_MCP ? ((E * LP + 3) & ~3) + N * LP + 256 + NMS_MCP_MISC_WORDS
+        const int words = kind == NMS_JIT_MCP ? ((E * LP + 3) & ~3) + N * LP + 256 + NMS_MCP_MISC_WORDS(64)
                                               : ((E * LP + 3) & ~3) + N * LP * 2 + 4 * N * C + 256 + NMS_MISC_WORDS;
         return words * 4;
     };
@@ -195,7 +195,7 @@ std::string nms_jit_source(const int *proto, int M, int N, int z, int Fp, int R,
             cls_cnt.push_back(n);
         }
     const int max_smem = 227 * 1024;
-    const int words = kind == NMS_JIT_MCP ? ((E * LP + 3) & ~3) + N * LP + 256 + NMS_MCP_MISC_WORDS
+    const int words = kind == NMS_JIT_MCP ? ((E * LP + 3) & ~3) + N * LP + 256 + NMS_MCP_MISC_WORDS(2 * Fp)
                                           : ((E * LP + 3) & ~3) + N * LP * 2 + 4 * N * C + 256 + NMS_MISC_WORDS;
     // registers: a check row of degree dc lives in dc registers plus the tournament's temporaries
     const int max_dc = *std::max_element(dc.begin(), dc.end());

@@ -30,17 +30,29 @@
 
 namespace nms {
 
-// state words, relative to P.off_misc; [2] = double-buffered by step parity
-constexpr int MCP_SYND = 0;    // [2] slot mask: the previous hard decision violates a check
-constexpr int MCP_GE1 = 2;     // [2] slots whose frame is at iteration >= 1 (its syndrome means something)
-constexpr int MCP_ATT = 4;     // [2] slots whose frame has used up its iterations: it stops whatever the syndrome says
-constexpr int MCP_ACT = 6;     // [2] slots that hold a frame
-constexpr int MCP_HMASK = 8;   // slots whose frame is copied to the harvest buffer in this step
-constexpr int MCP_TP = 16;     // [2][16] per slot pair: iteration index of the low | high << 16 frame
-constexpr int MCP_CNT = 48;    // [2][16] per slot pair: ones in the counted columns of the last hard decision, low | high << 16
-constexpr int MCP_HROW = 80;   // [32] harvest row of the slot's frame
-constexpr int MCP_ACC = 112;   // [32][8] uint64: the eight Monte-Carlo counters per slot, flushed once per launch
-constexpr int MCP_MISC_WORDS = MCP_ACC + 32 * 8 * 2;
+// state words, relative to P.off_misc; [2] = double-buffered by step parity; every slot mask is two words (slots 0-31, 32-63)
+constexpr int MCP_SYND = 0;    // [2][2] slot mask: the previous hard decision violates a check
+constexpr int MCP_GE1 = 4;     // [2][2] slots whose frame is at iteration >= 1 (its syndrome means something)
+constexpr int MCP_ATT = 8;     // [2][2] slots whose frame has used up its iterations: it stops whatever the syndrome says
+constexpr int MCP_ACT = 12;    // [2][2] slots that hold a frame
+constexpr int MCP_HMASK = 16;  // [2] slots whose frame is copied to the harvest buffer in this step
+constexpr int MCP_TP = 32;     // [2][32] per slot pair: iteration index of the low | high << 16 frame
+constexpr int MCP_CNT = 96;    // [2][32] per slot pair: ones in the counted columns of the last hard decision, low | high << 16
+constexpr int MCP_HROW = 160;  // [64] harvest row of the slot's frame
+constexpr int MCP_ACC = 224;   // [FB][8] uint64: the eight Monte-Carlo counters per slot, flushed once per launch
+static_assert(MCP_ACC == NMS_MCP_MISC_WORDS(0), "host and device agree on the state block");
+
+// slot masks: one word up to 32 frames per CTA, two beyond (z = 1 graphs interleave 64 frames per CTA)
+template <bool WIDE> struct McpMask { using type = uint32_t; };
+template <> struct McpMask<true> { using type = unsigned long long; };
+__device__ __forceinline__ int mpopc(uint32_t m) { return __popc(m); }
+__device__ __forceinline__ int mpopc(unsigned long long m) { return __popcll(m); }
+__device__ __forceinline__ int mffs(uint32_t m) { return __ffs(m); }
+__device__ __forceinline__ int mffs(unsigned long long m) { return __ffsll((long long)m); }
+__device__ __forceinline__ uint32_t mdrop_top(uint32_t m) { return m & ~(0x80000000u >> __clz(m)); }
+__device__ __forceinline__ unsigned long long mdrop_top(unsigned long long m) { return m & ~(0x8000000000000000ull >> __clzll((long long)m)); }
+__device__ __forceinline__ void mload(const uint32_t *w, uint32_t &m) { m = w[0]; }
+__device__ __forceinline__ void mload(const uint32_t *w, unsigned long long &m) { m = (unsigned long long)w[0] | ((unsigned long long)w[1] << 32); }
 
 __device__ __forceinline__ void sts16(uint32_t a, unsigned short v) { asm volatile("st.shared.u16 [%0], %1;" ::"r"(a), "h"(v)); }
 
@@ -52,17 +64,20 @@ struct McpKernel {
     static constexpr bool PAD = G::L != G::LP;
     static constexpr int NZ = G::N * G::z;
     static constexpr int NQUADS = (NZ + 3) / 4;
-    static constexpr uint32_t FBMASK = FB >= 32 ? 0xffffffffu : ((1u << FB) - 1u);
-    static_assert(FB <= 32, "slot masks are one word");
+    static constexpr bool WIDE = FB > 32;
+    using mask_t = typename McpMask<WIDE>::type;
+    static constexpr mask_t FBMASK = FB >= (WIDE ? 64 : 32) ? ~(mask_t)0 : (((mask_t)1 << (FB & (WIDE ? 63 : 31))) - 1);
+    static constexpr int NBW = (FB + 31) / 32;          // bookkeeping warps: one lane per slot
+    static_assert(FB <= 64 && G::C * G::R >= NBW, "slot masks are at most two words, one bookkeeping warp per word");
 
     // ---------------------------------------------------------------------------------------- sample generation
     // channel values of the frames entering the slots in `fresh` (rank r in the mask -> global frame first + r), written
     // as halves into the xq array; same samples, same order as gen_llr4 draws them for everyone else
-    static __device__ __forceinline__ void generate(const KParams &P, uint32_t sb, uint32_t fresh, unsigned long long first) {
+    static __device__ __forceinline__ void generate(const KParams &P, uint32_t sb, mask_t fresh, unsigned long long first) {
         const unsigned short hneg = __half_as_ushort(__float2half_rn(-P.qmax));   // a shortened bit: Q(-clip_LLR) to the decoder
         unsigned long long F = P.frame_offset + first;
-        for (uint32_t m = fresh; m != 0u; m &= m - 1u, ++F) {                      // uniform: one refilled slot after the other
-            const int f = __ffs(m) - 1;
+        for (mask_t m = fresh; m != 0; m &= m - 1, ++F) {                          // uniform: one refilled slot after the other
+            const int f = mffs(m) - 1;
             const uint32_t base = sb + (uint32_t)P.off_xq * 4u + (uint32_t)(f >> 1) * 4u + (uint32_t)(f & 1) * 2u;
             for (int quad = threadIdx.x; quad < NQUADS; quad += NTHR) {
                 const int k1 = 4 * quad + 1;                                       // 1-based index of the quad's first bit
@@ -187,86 +202,102 @@ struct McpKernel {
 
         for (int idx = tid; idx < P.w_words; idx += NTHR) smem_f(P.off_w + idx) = __ldg(P.w_all + idx);
         for (int idx = tid; idx < P.off_w; idx += NTHR) nms_smem[idx] = 0u;          // messages and channel values: finite
-        for (int idx = tid; idx < MCP_MISC_WORDS; idx += NTHR) misc[idx] = 0u;
+        for (int idx = tid; idx < NMS_MCP_MISC_WORDS(FB); idx += NTHR) misc[idx] = 0u;
         unsigned long long next = lo;                                                  // first frame not yet in a slot
-        uint32_t fresh = (hi - lo) >= (unsigned long long)FB ? FBMASK : ((1u << (int)(hi - lo)) - 1u);
+        mask_t fresh = (hi - lo) >= (unsigned long long)FB ? FBMASK : (((mask_t)1 << (int)(hi - lo)) - 1);
         unsigned long long first = next;                                               // frame of the lowest refilled slot
-        next += (unsigned long long)__popc(fresh);
-        uint32_t empty = ~fresh & FBMASK;
+        next += (unsigned long long)mpopc(fresh);
+        mask_t empty = ~fresh & FBMASK;
         __syncthreads();
-        if (tid == 0) misc[MCP_ACT] = fresh;
-        // bookkeeping state of slot `lane` (warp 0): iteration index of its frame, "was right at some iteration"
+        if (tid == 0) {
+            misc[MCP_ACT] = (uint32_t)fresh;
+            if constexpr (WIDE) misc[MCP_ACT + 1] = (uint32_t)((unsigned long long)fresh >> 32);
+        }
+        // bookkeeping state of slot `sl` (warps 0 .. NBW-1, one lane per slot): iteration index of its frame, "was right at
+        // some iteration", its counters
+        const int sl = warp * 32 + lane;
         int t = 0;
         bool ever = false;
-        unsigned long long *acc = reinterpret_cast<unsigned long long *>(misc + MCP_ACC) + (lane & 31) * 8;   // this slot's counters
-        if (fresh == 0u) return;
+        unsigned long long *acc = reinterpret_cast<unsigned long long *>(misc + MCP_ACC) + (sl < FB ? sl : 0) * 8;
+        if (fresh == 0) return;
 
         for (int s = 0;; ++s) {
             const int p = s & 1;
-            if (fresh != 0u) {
+            if (fresh != 0) {
                 generate(P, h.sb, fresh, first);
                 __syncthreads();
             }
             // ================================================================ VN phase
             {
-                const uint32_t kb = ~(fresh | empty) >> (2 * fp);                      // bit 0 / 1: low / high frame goes on
+                const uint32_t kb = (uint32_t)(~(fresh | empty) >> (2 * fp));          // bit 0 / 1: low / high frame goes on
                 const uint32_t keep = ((kb & 1u) ? 0x3c00u : 0u) | ((kb & 2u) ? 0x3c000000u : 0u);
                 const uint32_t freshsel = ((kb & 1u) ? 0u : 0xffffu) | ((kb & 2u) ? 0u : 0xffff0000u);
                 uint32_t cnt = 0;
                 if (P.sharing2 != 0) {
-                    const uint32_t tp = misc[MCP_TP + (p ^ 1) * 16 + fp];              // what the last CN phase ran
+                    const uint32_t tp = misc[MCP_TP + (p ^ 1) * 32 + fp];              // what the last CN phase ran
                     const int tl = (kb & 1u) ? min((int)(tp & 0xffffu) + 1, T - 1) : 0;
                     const int th = (kb & 2u) ? min((int)(tp >> 16) + 1, T - 1) : 0;
                     const uint32_t wv_lo = h2_wrow(h, P.h2w_v, tl, P.h2_wv), wv_hi = h2_wrow(h, P.h2w_v, th, P.h2_wv);
                     // shortened bits are k = j*z + a with short_s <= k + 1 <= short_e
                     const int sh_lo = P.short_s > 0 ? P.short_s - 1 - a_lane : 0x7fffffff, sh_hi = P.short_e - 1 - a_lane;
                     const float wsl = ldsf(wv_lo), wsh = ldsf(wv_hi);
-                    static_for<0, G::R>([&](auto sl) {
-                        if (slot == decltype(sl)::v)
-                            vn_slot<decltype(sl)::v, true>(P, h, keep, keep ^ SIGN2, freshsel, wv_lo, wv_hi, wsl, wsh, sh_lo, sh_hi, cnt);
+                    static_for<0, G::R>([&](auto sl_) {
+                        if (slot == decltype(sl_)::v)
+                            vn_slot<decltype(sl_)::v, true>(P, h, keep, keep ^ SIGN2, freshsel, wv_lo, wv_hi, wsl, wsh, sh_lo, sh_hi, cnt);
                     });
                 } else {
-                    static_for<0, G::R>([&](auto sl) {
-                        if (slot == decltype(sl)::v) vn_slot<decltype(sl)::v, false>(P, h, keep, keep ^ SIGN2, freshsel, 0u, 0u, 1.0f, 1.0f, 0, 0, cnt);
+                    static_for<0, G::R>([&](auto sl_) {
+                        if (slot == decltype(sl_)::v) vn_slot<decltype(sl_)::v, false>(P, h, keep, keep ^ SIGN2, freshsel, 0u, 0u, 1.0f, 1.0f, 0, 0, cnt);
                     });
                 }
                 // ones of this hard decision, per slot pair (skipped by warps that saw none: the common case once
                 // the channel errors are gone)
                 if (!act) cnt = 0u;
                 if (__any_sync(0xffffffffu, cnt != 0u)) {
+                    if constexpr (G::Fp >= 16) {           // (nearly) every lane of a warp serves another pair: no reduction to do
+                        if (cnt) atomicAdd(&misc[MCP_CNT + p * 32 + fp], cnt);
+                    } else {
 #pragma unroll
-                    for (int k = 0; k < G::Fp; ++k) {
-                        const uint32_t r = __reduce_add_sync(0xffffffffu, fp == k ? cnt : 0u);
-                        if (lane == 0 && r) atomicAdd(&misc[MCP_CNT + p * 16 + k], r);
+                        for (int k = 0; k < G::Fp; ++k) {
+                            const uint32_t r = __reduce_add_sync(0xffffffffu, fp == k ? cnt : 0u);
+                            if (lane == 0 && r) atomicAdd(&misc[MCP_CNT + p * 32 + k], r);
+                        }
                     }
                 }
             }
             __syncthreads();
             // ================================================================ CN phase
             {
-                const uint32_t tp = misc[MCP_TP + p * 16 + fp];
+                const uint32_t tp = misc[MCP_TP + p * 32 + fp];
                 uint32_t bad = 0;
                 cn_phase(P, h, slot, min((int)(tp & 0xffffu), T - 1), min((int)(tp >> 16), T - 1), bad);
-                uint32_t m = (bad & 1u) | ((bad >> 15) & 2u);
-                m = act ? m << (2 * fp) : 0u;
-                const uint32_t r = __reduce_or_sync(0xffffffffu, m);
-                if (lane == 0 && r) atomicOr(&misc[MCP_SYND + p], r);
+                const uint32_t m2 = act ? ((bad & 1u) | ((bad >> 15) & 2u)) : 0u;      // this lane's two frames
+                const int sh = 2 * fp;
+                const uint32_t r0 = __reduce_or_sync(0xffffffffu, sh < 32 ? m2 << sh : 0u);
+                if (lane == 0 && r0) atomicOr(&misc[MCP_SYND + p * 2], r0);
+                if constexpr (WIDE) {
+                    const uint32_t r1 = __reduce_or_sync(0xffffffffu, sh >= 32 ? m2 << (sh - 32) : 0u);
+                    if (lane == 0 && r1) atomicOr(&misc[MCP_SYND + p * 2 + 1], r1);
+                }
             }
             __syncthreads();
             // ================================================================ who stops, who enters
-            const uint32_t sbad = misc[MCP_SYND + p], actm = misc[MCP_ACT + p];
-            const uint32_t fin = actm & (((P.early_term ? ~sbad : 0u) & misc[MCP_GE1 + p]) | misc[MCP_ATT + p]);
-            const int nfin = __popc(fin);
+            mask_t sbad, actm, ge1m, attm;
+            mload(misc + MCP_SYND + p * 2, sbad); mload(misc + MCP_ACT + p * 2, actm);
+            mload(misc + MCP_GE1 + p * 2, ge1m); mload(misc + MCP_ATT + p * 2, attm);
+            const mask_t fin = actm & (((P.early_term ? ~sbad : (mask_t)0) & ge1m) | attm);
+            const int nfin = mpopc(fin);
             const unsigned long long avail = hi - next;
             const int nnew = avail >= (unsigned long long)nfin ? nfin : (int)avail;
-            uint32_t enter = fin;                                                      // the lowest nnew of the stopped slots
-            for (int k = nfin; k > nnew; --k) enter &= ~(0x80000000u >> __clz(enter));
-            if (warp == 0) {
-                const bool mine = lane < FB && ((actm >> lane) & 1u);
-                const bool stop = mine && ((fin >> lane) & 1u);
-                const uint32_t cw = misc[MCP_CNT + p * 16 + (lane >> 1 & 15)];
-                const uint32_t ones = (lane & 1) ? cw >> 16 : cw & 0xffffu;            // of APP_{t-1}
-                const bool fbad = (sbad >> lane) & 1u;
+            mask_t enter = fin;                                                        // the lowest nnew of the stopped slots
+            for (int k = nfin; k > nnew; --k) enter = mdrop_top(enter);
+            const mask_t actn = (actm & ~fin) | enter;
+            if (warp < NBW) {
+                const bool mine = sl < FB && ((actm >> sl) & 1);
+                const bool stop = mine && ((fin >> sl) & 1);
+                const uint32_t cw = misc[MCP_CNT + p * 32 + (sl >> 1 & 31)];
+                const uint32_t ones = (sl & 1) ? cw >> 16 : cw & 0xffffu;              // of APP_{t-1}
+                const bool fbad = (sbad >> sl) & 1;
                 if (mine && t >= 1 && ones == 0u) ever = true;                         // D9: right at some iteration
                 uint32_t hidx = 0xffffffffu;
                 if (stop) {
@@ -288,31 +319,32 @@ struct McpKernel {
                     ++t;
                 }
                 __syncwarp();
-                const bool on = lane < FB && (((actm & ~fin) | enter) >> lane) & 1u;
+                const bool on = sl < FB && ((actn >> sl) & 1);
                 const uint32_t ge1 = __ballot_sync(0xffffffffu, on && t >= 1);
                 const uint32_t att = __ballot_sync(0xffffffffu, on && t >= T);
                 const uint32_t hm = __ballot_sync(0xffffffffu, hidx != 0xffffffffu);
                 const int tn = __shfl_down_sync(0xffffffffu, t, 1);
-                if (lane < FB) misc[MCP_HROW + lane] = hidx;
-                if (lane < FB && !(lane & 1)) {
-                    misc[MCP_TP + (p ^ 1) * 16 + (lane >> 1)] = (uint32_t)t | ((uint32_t)tn << 16);
-                    misc[MCP_CNT + p * 16 + (lane >> 1)] = 0u;                         // both lanes of the pair have read it
+                if (sl < FB) misc[MCP_HROW + sl] = hidx;
+                if (sl < FB && !(sl & 1)) {
+                    misc[MCP_TP + (p ^ 1) * 32 + (sl >> 1)] = (uint32_t)t | ((uint32_t)tn << 16);
+                    misc[MCP_CNT + p * 32 + (sl >> 1)] = 0u;                           // both lanes of the pair have read it
                 }
-                if (lane == 0) {
-                    misc[MCP_GE1 + (p ^ 1)] = ge1;
-                    misc[MCP_ATT + (p ^ 1)] = att;
-                    misc[MCP_ACT + (p ^ 1)] = (actm & ~fin) | enter;
-                    misc[MCP_SYND + (p ^ 1)] = 0u;                                     // consumed one step ago
-                    misc[MCP_HMASK] = hm;
+                if (lane == 0) {                                                       // this warp's word of every mask
+                    misc[MCP_GE1 + (p ^ 1) * 2 + warp] = ge1;
+                    misc[MCP_ATT + (p ^ 1) * 2 + warp] = att;
+                    misc[MCP_ACT + (p ^ 1) * 2 + warp] = (uint32_t)(actn >> (32 * warp));
+                    misc[MCP_SYND + (p ^ 1) * 2 + warp] = 0u;                          // consumed one step ago
+                    misc[MCP_HMASK + warp] = hm;
                 }
             }
             // harvest: the stopped frames' channel values leave before the generator overwrites them
-            if (P.harvest_mode != 0 && fin != 0u && P.uncor_buf != nullptr) {
+            if (P.harvest_mode != 0 && fin != 0 && P.uncor_buf != nullptr) {
                 __syncthreads();
-                const uint32_t hm = misc[MCP_HMASK];
-                if (hm != 0u) {
+                mask_t hm;
+                mload(misc + MCP_HMASK, hm);
+                if (hm != 0) {
                     for (int f = 0; f < FB; ++f) {
-                        if (!((hm >> f) & 1u)) continue;
+                        if (!((hm >> f) & 1)) continue;
                         float *row = P.uncor_buf + (size_t)misc[MCP_HROW + f] * NZ;
                         const __half *xq = reinterpret_cast<const __half *>(nms_smem + P.off_xq) + (f & 1);
                         for (int k = tid; k < NZ; k += NTHR) {
@@ -329,12 +361,12 @@ struct McpKernel {
             first = next;
             next += (unsigned long long)nnew;
             fresh = enter;
-            if (((actm & ~fin) | enter) == 0u) break;
+            if (actn == 0) break;
         }
 
-        if (warp == 0 && P.counters != nullptr) {
+        if (warp < NBW && P.counters != nullptr) {
             for (int k = 0; k < 8; ++k) {
-                unsigned long long v = lane < FB ? acc[k] : 0ull;
+                unsigned long long v = sl < FB ? acc[k] : 0ull;
                 for (int o = 16; o > 0; o >>= 1) v += __shfl_down_sync(0xffffffffu, v, o);
                 if (lane == 0 && v) atomicAdd(P.counters + k, v);
             }

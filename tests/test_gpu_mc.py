@@ -228,12 +228,13 @@ def _sorted_rows(a):
     ("wimax", 3.0, 0, 5, 20011), ("wifi", 3.5, 0, 20, 50000), ("wifi", 3.5, 0, 50, 9000),
     ("5g_r050_z64", 2.5, 1, 20, 40000), ("5g_r050_z64", 1.5, 0, 50, 6000), ("5g_r073_z72", 4.5, 1, 20, 30011),
     ("5g_r073_z72", 3.0, 0, 20, 5000), ("5g_r073_z32", 3.0, 1, 20, 30000), ("5g_r033_z32", 0.5, 0, 20, 20000),
-    ("5g_r050_z32", 1.5, 1, 30, 20000)])
+    ("5g_r050_z32", 1.5, 1, 30, 20000), ("mackay", 3.0, 0, 20, 100003), ("mackay", 6.0, 0, 20, 70), ("bch", 4.0, 0, 20, 50000)])
 def test_persistent_kernel_counts_like_the_batch_kernel(key, snr, systematic, iters, n, codes, monkeypatch):
     """ldpc_mc_run with early termination: the persistent-slot kernel (slots refilled frame by frame, frames of one CTA
     at different iterations) against the batch kernel on the same global frame indices -- the eight counters and the
     harvested words, for every harvest criterion.  Covers shipped weights with per-iteration / per-check CN, UCN and VN
-    rows, ragged and tiny launches, frames that use up all iterations."""
+    rows, ragged and tiny launches, frames that use up all iterations, and the z = 1 graphs (64 slots per CTA: two-word
+    slot masks, two bookkeeping warps)."""
     import torch
     from ldpc_error_floor_b200 import _lib
     g, ws, dec = _decoder_for(codes, key, systematic, iters)
