@@ -25,7 +25,7 @@ GEOMETRIES = {
     # (Fp, R) per graph, measured on B200 with tools/geom_sweep.py (profiles/r01_geometry_sweep.md): few fat warps
     # (R = 2: each warp owns half of the rows / columns, 80-110 registers) beat many thin ones.  More than one
     # entry = variants compiled side by side, first = default, LDPC_B200_FP / LDPC_B200_R select at run time.
-    "wimax": [(4, 2), (8, 2)],
+    "wimax": [(4, 2), (8, 2)],   # round-2 re-sweep (profiles/r02_geometry_sweep_wimax.txt): (8,2) 46.2, (4,2) 43.6, (16,2) 43.7, (12,2) 41.3, (8,3) 40.6, (4,3) 39.3
     "wifi": [(7, 2)],
     "5g_r073_z72": [(3, 2)],
     "5g_r050_z64": [(2, 2)],
