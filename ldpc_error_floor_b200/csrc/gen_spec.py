@@ -56,6 +56,13 @@ GEOMETRIES_MCP = {
 
 def mcp_misc_words(FB):
     return 224 + FB * 16
+
+
+def mcp_np():
+    """NMS_MCP_NP of nms_common.cuh: producer warps of the persistent-slot kernels"""
+    import re
+    m = re.search(r"#define NMS_MCP_NP (\d+)", open(os.path.join(HERE, "nms_common.cuh")).read())
+    return int(m.group(1))
 SKIP = {"polar"}   # row degree 64 > 32: generic two-pass kernel
 
 
@@ -154,7 +161,12 @@ def emit(key, proto, z, Fp, R, outdir, f32=False, mcp=False):
     if mcp:
         if 2 * Fp > 64:
             return None
-        words = ((E * LP + 3) & ~3) + N * LP + 256 + mcp_misc_words(2 * Fp)
+        NP = mcp_np()
+        threads += 32 * NP                                                  # decoding warps + producer warps
+        ring = (2 * Fp * (((N * z + 3) & ~3) // 2) + 3) & ~3 if NP else 0    # NMS_MCP_RING_WORDS
+        words = ((E * LP + 3) & ~3) + N * LP + ring + 256 + mcp_misc_words(2 * Fp)
+        if words * 4 > MAX_SMEM:
+            return None
         minb = max(1, min(MAX_SMEM // (words * 4 + 1024), 2048 // threads, 65536 // (threads * 56)))
         src = f"""// GENERATED by gen_spec.py -- do not edit.  Graph "{key}": {M}x{N}, z={z}, E={E}; persistent-slot Monte-Carlo geometry Fp={Fp} R={R}.
 #include "../nms_mcp.cuh"

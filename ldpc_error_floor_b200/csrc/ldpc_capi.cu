@@ -296,6 +296,7 @@ void fill_smem_layout_mc(KParams *P) {
     off = (off + 3) & ~3;
     P->off_xa = off; P->off_xq = off; off += P->N * P->LP;
     P->off_hb = off; P->off_et = off; P->off_et2 = off;
+    P->off_ring = off; off += (NMS_MCP_RING_WORDS(P->FB, P->N * P->z) + 3) & ~3;   // the producers' ring (8-byte rows)
     P->off_w = off; off += (P->w_words + 3) & ~3;      // the state block holds 64-bit counters
     P->off_misc = off; off += NMS_MCP_MISC_WORDS(P->FB);
     P->smem_words = off;
@@ -524,9 +525,9 @@ extern "C" int ldpc_decoder_create2(const ldpc_graph_t *g, const int32_t sharing
             const void *f = tab[k].func();
             LaunchGeom geo{};
             geo.Fp = tab[k].Fp; geo.FB = 2 * geo.Fp; geo.L = g->z * geo.Fp; geo.LP = (geo.L + 31) & ~31; geo.C = geo.LP / 32;
-            geo.R = tab[k].R; geo.threads = geo.C * geo.R * 32;
+            geo.R = tab[k].R; geo.threads = geo.C * geo.R * 32 + NMS_MCP_NP * 32;   // decoding warps + producer warps
             KParams tmp{};
-            tmp.E = g->E; tmp.N = g->N; tmp.LP = geo.LP; tmp.w_words = w_words; tmp.FB = geo.FB;
+            tmp.E = g->E; tmp.N = g->N; tmp.z = g->z; tmp.LP = geo.LP; tmp.w_words = w_words; tmp.FB = geo.FB;
             fill_smem_layout_mc(&tmp);
             geo.smem_bytes = tmp.smem_words * 4;
             if (geo.smem_bytes > 227 * 1024) continue;
@@ -558,10 +559,10 @@ extern "C" int ldpc_decoder_create2(const ldpc_graph_t *g, const int32_t sharing
             if (er && atoi(er) > 0) R = atoi(er);
             LaunchGeom geo{};
             geo.Fp = Fp; geo.FB = 2 * Fp; geo.L = g->z * Fp; geo.LP = (geo.L + 31) & ~31; geo.C = geo.LP / 32; geo.R = R;
-            geo.threads = geo.C * R * 32;
+            geo.threads = geo.C * R * 32 + (kind == NMS_JIT_MCP ? NMS_MCP_NP * 32 : 0);
             if (geo.C > 16 || geo.threads > 1024 || geo.FB > LDPC_MAX_FB) continue;
             KParams tmp{};
-            tmp.E = g->E; tmp.N = g->N; tmp.L = geo.L; tmp.LP = geo.LP; tmp.C = geo.C; tmp.qms = 1; tmp.no_xq = no_xq; tmp.FB = geo.FB;
+            tmp.E = g->E; tmp.N = g->N; tmp.z = g->z; tmp.L = geo.L; tmp.LP = geo.LP; tmp.C = geo.C; tmp.qms = 1; tmp.no_xq = no_xq; tmp.FB = geo.FB;
             tmp.w_words = w_words; tmp.w_staged = w_words > 0 && w_words <= NMS_WSTAGE_MAX_WORDS;
             if (kind == NMS_JIT_MCP) fill_smem_layout_mc(&tmp); else fill_smem_layout(&tmp, true, false);
             geo.smem_bytes = tmp.smem_words * 4;

@@ -89,6 +89,7 @@ struct KParams {
     float *uncor_buf; unsigned int *uncor_count; unsigned int uncor_cap; int harvest_mode;
     // shared-memory carve-up (word offsets; the message array always starts at word 0)
     int off_xa, off_xq, off_hb, off_et, off_et2, off_w, off_misc, smem_words;   // off_et (E + 1 words) / off_et2: float kernels only
+    int off_ring;      // persistent-slot kernels: the producers' ring of ready frames (NMS_MCP_RING_WORDS)
     // tables
     unsigned short row_ptr[LDPC_MAX_M + 1];   // E(C) edges of proto row i: [row_ptr[i], row_ptr[i+1])
     unsigned short col_ptr[LDPC_MAX_N + 1];   // CSR by proto column into vn_edge
@@ -123,6 +124,16 @@ extern "C" const NmsSpecEntry *nms_spec_f32q_table(int *count);   // quantised t
 extern "C" const NmsSpecEntry *nms_spec_mcp_table(int *count);    // persistent-slot Monte-Carlo kernels (nms_mcp.cuh)
 #endif
 #define NMS_MCP_MISC_WORDS(FB) (224 + (FB) * 16)   // their per-CTA state words: masks / per-pair words + 8 uint64 counters per slot
+// Producer warps of the persistent-slot kernels (warp specialisation): with NMS_MCP_NP > 0 that many extra warps run the
+// sample generator ahead into a ring of FB ready frames in shared memory while the other warps decode; 0 = the decoding warps
+// generate in their own loop.  Measured on B200 (profiles/r02_mc_sweep.txt, "producer warps"): one producer warp cannot keep up
+// (a single warp sustains ~0.3 IPC on the Philox chain: z72 at 7 dB 23 instead of 37 M frames/s); three are +2..3 % on z72,
+// -3..6 % on WiMAX and -10..18 % on MacKay at 4-6 dB (the ring costs shared memory, i.e. resident CTAs, and the all-warp
+// generator already runs at full issue rate) -- so the default stays 0.  One constant for host and device.
+#ifndef NMS_MCP_NP
+#define NMS_MCP_NP 0
+#endif
+#define NMS_MCP_RING_WORDS(FB, NZ) (NMS_MCP_NP > 0 ? (FB) * ((((NZ) + 3) & ~3) / 2) : 0)   // FB frames of NZ halves, 8-byte rows
 
 // ---- Philox4x32-10 (Salmon et al., SC'11), written out so the host tests can restate it
 __host__ __device__ __forceinline__ void philox4x32_10(uint32_t c0, uint32_t c1, uint32_t c2, uint32_t c3,

@@ -133,7 +133,7 @@ void nms_jit_pick_geometry(int M, int N, int E, int z, int kind, int max_dc, int
     const int max_smem = 227 * 1024, fp_max = 32;
     const int regs = std::min(128, std::max(56, (2 * max_dc + 40 + 7) & ~7));
     auto smem_of = [&](int LP, int C) {
-        const int words = kind == NMS_JIT_MCP ? ((E * LP + 3) & ~3) + N * LP + 256 + NMS_MCP_MISC_WORDS(64)
+        const int words = kind == NMS_JIT_MCP ? ((E * LP + 3) & ~3) + N * LP + 256 + NMS_MCP_MISC_WORDS(64) + NMS_MCP_RING_WORDS(LP / z * 2, N * z) + 4
                                               : ((E * LP + 3) & ~3) + N * LP * 2 + 4 * N * C + 256 + NMS_MISC_WORDS;
         return words * 4;
     };
@@ -174,7 +174,7 @@ std::string nms_jit_source(const int *proto, int M, int N, int z, int Fp, int R,
     for (int e = 0; e < E; ++e) col_ptr[col[e] + 1]++;
     for (int j = 0; j < N; ++j) col_ptr[j + 1] += col_ptr[j];
     for (int e = 0; e < E; ++e) col_edge[col_ptr[col[e]] + fill[col[e]]++] = e;
-    const int L = z * Fp, LP = (L + 31) & ~31, C = LP / 32, threads = C * R * 32;
+    const int L = z * Fp, LP = (L + 31) & ~31, C = LP / 32, threads = C * R * 32 + (kind == NMS_JIT_MCP ? NMS_MCP_NP * 32 : 0);
     std::vector<int> dc(M), dv(N), cn_order(M), vn_order(N);
     for (int i = 0; i < M; ++i) dc[i] = row_ptr[i + 1] - row_ptr[i];
     for (int j = 0; j < N; ++j) dv[j] = col_ptr[j + 1] - col_ptr[j];
@@ -195,7 +195,7 @@ std::string nms_jit_source(const int *proto, int M, int N, int z, int Fp, int R,
             cls_cnt.push_back(n);
         }
     const int max_smem = 227 * 1024;
-    const int words = kind == NMS_JIT_MCP ? ((E * LP + 3) & ~3) + N * LP + 256 + NMS_MCP_MISC_WORDS(2 * Fp)
+    const int words = kind == NMS_JIT_MCP ? ((E * LP + 3) & ~3) + N * LP + 256 + NMS_MCP_MISC_WORDS(2 * Fp) + NMS_MCP_RING_WORDS(2 * Fp, N * z) + 4
                                           : ((E * LP + 3) & ~3) + N * LP * 2 + 4 * N * C + 256 + NMS_MISC_WORDS;
     // registers: a check row of degree dc lives in dc registers plus the tournament's temporaries
     const int max_dc = *std::max_element(dc.begin(), dc.end());

@@ -36,6 +36,8 @@ constexpr int MCP_GE1 = 4;     // [2][2] slots whose frame is at iteration >= 1 
 constexpr int MCP_ATT = 8;     // [2][2] slots whose frame has used up its iterations: it stops whatever the syndrome says
 constexpr int MCP_ACT = 12;    // [2][2] slots that hold a frame
 constexpr int MCP_HMASK = 16;  // [2] slots whose frame is copied to the harvest buffer in this step
+constexpr int MCP_PROD = 20;   // frames of this CTA's share the producer warps have put into the ring so far
+constexpr int MCP_CONS = 21;   // ... and how many of them the decoding warps have taken out (their ring rows are free)
 constexpr int MCP_TP = 32;     // [2][32] per slot pair: iteration index of the low | high << 16 frame
 constexpr int MCP_CNT = 96;    // [2][32] per slot pair: ones in the counted columns of the last hard decision, low | high << 16
 constexpr int MCP_HROW = 160;  // [64] harvest row of the slot's frame
@@ -55,11 +57,27 @@ __device__ __forceinline__ void mload(const uint32_t *w, uint32_t &m) { m = w[0]
 __device__ __forceinline__ void mload(const uint32_t *w, unsigned long long &m) { m = (unsigned long long)w[0] | ((unsigned long long)w[1] << 32); }
 
 __device__ __forceinline__ void sts16(uint32_t a, unsigned short v) { asm volatile("st.shared.u16 [%0], %1;" ::"r"(a), "h"(v)); }
+__device__ __forceinline__ void sts64u(uint32_t a, uint32_t lo, uint32_t hi) { asm volatile("st.shared.v2.u32 [%0], {%1, %2};" ::"r"(a), "r"(lo), "r"(hi)); }
+__device__ __forceinline__ unsigned short lds16(uint32_t a) {
+    unsigned short v;
+    asm volatile("ld.shared.u16 %0, [%1];" : "=h"(v) : "r"(a));
+    return v;
+}
+__device__ __forceinline__ uint32_t ld_flag(const uint32_t *p) { return *reinterpret_cast<const volatile uint32_t *>(p); }
+__device__ __forceinline__ void st_flag(uint32_t *p, uint32_t v) { *reinterpret_cast<volatile uint32_t *>(p) = v; }
+// barrier among the first `n` threads of the CTA (the decoding warps) / among the producer warps: named barriers 1 and 2
+template <int N> __device__ __forceinline__ void bar_named(int id) { asm volatile("bar.sync %0, %1;" ::"r"(id), "n"(N) : "memory"); }
 
 template <class G>
 struct McpKernel {
     static constexpr int FB = 2 * G::Fp;
-    static constexpr int NTHR = G::C * G::R * 32;
+    static constexpr int NTHR = G::C * G::R * 32;      // decoding threads (threads NTHR .. NTHR + 32 NP - 1 are the producers)
+    static constexpr int NP = NMS_MCP_NP;
+    static constexpr int RS = ((G::N * G::z + 3) & ~3);  // halves per ring row
+    static __device__ __forceinline__ void cbar() {     // barrier of the decoding warps
+        if constexpr (NP > 0) bar_named<NTHR>(1);
+        else __syncthreads();
+    }
     static constexpr uint32_t LP4 = G::LP * 4u;
     static constexpr bool PAD = G::L != G::LP;
     static constexpr int NZ = G::N * G::z;
@@ -118,6 +136,69 @@ struct McpKernel {
                     if (NZ % 4 == 0 || k < NZ) sts16(base + (uint32_t)(j * G::LP + a * G::Fp) * 4u, __half_as_ushort(__float2half_rn(x)));
                     if (++a == G::z) { a = 0; ++j; }
                 }
+            }
+        }
+    }
+
+    // ------------------------------------------------------------------------------------------ producer warps
+    // The sample generator as its own warps: frame i of the CTA's share (global frame lo + i) goes into ring row i % FB as
+    // NZ halves in bit order, as soon as that row is free; MCP_PROD / MCP_CONS are the two ends of the ring.  Same samples
+    // as generate() (and everyone else): gen_normal4 of (global frame, quad).
+    static __device__ __forceinline__ void produce(const KParams &P, uint32_t sb, unsigned long long lo, uint32_t total) {
+        uint32_t *misc = nms_smem + P.off_misc;
+        const int ptid = threadIdx.x - NTHR;
+        const unsigned short hneg = __half_as_ushort(__float2half_rn(-P.qmax));
+        const uint32_t hneg2 = (uint32_t)hneg | ((uint32_t)hneg << 16);
+        for (uint32_t i = 0; i < total; ++i) {
+            while ((int)(i - ld_flag(&misc[MCP_CONS])) >= FB) __nanosleep(100);       // ring full: the decoders are busy
+            const unsigned long long F = P.frame_offset + lo + i;
+            const uint32_t row = sb + (uint32_t)P.off_ring * 4u + (uint32_t)(i % FB) * (uint32_t)(RS * 2);
+            for (int quad = ptid; quad < NQUADS; quad += NP * 32) {
+                const int k1 = 4 * quad + 1;                                           // 1-based index of the quad's first bit
+                const bool inp = P.punct_s > 0 && k1 + 3 >= P.punct_s && k1 <= P.punct_e;
+                const bool ins = P.short_s > 0 && k1 + 3 >= P.short_s && k1 <= P.short_e;
+                uint32_t w0, w1;
+                if (!(inp || ins)) {                                                   // four plain samples
+                    float n[4];
+                    gen_normal4(P, F, quad, n);
+                    w0 = h2u(__floats2half2_rn(llr_from_normal(P, n[0]), llr_from_normal(P, n[1])));
+                    w1 = h2u(__floats2half2_rn(llr_from_normal(P, n[2]), llr_from_normal(P, n[3])));
+                } else if (P.punct_s > 0 && k1 >= P.punct_s && k1 + 3 <= P.punct_e) {
+                    w0 = w1 = 0u;                                                      // punctured: no sample needed
+                } else if (P.short_s > 0 && k1 >= P.short_s && k1 + 3 <= P.short_e) {
+                    w0 = w1 = hneg2;                                                   // shortened: Q(-clip_LLR)
+                } else {                                                               // a quad across a range boundary
+                    float v[4];
+                    gen_llr4(P, F, quad, v);
+#pragma unroll
+                    for (int k4 = 0; k4 < 4; ++k4) v[k4] = fminf(fmaxf(v[k4], -P.qmax), P.qmax);
+                    w0 = h2u(__floats2half2_rn(v[0], v[1]));
+                    w1 = h2u(__floats2half2_rn(v[2], v[3]));
+                }
+                sts64u(row + (uint32_t)quad * 8u, w0, w1);
+            }
+            __threadfence_block();
+            if constexpr (NP > 1) bar_named<NP * 32>(2);
+            else __syncwarp();
+            if (ptid == 0) st_flag(&misc[MCP_PROD], i + 1u);
+        }
+    }
+
+    // decoding warps: move the frames entering the slots in `fresh` (rank r -> frame `rel` + r of the CTA's share) from the
+    // ring into the xq array; waits for the producers if they are behind
+    static __device__ __forceinline__ void take(const KParams &P, uint32_t sb, mask_t fresh, uint32_t rel) {
+        uint32_t *misc = nms_smem + P.off_misc;
+        const uint32_t need = rel + (uint32_t)mpopc(fresh);
+        while (ld_flag(&misc[MCP_PROD]) < need) { }
+        __threadfence_block();
+        uint32_t i = rel;
+        for (mask_t m = fresh; m != 0; m &= m - 1, ++i) {
+            const int f = mffs(m) - 1;
+            const uint32_t row = sb + (uint32_t)P.off_ring * 4u + (i % FB) * (uint32_t)(RS * 2);
+            const uint32_t base = sb + (uint32_t)P.off_xq * 4u + (uint32_t)(f >> 1) * 4u + (uint32_t)(f & 1) * 2u;
+            for (int k = threadIdx.x; k < NZ; k += NTHR) {
+                const int j = k / G::z, a = k - j * G::z;
+                sts16(base + (uint32_t)(j * G::LP + a * G::Fp) * 4u, lds16(row + (uint32_t)k * 2u));
             }
         }
     }
@@ -200,15 +281,22 @@ struct McpKernel {
         const unsigned long long nfr = (unsigned long long)P.n_frames;
         const unsigned long long lo = nfr * blockIdx.x / gridDim.x, hi = nfr * (blockIdx.x + 1ull) / gridDim.x;
 
-        for (int idx = tid; idx < P.w_words; idx += NTHR) smem_f(P.off_w + idx) = __ldg(P.w_all + idx);
-        for (int idx = tid; idx < P.off_w; idx += NTHR) nms_smem[idx] = 0u;          // messages and channel values: finite
-        for (int idx = tid; idx < NMS_MCP_MISC_WORDS(FB); idx += NTHR) misc[idx] = 0u;
+        constexpr int NALL = NTHR + NP * 32;
+        for (int idx = tid; idx < P.w_words; idx += NALL) smem_f(P.off_w + idx) = __ldg(P.w_all + idx);
+        for (int idx = tid; idx < P.off_w; idx += NALL) nms_smem[idx] = 0u;          // messages, channel values, ring: finite
+        for (int idx = tid; idx < NMS_MCP_MISC_WORDS(FB); idx += NALL) misc[idx] = 0u;
         unsigned long long next = lo;                                                  // first frame not yet in a slot
         mask_t fresh = (hi - lo) >= (unsigned long long)FB ? FBMASK : (((mask_t)1 << (int)(hi - lo)) - 1);
         unsigned long long first = next;                                               // frame of the lowest refilled slot
         next += (unsigned long long)mpopc(fresh);
         mask_t empty = ~fresh & FBMASK;
-        __syncthreads();
+        __syncthreads();                                  // the only barrier all warps share
+        if constexpr (NP > 0) {
+            if (tid >= NTHR) {                            // producer warps: nothing but samples from here on
+                produce(P, h.sb, lo, (uint32_t)(hi - lo));
+                return;
+            }
+        }
         if (tid == 0) {
             misc[MCP_ACT] = (uint32_t)fresh;
             if constexpr (WIDE) misc[MCP_ACT + 1] = (uint32_t)((unsigned long long)fresh >> 32);
@@ -224,8 +312,17 @@ struct McpKernel {
         for (int s = 0;; ++s) {
             const int p = s & 1;
             if (fresh != 0) {
-                generate(P, h.sb, fresh, first);
-                __syncthreads();
+                if constexpr (NP > 0) {
+                    take(P, h.sb, fresh, (uint32_t)(first - lo));
+                    cbar();
+                    if (tid == 0) {                       // those ring rows are free (every copy out of them is behind the barrier)
+                        __threadfence_block();
+                        st_flag(&misc[MCP_CONS], (uint32_t)(first - lo) + (uint32_t)mpopc(fresh));
+                    }
+                } else {
+                    generate(P, h.sb, fresh, first);
+                    cbar();
+                }
             }
             // ================================================================ VN phase
             {
@@ -265,7 +362,7 @@ struct McpKernel {
                     }
                 }
             }
-            __syncthreads();
+            cbar();
             // ================================================================ CN phase
             {
                 const uint32_t tp = misc[MCP_TP + p * 32 + fp];
@@ -280,7 +377,7 @@ struct McpKernel {
                     if (lane == 0 && r1) atomicOr(&misc[MCP_SYND + p * 2 + 1], r1);
                 }
             }
-            __syncthreads();
+            cbar();
             // ================================================================ who stops, who enters
             mask_t sbad, actm, ge1m, attm;
             mload(misc + MCP_SYND + p * 2, sbad); mload(misc + MCP_ACT + p * 2, actm);
@@ -339,7 +436,7 @@ struct McpKernel {
             }
             // harvest: the stopped frames' channel values leave before the generator overwrites them
             if (P.harvest_mode != 0 && fin != 0 && P.uncor_buf != nullptr) {
-                __syncthreads();
+                cbar();
                 mask_t hm;
                 mload(misc + MCP_HMASK, hm);
                 if (hm != 0) {
@@ -354,7 +451,7 @@ struct McpKernel {
                             row[k] = v;
                         }
                     }
-                    __syncthreads();
+                    cbar();
                 }
             }
             empty = (empty | fin) & ~enter;
