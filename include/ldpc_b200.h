@@ -160,12 +160,48 @@ int ldpc_decode(const ldpc_decoder_t *d, const float *llr_dev, int64_t B, int32_
                 int32_t early_term, float *app_dev, int32_t app_all_iters, uint32_t *hard_dev,
                 int32_t *iters_dev, uint8_t *flags_dev, int32_t *biterr_dev, void *stream);
 
-/* Same with HOST buffers: pinned or pageable host memory in and out, chunked over two
- * streams so copies overlap compute; synchronous.  This is the end-to-end call. */
+/* Same with HOST buffers: pinned or pageable host memory in and out, chunked over four
+ * streams so copies overlap compute; synchronous.  This is the end-to-end call: what a reference
+ * maintainer binds in place of sess.run(..., feed_dict={xa_input: ...}) (Print_Functions.py:148-150).
+ * float32 words are the bound of this path (PCIe), so for a quantised decoder the library's host
+ * threads pack part of the chunks to int8 (one byte per value) while the others travel as they are:
+ * same decoder input bit for bit -- a quantised decoder sees a channel value only through Q(x)
+ * (Main_Functions.py:321-322) and, with VN weights, Q(x * w) (:168-177), so words are packed always
+ * without VN weights and, with them, whenever every value of the chunk is on the quantiser grid
+ * (always, in the reference's flows).  LDPC_B200_NO_HOST_PACK=1 keeps float32 for every chunk,
+ * LDPC_B200_HOST_THREADS sets the pool size (default: hardware threads / LOCAL_WORLD_SIZE, <= 16). */
 int ldpc_decode_host(const ldpc_decoder_t *d, const float *llr_host, int64_t B, int32_t iters,
                      int32_t early_term, float *app_host, int32_t app_all_iters,
                      uint32_t *hard_host, int32_t *iters_host, uint8_t *flags_host,
                      int32_t *biterr_host);
+
+/* What the last ldpc_decode_host / ldpc_decode_q8_host call on this handle did. */
+typedef struct {
+    int32_t threads;            /* host threads that packed / staged */
+    int32_t chunks_q8;          /* chunks that crossed PCIe as int8 */
+    int32_t chunks_f32;         /* chunks that crossed as float32 by choice (DMA engine and cores share the load) */
+    int32_t chunks_unencodable; /* chunks that crossed as float32 because a value has no int8 form */
+    double float_share;         /* share of float32 chunks the next call starts with */
+    double s_pack;      /* feeder thread: packing / staging (seconds) */
+    double s_wait;      /* calling thread: waiting for the device */
+    double s_wait_feed; /* calling thread: waiting for the feeder */
+    double s_copy_out;  /* calling thread: handing results to the caller */
+    double s_total;     /* the whole call */
+    int64_t h2d_bytes, d2h_bytes;               /* bytes actually copied */
+} ldpc_host_stats_t;
+int ldpc_decode_host_stats(const ldpc_decoder_t *d, ldpc_host_stats_t *out);
+
+/* The packing pass on its own (pack once, decode many times with ldpc_decode_q8_host; no GPU work):
+ * q8_host[i] = k with k * ldpc_decoder_q8_step(d) the decoder's view of llr_host[i]; *n_unencodable = values
+ * that have no such k (always 0 for decoders without VN weights; off-grid or out-of-range values otherwise).
+ * LDPC_E_UNSUPPORTED for float decoders and q_bit 6 (saturates off its grid). */
+int ldpc_pack_q8_host(const ldpc_decoder_t *d, const float *llr_host, int64_t B, int8_t *q8_host,
+                      int64_t *n_unencodable);
+/* The same pass without a handle (step = 1/qk and qmax of Main_Functions.py:483-492; qmax / step <= 127).
+ * lossless = 0: q8 = Q(x) / step for every x (NaN -> -qmax, as the kernels' clamp does); lossless = 1: only
+ * values that are on the grid and inside +-qmax count as encodable. */
+int ldpc_pack_q8_values(const float *x, int64_t n, float step, float qmax, int32_t lossless, int8_t *q8,
+                        int64_t *n_unencodable);
 
 /* ---- non-zero codewords ("next" row N3 of SURVEY.md 8f) ----------------------------------------
  * The reference can train / evaluate on random codewords Y = infoWord . code_GM mod 2 (Print_Functions.py:40-46 with

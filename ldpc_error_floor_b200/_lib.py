@@ -67,6 +67,9 @@ SYMBOLS = {
     "ldpc_decoder_q8_step": (ctypes.c_float, [_P]),
     "ldpc_decode_q8": (ctypes.c_int, [_P, _P, ctypes.c_float, _I64, _I32, _I32, _P, _P, _P, _P, _P, _P]),
     "ldpc_decode_q8_host": (ctypes.c_int, [_P, _P, ctypes.c_float, _I64, _I32, _I32, _P, _P, _P, _P]),
+    "ldpc_decode_host_stats": (ctypes.c_int, [_P, _P]),
+    "ldpc_pack_q8_host": (ctypes.c_int, [_P, _P, _I64, _P, _P]),
+    "ldpc_pack_q8_values": (ctypes.c_int, [_P, _I64, ctypes.c_float, ctypes.c_float, _I32, _P, _P]),
     "ldpc_llr_generate": (ctypes.c_int, [_P, ctypes.c_double, _I64, _U64, _U64, _P, _P]),
     "ldpc_normal_probe": (ctypes.c_int, [_I32, _U64, _U64, _I64, _I32, _P, _P, _P]),
     "ldpc_mc_run": (ctypes.c_int, [_P, ctypes.c_double, _I64, _U64, _U64, _I32, _I32, _I32, _P, _P, _P, _U32, _P]),
@@ -116,6 +119,29 @@ def check(rc: int) -> None:
 
 
 ALU_PROBE_KINDS = {"ffma": 0, "fmnmx": 1, "lop3": 2, "iadd": 3, "hfma2": 4, "hmnmx2": 5, "fadd": 6}
+
+
+class HostStats(ctypes.Structure):
+    """ldpc_host_stats_t (include/ldpc_b200.h)."""
+    _fields_ = [("threads", ctypes.c_int32), ("chunks_q8", ctypes.c_int32), ("chunks_f32", ctypes.c_int32),
+                ("chunks_unencodable", ctypes.c_int32), ("float_share", ctypes.c_double), ("s_pack", ctypes.c_double),
+                ("s_wait", ctypes.c_double), ("s_wait_feed", ctypes.c_double), ("s_copy_out", ctypes.c_double), ("s_total", ctypes.c_double),
+                ("h2d_bytes", ctypes.c_int64), ("d2h_bytes", ctypes.c_int64)]
+
+    def as_dict(self) -> dict:
+        return {name: getattr(self, name) for name, _ in self._fields_}
+
+
+def pack_q8_values(x, step: float, qmax: float, lossless: bool):
+    """ldpc_pack_q8_values: float32 values -> int8 multiples of `step` (host threads, no GPU).  Returns (int8 array of
+    x's shape, number of values without an int8 form)."""
+    import numpy as np
+    x = np.ascontiguousarray(x, dtype=np.float32)
+    out = np.empty(x.shape, dtype=np.int8)
+    bad = ctypes.c_int64(0)
+    check(load().ldpc_pack_q8_values(x.ctypes.data, x.size, float(step), float(qmax), 1 if lossless else 0,
+                                     out.ctypes.data, ctypes.byref(bad)))
+    return out, int(bad.value)
 
 
 def jit_prebuild(proto, z: int) -> int:

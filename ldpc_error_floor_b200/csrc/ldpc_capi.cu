@@ -8,8 +8,11 @@
 #include "nms_common.cuh"
 #include "nms_train.cuh"
 #include "nms_jit.h"
+#include "host_pack.h"
 
 #include <algorithm>
+#include <atomic>
+#include <chrono>
 #include <cmath>
 #include <cstdarg>
 #include <cstdio>
@@ -78,27 +81,35 @@ struct ldpc_graph {
     ldpc_graph_info_t info{};
 };
 
+constexpr int HOST_SLOTS = 4;   // chunks in flight per ldpc_decode_host call (device buffers, stream, pinned staging each)
+
 struct HostScratch {
     size_t cap_frames = 0;
     bool with_app = false;
     int app_iters = 0;
-    float *llr[2] = {nullptr, nullptr};
-    float *app[2] = {nullptr, nullptr};
-    uint32_t *hard[2] = {nullptr, nullptr};
-    int *iters[2] = {nullptr, nullptr};
-    uint8_t *flags[2] = {nullptr, nullptr};
-    int *biterr[2] = {nullptr, nullptr};
+    float *llr[HOST_SLOTS] = {};      // float32 words of a chunk, or (same buffer) its int8 form
+    float *app[HOST_SLOTS] = {};
+    uint32_t *hard[HOST_SLOTS] = {};
+    int *iters[HOST_SLOTS] = {};
+    uint8_t *flags[HOST_SLOTS] = {};
+    int *biterr[HOST_SLOTS] = {};
     // pinned host staging of the per-frame outputs, so the device-to-host copies stay asynchronous even when
-    // the caller's result arrays are pageable (one blocking copy would serialise the two-stream pipeline)
-    uint32_t *h_hard[2] = {nullptr, nullptr};
-    int *h_iters[2] = {nullptr, nullptr};
-    uint8_t *h_flags[2] = {nullptr, nullptr};
-    int *h_biterr[2] = {nullptr, nullptr};
-    cudaStream_t st[2] = {nullptr, nullptr};
-    // pinned staging of the INPUT words for callers that pass pageable memory (numpy arrays): a few host threads copy the
-    // next chunk in while the device works on the current one, instead of the driver's synchronous staged copy
-    char *h_in[2] = {nullptr, nullptr};
+    // the caller's result arrays are pageable (one blocking copy would serialise the pipeline)
+    // (two per slot, used alternately: the results of a slot's previous chunk are handed over AFTER its next chunk has been
+    // issued, so that copy is never between the device and its next piece of work)
+    uint32_t *h_hard[2 * HOST_SLOTS] = {};
+    int *h_iters[2 * HOST_SLOTS] = {};
+    uint8_t *h_flags[2 * HOST_SLOTS] = {};
+    int *h_biterr[2 * HOST_SLOTS] = {};
+    cudaStream_t st[HOST_SLOTS] = {};
+    cudaEvent_t ev_h2d[HOST_SLOTS] = {};   // recorded behind the host-to-device copy of the slot's current chunk
+    // pinned staging of the INPUT words: the int8 form the host threads pack a float32 chunk into (one byte per value), or
+    // the float32 words themselves for callers that pass pageable memory and words that have no int8 form
+    char *h_in[HOST_SLOTS] = {};
     size_t h_in_bytes = 0;
+    // share of the chunks that travel as float32 while the host threads pack the others (adapted from call to call)
+    double float_share = 0.25;
+    ldpc_host_stats_t stats{};
     unsigned long long *counters = nullptr;
     unsigned int *ucount = nullptr;
     float *ubuf = nullptr;
@@ -697,12 +708,15 @@ extern "C" int ldpc_decoder_create2(const ldpc_graph_t *g, const int32_t sharing
 
 namespace {
 void free_scratch(HostScratch &h) {
-    for (int i = 0; i < 2; ++i) {
+    for (int i = 0; i < HOST_SLOTS; ++i) {
         cudaFree(h.llr[i]); cudaFree(h.app[i]); cudaFree(h.hard[i]); cudaFree(h.iters[i]);
         cudaFree(h.flags[i]); cudaFree(h.biterr[i]);
-        cudaFreeHost(h.h_hard[i]); cudaFreeHost(h.h_iters[i]); cudaFreeHost(h.h_flags[i]); cudaFreeHost(h.h_biterr[i]);
+        for (int j = i; j < 2 * HOST_SLOTS; j += HOST_SLOTS) {
+            cudaFreeHost(h.h_hard[j]); cudaFreeHost(h.h_iters[j]); cudaFreeHost(h.h_flags[j]); cudaFreeHost(h.h_biterr[j]);
+        }
         cudaFreeHost(h.h_in[i]);
         if (h.st[i]) cudaStreamDestroy(h.st[i]);
+        if (h.ev_h2d[i]) cudaEventDestroy(h.ev_h2d[i]);
     }
     cudaFree(h.counters); cudaFree(h.ucount); cudaFree(h.ubuf);
     h = HostScratch();
@@ -891,36 +905,94 @@ int ensure_host_scratch(ldpc_decoder *d, size_t chunk, bool with_app, int app_it
     HostScratch &h = d->hs;
     if (h.cap_frames >= chunk && (!with_app || (h.with_app && h.app_iters >= app_iters))) return LDPC_OK;
     unsigned long long *cnt = h.counters; unsigned int *uc = h.ucount; float *ub = h.ubuf; size_t ur = h.ubuf_rows;
+    const double share = h.float_share;
     h.counters = nullptr; h.ucount = nullptr; h.ubuf = nullptr;
     free_scratch(h);
-    h.counters = cnt; h.ucount = uc; h.ubuf = ub; h.ubuf_rows = ur;
+    h.counters = cnt; h.ucount = uc; h.ubuf = ub; h.ubuf_rows = ur; h.float_share = share;
     const KParams &P = d->base;
-    for (int i = 0; i < 2; ++i) {
+    for (int i = 0; i < HOST_SLOTS; ++i) {
         CUDA_TRY(cudaStreamCreateWithFlags(&h.st[i], cudaStreamNonBlocking));
+        CUDA_TRY(cudaEventCreateWithFlags(&h.ev_h2d[i], cudaEventDisableTiming));
         CUDA_TRY(cudaMalloc(&h.llr[i], chunk * P.NZ * sizeof(float)));
         CUDA_TRY(cudaMalloc(&h.hard[i], chunk * P.HW * sizeof(uint32_t)));
         CUDA_TRY(cudaMalloc(&h.iters[i], chunk * sizeof(int)));
         CUDA_TRY(cudaMalloc(&h.flags[i], chunk));
         CUDA_TRY(cudaMalloc(&h.biterr[i], chunk * sizeof(int)));
-        CUDA_TRY(cudaMallocHost(&h.h_hard[i], chunk * P.HW * sizeof(uint32_t)));
-        CUDA_TRY(cudaMallocHost(&h.h_iters[i], chunk * sizeof(int)));
-        CUDA_TRY(cudaMallocHost(&h.h_flags[i], chunk));
-        CUDA_TRY(cudaMallocHost(&h.h_biterr[i], chunk * sizeof(int)));
+        for (int j = i; j < 2 * HOST_SLOTS; j += HOST_SLOTS) {
+            CUDA_TRY(cudaMallocHost(&h.h_hard[j], chunk * P.HW * sizeof(uint32_t)));
+            CUDA_TRY(cudaMallocHost(&h.h_iters[j], chunk * sizeof(int)));
+            CUDA_TRY(cudaMallocHost(&h.h_flags[j], chunk));
+            CUDA_TRY(cudaMallocHost(&h.h_biterr[j], chunk * sizeof(int)));
+        }
         if (with_app) CUDA_TRY(cudaMalloc(&h.app[i], (size_t)app_iters * chunk * P.NZ * sizeof(float)));
     }
     h.cap_frames = chunk; h.with_app = with_app; h.app_iters = app_iters;
     return LDPC_OK;
 }
-}   // namespace
 
-namespace {
+int ensure_host_staging(HostScratch &h, size_t bytes) {
+    if (h.h_in_bytes >= bytes) return LDPC_OK;
+    for (int i = 0; i < HOST_SLOTS; ++i) { cudaFreeHost(h.h_in[i]); h.h_in[i] = nullptr; }
+    h.h_in_bytes = 0;
+    for (int i = 0; i < HOST_SLOTS; ++i) CUDA_TRY(cudaMallocHost(&h.h_in[i], bytes));
+    h.h_in_bytes = bytes;
+    return LDPC_OK;
+}
+
+// Can float32 words of this decoder cross PCIe as int8?  0: no; 1: always (the decoder sees the channel value only through
+// Q(x)); 2: when the words are on the quantiser grid already (VN weights also form Q(x * w) from the raw value).
+int host_pack_mode(const ldpc_decoder *d, float *qk, float *kmax) {
+    if (d->decoding_type != 2 || d->q_bit == 6 || env_on("LDPC_B200_NO_HOST_PACK")) return 0;   // q_bit 6 saturates at 15.5: off its grid
+    const float step = d->q_bit == 5 ? 0.5f : (d->q_bit == 3 ? 2.0f : 1.0f);
+    *qk = 1.0f / step;
+    *kmax = d->base.qmax / step;
+    return d->sharing[2] == 0 ? 1 : 2;
+}
+
+double now_s() {
+    using clk = std::chrono::steady_clock;
+    return std::chrono::duration<double>(clk::now().time_since_epoch()).count();
+}
+
+bool host_ptr_pageable(const void *p) {
+    cudaPointerAttributes attr;
+    if (cudaPointerGetAttributes(&attr, p) != cudaSuccess) { cudaGetLastError(); return true; }
+    return attr.type == cudaMemoryTypeUnregistered;
+}
+
+// The host-buffer pipeline.  A call is cut into chunks (a few waves of CTAs, ~32 MiB of float32 words; the first ones
+// shorter so the device starts early); chunk c uses slot c mod HOST_SLOTS (device buffers, stream, pinned staging), so up
+// to HOST_SLOTS - 1 chunks are queued on the device while the host prepares the next ones.  float32 words of a quantised
+// decoder cross PCIe in one of two forms, chosen per chunk:
+//   * as they are (DMA straight from the caller's pinned memory: no host work, 4 bytes per value), or
+//   * packed to int8 by the host threads (host_pack.cpp: 1 byte per value) -- the same decoder input bit for bit.
+// PCIe bounds the first form (the decoder is ~2x faster than 55 GB/s of float32 words), the host's cores the second, and the
+// two resources work side by side: `float_share` of the chunks goes the first way, the others the second.
+// Two host threads drive a call: a FEEDER prepares chunks ahead (decides the form, packs / stages into the slot's pinned
+// buffer as soon as the copy that last read it has completed -- an event, not the whole stream), the CALLING thread waits
+// for a slot's previous results, hands them to the caller, and issues copy + kernel + result copies for the next prepared
+// chunk.  The share follows what the calling thread waits for: the feeder -> leave more chunks to the DMA engine; the
+// device -> pack more.  Pageable input is always packed (reading it is the cost either way) unless it has no int8 form;
+// then the same threads stage it through pinned memory.
+struct HostFeed {
+    enum : int { PENDING = 0, DIRECT_F32, DIRECT_Q8, STAGED_F32, STAGED_Q8, FAILED };
+    std::vector<std::atomic<int>> state;            // per chunk: how the calling thread finds its words
+    std::atomic<long long> issued[HOST_SLOTS];      // copies issued from slot r's staging buffer so far
+    std::atomic<double> share{0.0};
+    std::atomic<bool> abort{false};
+    std::atomic<int> chunks_q8{0}, chunks_unencodable{0};
+    double s_pack = 0.0;
+    explicit HostFeed(size_t n) : state(n) {
+        for (auto &x : state) x.store(PENDING, std::memory_order_relaxed);
+        for (auto &x : issued) x.store(0, std::memory_order_relaxed);
+    }
+};
+
 int decode_host_impl(const ldpc_decoder_t *dc, const void *src_host, bool q8, float step, int64_t B, int32_t iters,
                      int32_t early_term, float *app_host, int32_t app_all_iters, uint32_t *hard_host,
                      int32_t *iters_host, uint8_t *flags_host, int32_t *biterr_host) {
     ldpc_decoder *d = const_cast<ldpc_decoder *>(dc);
-    const float *llr_host = (const float *)src_host;
-    const size_t elem = q8 ? 1 : sizeof(float);
-    if (!d || (!llr_host && B > 0) || B < 0) return fail(LDPC_E_INVALID, "decode_host: bad arguments");
+    if (!d || (!src_host && B > 0) || B < 0) return fail(LDPC_E_INVALID, "decode_host: bad arguments");
     if (q8 && step == 0.0f) step = quantiser_step(d);
     if (q8 && !(step > 0.0f)) return fail(LDPC_E_INVALID, "decode_q8_host: step must be positive for a float decoder");
     if (iters < 0 || iters > d->T) return fail(LDPC_E_INVALID, "decode_host: iters %d outside 0..%d", iters, d->T);
@@ -928,95 +1000,222 @@ int decode_host_impl(const ldpc_decoder_t *dc, const void *src_host, bool q8, fl
     DeviceGuard guard(d->device);
     if (!guard.ok) return fail(LDPC_E_CUDA, "cudaSetDevice(%d) failed", d->device);
     std::lock_guard<std::mutex> lock(d->mu);
+    const double t_begin = now_s();
     const KParams &P0 = d->base;
+    const size_t NZ = (size_t)P0.NZ;
     const int T_run = iters == 0 ? d->T : iters;
     const int app_iters = app_host ? (app_all_iters ? T_run : 1) : 0;
-    // chunk: a multiple of the frames one full wave of CTAs decodes, ~32 MiB of LLRs
-    const size_t wave = (size_t)d->sm_count * d->geom.ctas_per_sm * P0.FB;
-    size_t chunk = std::max<size_t>(wave, ((32u << 20) / (P0.NZ * sizeof(float)) / wave) * wave);
+    const bool use_alt = d->func_alt != nullptr && !early_term;
+    const LaunchGeom &geo = use_alt ? d->geom_alt : d->geom;
+    const int FBg = use_alt ? d->base_alt.FB : P0.FB;
+    const size_t wave = (size_t)d->sm_count * geo.ctas_per_sm * FBg;
+    size_t chunk = std::max<size_t>(wave, ((32u << 20) / (NZ * sizeof(float)) / wave) * wave);
     if (app_iters) chunk = wave;
-    chunk = std::min<size_t>(chunk, ((size_t)B + P0.FB - 1) / P0.FB * P0.FB);
+    chunk = std::min<size_t>(chunk, ((size_t)B + FBg - 1) / FBg * FBg);
     int rc = ensure_host_scratch(d, chunk, app_iters > 0, app_iters);
     if (rc != LDPC_OK) return rc;
     HostScratch &h = d->hs;
-    // results of the chunk that last used buffer pair k: staged in pinned memory, handed to the caller once
-    // stream k has drained (which the next use of pair k, two chunks later, has to wait for anyway)
-    int64_t pend_off[2] = {0, 0}, pend_n[2] = {0, 0};
-    auto drain = [&](int k) -> int {
-        CUDA_TRY(cudaStreamSynchronize(h.st[k]));
-        const int64_t off = pend_off[k], nb = pend_n[k];
-        if (nb > 0) {
-            if (hard_host) std::memcpy(hard_host + off * P0.HW, h.h_hard[k], (size_t)nb * P0.HW * 4);
-            if (iters_host) std::memcpy(iters_host + off, h.h_iters[k], (size_t)nb * 4);
-            if (flags_host) std::memcpy(flags_host + off, h.h_flags[k], (size_t)nb);
-            if (biterr_host) std::memcpy(biterr_host + off, h.h_biterr[k], (size_t)nb * 4);
+
+    float qk = 1.0f, kmax = 0.0f;
+    const int pack_mode = (q8 || app_iters) ? 0 : host_pack_mode(d, &qk, &kmax);
+    const bool pageable = host_ptr_pageable(src_host);
+    const size_t elem = q8 ? 1 : sizeof(float);
+    if (pack_mode || pageable) {
+        rc = ensure_host_staging(h, chunk * NZ * ((pageable && !q8) ? sizeof(float) : 1));
+        if (rc != LDPC_OK) return rc;
+    }
+    // the chunks of this call
+    std::vector<int64_t> c_off, c_n;
+    for (int64_t off = 0; off < B;) {
+        const int64_t nb = std::min<int64_t>((int64_t)std::min(chunk, wave * (c_off.size() + 1)), B - off);
+        c_off.push_back(off); c_n.push_back(nb);
+        off += nb;
+    }
+    const int nchunks = (int)c_off.size();
+    ldpc_host_stats_t stats{};
+    HostFeed feed((size_t)nchunks);
+    feed.share.store(pageable ? 0.0 : h.float_share);
+    const bool threaded = pack_mode != 0 || pageable;
+    stats.threads = threaded ? hostpack::pool_threads() : 1;
+
+    // ---- feeder: chunk c -> (form, where its words are)
+    auto feeder = [&]() {
+        if (cudaSetDevice(d->device) != cudaSuccess) { cudaGetLastError(); }
+        double credit = 0.5;
+        int unencodable_run = 0;
+        for (int c = 0; c < nchunks; ++c) {
+            const int r = c % HOST_SLOTS;
+            const char *src = (const char *)src_host + (size_t)c_off[c] * NZ * elem;
+            const size_t nval = (size_t)c_n[c] * NZ;
+            bool want_pack = false;
+            if (pack_mode && unencodable_run < 2) {
+                credit += 1.0 - feed.share.load(std::memory_order_relaxed);   // error diffusion over the chunks
+                if (credit >= 1.0) { credit -= 1.0; want_pack = true; }
+            }
+            int result = q8 ? HostFeed::DIRECT_Q8 : HostFeed::DIRECT_F32;
+            if (want_pack || pageable) {
+                // the staging buffer of slot r is free once the copy that last read it has completed
+                const long long need = c / HOST_SLOTS;
+                for (int spin = 0; feed.issued[r].load(std::memory_order_acquire) < need; ++spin) {
+                    if (feed.abort.load(std::memory_order_relaxed)) return;
+                    if (spin > 200) std::this_thread::yield();
+                }
+                if (need > 0 && cudaEventSynchronize(h.ev_h2d[r]) != cudaSuccess) {
+                    cudaGetLastError();
+                    feed.state[c].store(HostFeed::FAILED, std::memory_order_release);
+                    return;
+                }
+                const double t0 = now_s();
+                if (want_pack) {
+                    const int64_t bad = hostpack::pack_q8_mt((const float *)src, (int64_t)nval, qk, kmax, pack_mode == 2,
+                                                             (int8_t *)h.h_in[r], true);
+                    if (bad == 0) { result = HostFeed::STAGED_Q8; unencodable_run = 0; feed.chunks_q8.fetch_add(1); }
+                    else { ++unencodable_run; feed.chunks_unencodable.fetch_add(1); want_pack = false; }
+                }
+                if (!want_pack && pageable) {
+                    hostpack::memcpy_mt(h.h_in[r], src, nval * elem);
+                    result = q8 ? HostFeed::STAGED_Q8 : HostFeed::STAGED_F32;
+                }
+                feed.s_pack += now_s() - t0;
+            }
+            feed.state[c].store(result, std::memory_order_release);
         }
-        pend_n[k] = 0;
+    };
+    std::thread feeder_thread;
+    struct Joiner {
+        std::thread &t; HostFeed &f;
+        ~Joiner() { f.abort.store(true); if (t.joinable()) t.join(); }
+    } joiner{feeder_thread, feed};
+    if (threaded && nchunks > 1) feeder_thread = std::thread(feeder);
+    else feeder();   // one chunk (or nothing to prepare): no second thread
+
+    // results of a chunk: copied by its stream into pinned staging buffer (slot, parity), handed to the caller by hand_over()
+    // once the stream has drained -- which the slot's next chunk waits for anyway
+    struct Pending { int64_t off = 0, n = 0; int buf = 0; } pend[HOST_SLOTS];
+    auto wait_slot = [&](int k) -> int {
+        const double t0 = now_s();
+        CUDA_TRY(cudaStreamSynchronize(h.st[k]));
+        stats.s_wait += now_s() - t0;
         return LDPC_OK;
     };
-    // pageable caller memory?  (cudaMemcpyAsync from it is staged by the driver and blocks: stage it ourselves, in parallel)
-    bool pageable = false;
-    {
-        cudaPointerAttributes attr;
-        if (cudaPointerGetAttributes(&attr, src_host) != cudaSuccess) { cudaGetLastError(); pageable = true; }
-        else pageable = attr.type == cudaMemoryTypeUnregistered;
-    }
-    if (pageable && h.h_in_bytes < chunk * P0.NZ * elem) {
-        for (int i = 0; i < 2; ++i) { cudaFreeHost(h.h_in[i]); h.h_in[i] = nullptr; }
-        h.h_in_bytes = 0;
-        for (int i = 0; i < 2; ++i) CUDA_TRY(cudaMallocHost(&h.h_in[i], chunk * P0.NZ * elem));
-        h.h_in_bytes = chunk * P0.NZ * elem;
-    }
-    const unsigned hw = std::max(1u, std::thread::hardware_concurrency());
-    const int n_copy = (int)std::min(8u, std::max(1u, hw / 2));
-    auto stage_in = [&](char *dst, const char *src, size_t bytes) {
-        if (bytes < (4u << 20) || n_copy == 1) { std::memcpy(dst, src, bytes); return; }
-        std::vector<std::thread> th;
-        const size_t per = ((bytes + n_copy - 1) / n_copy + 4095) & ~(size_t)4095;
-        for (int t = 1; t < n_copy; ++t) {
-            const size_t lo = std::min(bytes, per * t), hi = std::min(bytes, per * (t + 1));
-            if (hi > lo) th.emplace_back([=] { std::memcpy(dst + lo, src + lo, hi - lo); });
-        }
-        std::memcpy(dst, src, std::min(bytes, per));
-        for (auto &t : th) t.join();
+    auto hand_over = [&](const Pending &p) {
+        if (p.n <= 0) return;
+        const double t1 = now_s();
+        const int64_t off = p.off, nb = p.n;
+        const int b = p.buf;
+        if (hard_host) std::memcpy(hard_host + off * P0.HW, h.h_hard[b], (size_t)nb * P0.HW * 4);
+        if (iters_host) std::memcpy(iters_host + off, h.h_iters[b], (size_t)nb * 4);
+        if (flags_host) std::memcpy(flags_host + off, h.h_flags[b], (size_t)nb);
+        if (biterr_host) std::memcpy(biterr_host + off, h.h_biterr[b], (size_t)nb * 4);
+        stats.s_copy_out += now_s() - t1;
     };
-    int k = 0;
-    for (int64_t off = 0; off < B; off += (int64_t)chunk, k ^= 1) {
-        const int64_t nb = std::min<int64_t>((int64_t)chunk, B - off);
+
+    double share = feed.share.load();
+    double win_dev = 0.0, win_feed = 0.0, win_t0 = now_s();
+    int win_chunks = 0;
+    for (int c = 0; c < nchunks; ++c) {
+        const int k = c % HOST_SLOTS;
+        const int64_t off = c_off[c], nb = c_n[c];
         cudaStream_t st = h.st[k];
-        rc = drain(k);
+        const double wait_before = stats.s_wait;
+        rc = wait_slot(k);
         if (rc != LDPC_OK) return rc;
-        const char *src = (const char *)src_host + (size_t)off * P0.NZ * elem;
-        if (pageable) {
-            stage_in(h.h_in[k], src, (size_t)nb * P0.NZ * elem);      // stream k has drained: its staging buffer is free
-            src = h.h_in[k];
-        }
-        CUDA_TRY(cudaMemcpyAsync(h.llr[k], src, (size_t)nb * P0.NZ * elem, cudaMemcpyHostToDevice, st));
+        win_dev += stats.s_wait - wait_before;
+        const Pending done = pend[k];          // complete now; handed over below, after this chunk has been issued
+        pend[k] = Pending();
+        const double tf0 = now_s();
+        int form;
+        for (int spin = 0; (form = feed.state[c].load(std::memory_order_acquire)) == HostFeed::PENDING; ++spin)
+            if (spin > 200) std::this_thread::yield();
+        const double tf = now_s() - tf0;
+        stats.s_wait_feed += tf; win_feed += tf;
+        if (form == HostFeed::FAILED) return fail(LDPC_E_CUDA, "decode_host: waiting for a staging buffer failed");
+        const bool as_q8 = form == HostFeed::DIRECT_Q8 || form == HostFeed::STAGED_Q8;
+        const bool staged = form == HostFeed::STAGED_F32 || form == HostFeed::STAGED_Q8;
+        const char *src = staged ? h.h_in[k] : (const char *)src_host + (size_t)off * NZ * elem;
+        const size_t bytes = (size_t)nb * NZ * (as_q8 ? 1 : sizeof(float));
+        CUDA_TRY(cudaMemcpyAsync(h.llr[k], src, bytes, cudaMemcpyHostToDevice, st));
+        CUDA_TRY(cudaEventRecord(h.ev_h2d[k], st));
+        feed.issued[k].fetch_add(1, std::memory_order_release);
+        stats.h2d_bytes += (int64_t)bytes;
         KParams P = P0;
         P.T_run = T_run; P.early_term = early_term ? 1 : 0;
-        P.llr = q8 ? nullptr : h.llr[k]; P.llr_q8 = q8 ? (const signed char *)h.llr[k] : nullptr; P.q8_step = step;
+        P.llr = as_q8 ? nullptr : h.llr[k]; P.llr_q8 = as_q8 ? (const signed char *)h.llr[k] : nullptr;
+        P.q8_step = q8 ? step : 1.0f / qk;
         P.n_frames = nb;
         P.app = app_iters ? h.app[k] : nullptr; P.app_all = app_all_iters ? 1 : 0; P.app_stride_t = (long long)nb * P.NZ;
         P.hard = hard_host ? h.hard[k] : nullptr; P.iters = iters_host ? h.iters[k] : nullptr;
         P.flags = flags_host ? h.flags[k] : nullptr; P.biterr = biterr_host ? h.biterr[k] : nullptr;
         rc = launch(d, P, st);
         if (rc != LDPC_OK) return rc;
-        if (hard_host) CUDA_TRY(cudaMemcpyAsync(h.h_hard[k], h.hard[k], (size_t)nb * P.HW * 4, cudaMemcpyDeviceToHost, st));
-        if (iters_host) CUDA_TRY(cudaMemcpyAsync(h.h_iters[k], h.iters[k], (size_t)nb * 4, cudaMemcpyDeviceToHost, st));
-        if (flags_host) CUDA_TRY(cudaMemcpyAsync(h.h_flags[k], h.flags[k], (size_t)nb, cudaMemcpyDeviceToHost, st));
-        if (biterr_host) CUDA_TRY(cudaMemcpyAsync(h.h_biterr[k], h.biterr[k], (size_t)nb * 4, cudaMemcpyDeviceToHost, st));
-        pend_off[k] = off; pend_n[k] = nb;
+        const int rb = k + HOST_SLOTS * ((c / HOST_SLOTS) & 1);
+        if (hard_host) CUDA_TRY(cudaMemcpyAsync(h.h_hard[rb], h.hard[k], (size_t)nb * P.HW * 4, cudaMemcpyDeviceToHost, st));
+        if (iters_host) CUDA_TRY(cudaMemcpyAsync(h.h_iters[rb], h.iters[k], (size_t)nb * 4, cudaMemcpyDeviceToHost, st));
+        if (flags_host) CUDA_TRY(cudaMemcpyAsync(h.h_flags[rb], h.flags[k], (size_t)nb, cudaMemcpyDeviceToHost, st));
+        if (biterr_host) CUDA_TRY(cudaMemcpyAsync(h.h_biterr[rb], h.biterr[k], (size_t)nb * 4, cudaMemcpyDeviceToHost, st));
+        stats.d2h_bytes += (int64_t)nb * ((hard_host ? P.HW * 4 : 0) + (iters_host ? 4 : 0) + (flags_host ? 1 : 0) + (biterr_host ? 4 : 0));
+        pend[k].off = off; pend[k].n = nb; pend[k].buf = rb;
         if (app_iters) {
             const size_t row = (size_t)nb * P.NZ * sizeof(float);
             CUDA_TRY(cudaMemcpy2DAsync(app_host + off * P.NZ, (size_t)B * P.NZ * sizeof(float), h.app[k], row, row,
                                        (size_t)app_iters, cudaMemcpyDeviceToHost, st));
+            stats.d2h_bytes += (int64_t)(row * app_iters);
+        }
+        hand_over(done);
+        if (pack_mode && !pageable && ++win_chunks == 6) {
+            const double now = now_s(), el = std::max(1e-9, now - win_t0);
+            if (win_feed / el > 0.10) share = std::min(1.0, share + 0.06);        // the cores are the limit
+            else if (win_dev / el > 0.15) share = std::max(0.0, share - 0.06);    // the device or PCIe is
+            feed.share.store(share, std::memory_order_relaxed);
+            win_chunks = 0; win_dev = win_feed = 0.0; win_t0 = now;
         }
     }
-    rc = drain(k);          // older chunk first, so the caller's arrays fill in order
-    if (rc != LDPC_OK) return rc;
-    return drain(k ^ 1);
+    for (int i = 0; i < HOST_SLOTS; ++i) {   // oldest chunk first, so the caller's arrays fill in order
+        const int k = (nchunks + i) % HOST_SLOTS;
+        rc = wait_slot(k);
+        if (rc != LDPC_OK) return rc;
+        hand_over(pend[k]);
+        pend[k] = Pending();
+    }
+    if (feeder_thread.joinable()) feeder_thread.join();
+    if (pack_mode && !pageable) h.float_share = share;
+    stats.chunks_q8 = feed.chunks_q8.load(); stats.chunks_unencodable = feed.chunks_unencodable.load();
+    stats.chunks_f32 = nchunks - stats.chunks_q8 - stats.chunks_unencodable;
+    if (q8) { stats.chunks_q8 = nchunks; stats.chunks_f32 = 0; }
+    stats.s_pack = feed.s_pack;
+    stats.float_share = share;
+    stats.s_total = now_s() - t_begin;
+    h.stats = stats;
+    return LDPC_OK;
 }
 }   // namespace
+
+extern "C" int ldpc_decode_host_stats(const ldpc_decoder_t *d, ldpc_host_stats_t *out) {
+    if (!d || !out) return fail(LDPC_E_INVALID, "decode_host_stats: bad arguments");
+    std::lock_guard<std::mutex> lock(const_cast<ldpc_decoder *>(d)->mu);
+    *out = d->hs.stats;
+    return LDPC_OK;
+}
+
+extern "C" int ldpc_pack_q8_values(const float *x, int64_t n, float step, float qmax, int32_t lossless, int8_t *q8,
+                                   int64_t *n_unencodable) {
+    if (n < 0 || (n > 0 && (!x || !q8)) || !(step > 0.0f) || !(qmax > 0.0f) || qmax / step > 127.0f)
+        return fail(LDPC_E_INVALID, "pack_q8_values: bad arguments");
+    const int64_t bad = hostpack::pack_q8_mt(x, n, 1.0f / step, qmax / step, lossless ? 1 : 0, q8);
+    if (n_unencodable) *n_unencodable = bad;
+    return LDPC_OK;
+}
+
+extern "C" int ldpc_pack_q8_host(const ldpc_decoder_t *d, const float *llr_host, int64_t B, int8_t *q8_host,
+                                 int64_t *n_unencodable) {
+    if (!d || B < 0 || (B > 0 && (!llr_host || !q8_host))) return fail(LDPC_E_INVALID, "pack_q8_host: bad arguments");
+    float qk = 1.0f, kmax = 0.0f;
+    const int mode = host_pack_mode(d, &qk, &kmax);
+    if (mode == 0) return fail(LDPC_E_UNSUPPORTED, "pack_q8_host: this decoder has no int8 word form (float decoder, or q_bit 6)");
+    const int64_t bad = hostpack::pack_q8_mt(llr_host, B * (int64_t)d->base.NZ, qk, kmax, mode == 2, q8_host);
+    if (n_unencodable) *n_unencodable = bad;
+    return LDPC_OK;
+}
 
 extern "C" int ldpc_decode_host(const ldpc_decoder_t *d, const float *llr_host, int64_t B, int32_t iters,
                                 int32_t early_term, float *app_host, int32_t app_all_iters, uint32_t *hard_host,

@@ -244,9 +244,25 @@ class NMSDecoder:
         return r.app.reshape(-1, self.graph.NZ)
 
     # -------------------------------------------------------------------- decode (host buffers)
-    def decode_host(self, llr, iters: int = 0, early_term: bool = False, app: Optional[str] = None) -> Dict:
+    def _host_results(self, B: int, out: Optional[Dict]):
+        """Result arrays of a host-buffer call: fresh ones, or those of `out` (a dict an earlier call returned) when their
+        shapes fit -- a steady-state loop then writes into memory that is already mapped instead of faulting in ~80 bytes
+        per frame of new pages per call."""
+        shapes = {"hard_packed": ((B, self.hard_words), np.uint32), "iters": ((B,), np.int32), "flags": ((B,), np.uint8),
+                  "biterr": ((B,), np.int32)}
+        res = []
+        for key, (shape, dt) in shapes.items():
+            a = out.get(key) if out is not None else None
+            if not (isinstance(a, np.ndarray) and a.shape == shape and a.dtype == dt and a.flags.c_contiguous and a.flags.writeable):
+                a = np.empty(shape, dtype=dt)
+            res.append(a)
+        return res
+
+    def decode_host(self, llr, iters: int = 0, early_term: bool = False, app: Optional[str] = None,
+                    out: Optional[Dict] = None) -> Dict:
         """End-to-end call: llr is a host array (numpy or CPU torch tensor, pinned or not); results
-        come back in host numpy arrays.  Copies and kernels are pipelined inside the library."""
+        come back in host numpy arrays (those of `out`, the dict of an earlier call, when given: they are overwritten).
+        Copies and kernels are pipelined inside the library."""
         g = self.graph
         if isinstance(llr, torch.Tensor):
             if llr.is_cuda:
@@ -260,10 +276,7 @@ class NMSDecoder:
         if arr.size != B * g.NZ:
             raise ValueError(f"decode_host: llr has {arr.size} elements, expected {B}x{g.NZ}")
         T_run = self.T if iters == 0 else iters
-        hard = np.empty((B, self.hard_words), dtype=np.uint32)
-        it = np.empty((B,), dtype=np.int32)
-        fl = np.empty((B,), dtype=np.uint8)
-        be = np.empty((B,), dtype=np.int32)
+        hard, it, fl, be = self._host_results(B, out)
         app_a = None
         if app == "last":
             app_a = np.empty((B, g.NZ), dtype=np.float32)
@@ -339,8 +352,10 @@ class NMSDecoder:
                                               ctypes.c_void_p(stream)))
         return DecodeResult(None, hard, it, fl, be, None)
 
-    def decode_q8_host(self, words, iters: int = 0, early_term: bool = False, step: float = 0.0) -> Dict:
-        """End-to-end call on host int8 words (numpy or CPU tensor, pinned or not); results in numpy arrays."""
+    def decode_q8_host(self, words, iters: int = 0, early_term: bool = False, step: float = 0.0,
+                       out: Optional[Dict] = None) -> Dict:
+        """End-to-end call on host int8 words (numpy or CPU tensor, pinned or not); results in numpy arrays (`out`: see
+        decode_host)."""
         g = self.graph
         arr = words.contiguous().numpy() if isinstance(words, torch.Tensor) else np.ascontiguousarray(words)
         if arr.dtype != np.int8:
@@ -348,14 +363,31 @@ class NMSDecoder:
         B = arr.shape[0]
         if arr.size != B * g.NZ:
             raise ValueError(f"decode_q8_host: {arr.size} elements, expected {B}x{g.NZ}")
-        hard = np.empty((B, self.hard_words), dtype=np.uint32)
-        it = np.empty((B,), dtype=np.int32)
-        fl = np.empty((B,), dtype=np.uint8)
-        be = np.empty((B,), dtype=np.int32)
+        hard, it, fl, be = self._host_results(B, out)
         _lib.check(_lib.load().ldpc_decode_q8_host(self._h, arr.ctypes.data, float(step), B, int(iters),
                                                    1 if early_term else 0, hard.ctypes.data, it.ctypes.data,
                                                    fl.ctypes.data, be.ctypes.data))
         return {"hard_packed": hard, "iters": it, "flags": fl, "biterr": be, "app": None}
+
+    def host_stats(self) -> Dict:
+        """What the last decode_host / decode_q8_host call did (ldpc_decode_host_stats): chunks sent as int8 / float32,
+        host threads, seconds the calling thread packed / waited for the device, bytes copied."""
+        st = _lib.HostStats()
+        _lib.check(_lib.load().ldpc_decode_host_stats(self._h, ctypes.byref(st)))
+        return st.as_dict()
+
+    def pack_q8(self, llr):
+        """float32 host words -> (int8 words in units of the quantiser step, number of values with no int8 form):
+        the packing pass of decode_host on its own (ldpc_pack_q8_host), for callers that decode a word set repeatedly
+        with decode_q8_host."""
+        arr = llr.contiguous().numpy() if isinstance(llr, torch.Tensor) else np.ascontiguousarray(llr, dtype=np.float32)
+        B = arr.shape[0]
+        if arr.dtype != np.float32 or arr.size != B * self.graph.NZ:
+            raise ValueError(f"pack_q8: float32 [B, {self.graph.NZ}] expected")
+        out = np.empty((B, self.graph.NZ), dtype=np.int8)
+        bad = ctypes.c_int64(0)
+        _lib.check(_lib.load().ldpc_pack_q8_host(self._h, arr.ctypes.data, B, out.ctypes.data, ctypes.byref(bad)))
+        return out, int(bad.value)
 
     # --------------------------------------------------------------------- generator / MC / post
     def generate(self, sigma: float, n_frames: int, seed: int, frame_offset: int = 0, codeword=None) -> torch.Tensor:
