@@ -13,9 +13,13 @@
 // so the quantised path is bit-exact and the trained decoder is the decoder the fast kernels run.
 // Checked against torch.autograd of the reference's own code (tests/golden/grad_*.npz).
 #include "nms_train.cuh"
+#include <cstdlib>
 
 #define TRAIN_MAX_DC 64
-#define TRAIN_THREADS 256
+// threads per CTA (= per frame) are a launch-time choice: a frame is one CTA, so the per-frame latency -- what bounds a
+// training batch of 20-40 frames on 148 SMs -- falls with the thread count until barriers take over
+#define TRAIN_MAX_THREADS 1024
+#define TRAIN_THREADS ((int)blockDim.x)
 
 namespace {
 
@@ -165,7 +169,7 @@ __device__ void cn_forward(const TrainParams &P, const Smem &S, int t) {
     __syncthreads();
 }
 
-__global__ void __launch_bounds__(TRAIN_THREADS) nms_train_kernel(const TrainParams P) {
+__global__ void __launch_bounds__(TRAIN_MAX_THREADS) nms_train_kernel(const TrainParams P) {
     extern __shared__ __align__(16) unsigned char train_smem[];
     Smem S;
     float *f = reinterpret_cast<float *>(train_smem);
@@ -363,7 +367,17 @@ cudaError_t nms_launch_train(const TrainParams &P, cudaStream_t st) {
     const size_t smem = nms_train_smem_bytes(P);
     cudaError_t e = cudaFuncSetAttribute(nms_train_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return e;
-    nms_train_kernel<<<P.B, TRAIN_THREADS, smem, st>>>(P);
+    // measured (tools/train_bench.py, profiles/r02_train_step.txt): while every frame can have an SM of its own, 1024 threads
+    // per frame are fastest (z72 batch 40: 2.35 ms at 256, 1.57 at 512, 1.23 at 1024); beyond that 512 (WiMAX batch 200)
+    static const int forced = [] {
+        const char *e = getenv("LDPC_B200_TRAIN_THREADS");
+        const int v = e ? atoi(e) : 0;
+        return (v >= 32 && v <= TRAIN_MAX_THREADS && v % 32 == 0) ? v : 0;
+    }();
+    int dev = 0, sms = 148;
+    if (cudaGetDevice(&dev) == cudaSuccess) cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    const int threads = forced ? forced : (P.B <= sms ? 1024 : 512);
+    nms_train_kernel<<<P.B, threads, smem, st>>>(P);
     nms_note_launch();
     return cudaGetLastError();
 }
