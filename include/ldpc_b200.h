@@ -164,7 +164,8 @@ int ldpc_decode(const ldpc_decoder_t *d, const float *llr_dev, int64_t B, int32_
  * streams so copies overlap compute; synchronous.  This is the end-to-end call: what a reference
  * maintainer binds in place of sess.run(..., feed_dict={xa_input: ...}) (Print_Functions.py:148-150).
  * float32 words are the bound of this path (PCIe), so for a quantised decoder the library's host
- * threads pack part of the chunks to int8 (one byte per value) while the others travel as they are:
+ * threads pack chunks to int8 (one byte per value) from the front of the call while the DMA engine
+ * takes chunks from its back as they are -- the two lanes meet wherever their speeds put them:
  * same decoder input bit for bit -- a quantised decoder sees a channel value only through Q(x)
  * (Main_Functions.py:321-322) and, with VN weights, Q(x * w) (:168-177), so words are packed always
  * without VN weights and, with them, whenever every value of the chunk is on the quantiser grid
@@ -178,14 +179,15 @@ int ldpc_decode_host(const ldpc_decoder_t *d, const float *llr_host, int64_t B, 
 /* What the last ldpc_decode_host / ldpc_decode_q8_host call on this handle did. */
 typedef struct {
     int32_t threads;            /* host threads that packed / staged */
+    int32_t chunks_total;       /* chunks of the call */
     int32_t chunks_q8;          /* chunks that crossed PCIe as int8 */
     int32_t chunks_f32;         /* chunks that crossed as float32 by choice (DMA engine and cores share the load) */
     int32_t chunks_unencodable; /* chunks that crossed as float32 because a value has no int8 form */
-    double float_share;         /* share of float32 chunks the next call starts with */
+    double float_share;         /* share of the chunks that crossed as float32 */
     double s_pack;      /* feeder thread: packing / staging (seconds) */
     double s_wait;      /* calling thread: waiting for the device */
     double s_wait_feed; /* calling thread: waiting for the feeder */
-    double s_copy_out;  /* calling thread: handing results to the caller */
+    double s_copy_out;  /* copying results into the caller's arrays (feeder thread + pool; calling thread for short calls) */
     double s_total;     /* the whole call */
     int64_t h2d_bytes, d2h_bytes;               /* bytes actually copied */
 } ldpc_host_stats_t;

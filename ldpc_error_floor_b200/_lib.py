@@ -123,7 +123,7 @@ ALU_PROBE_KINDS = {"ffma": 0, "fmnmx": 1, "lop3": 2, "iadd": 3, "hfma2": 4, "hmn
 
 class HostStats(ctypes.Structure):
     """ldpc_host_stats_t (include/ldpc_b200.h)."""
-    _fields_ = [("threads", ctypes.c_int32), ("chunks_q8", ctypes.c_int32), ("chunks_f32", ctypes.c_int32),
+    _fields_ = [("threads", ctypes.c_int32), ("chunks_total", ctypes.c_int32), ("chunks_q8", ctypes.c_int32), ("chunks_f32", ctypes.c_int32),
                 ("chunks_unencodable", ctypes.c_int32), ("float_share", ctypes.c_double), ("s_pack", ctypes.c_double),
                 ("s_wait", ctypes.c_double), ("s_wait_feed", ctypes.c_double), ("s_copy_out", ctypes.c_double), ("s_total", ctypes.c_double),
                 ("h2d_bytes", ctypes.c_int64), ("d2h_bytes", ctypes.c_int64)]

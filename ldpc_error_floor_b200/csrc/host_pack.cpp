@@ -14,6 +14,7 @@
 #include <cstdlib>
 #include <cstring>
 #include <mutex>
+#include <system_error>
 #include <thread>
 #include <vector>
 
@@ -118,7 +119,11 @@ class Pool {
             n = std::min(16, std::max(1, hw / local - 1));
         }
         nthreads_ = std::min(n, 64);
-        for (int t = 1; t < nthreads_; ++t) workers_.emplace_back([this] { work(); });
+        try {
+            for (int t = 1; t < nthreads_; ++t) workers_.emplace_back([this] { work(); });
+        } catch (...) {   // thread limit of the process: go on with the workers that did start
+        }
+        nthreads_ = (int)workers_.size() + 1;
     }
     ~Pool() {
         {

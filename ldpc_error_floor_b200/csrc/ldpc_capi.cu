@@ -107,8 +107,6 @@ struct HostScratch {
     // the float32 words themselves for callers that pass pageable memory and words that have no int8 form
     char *h_in[HOST_SLOTS] = {};
     size_t h_in_bytes = 0;
-    // share of the chunks that travel as float32 while the host threads pack the others (adapted from call to call)
-    double float_share = 0.25;
     ldpc_host_stats_t stats{};
     unsigned long long *counters = nullptr;
     unsigned int *ucount = nullptr;
@@ -905,10 +903,9 @@ int ensure_host_scratch(ldpc_decoder *d, size_t chunk, bool with_app, int app_it
     HostScratch &h = d->hs;
     if (h.cap_frames >= chunk && (!with_app || (h.with_app && h.app_iters >= app_iters))) return LDPC_OK;
     unsigned long long *cnt = h.counters; unsigned int *uc = h.ucount; float *ub = h.ubuf; size_t ur = h.ubuf_rows;
-    const double share = h.float_share;
     h.counters = nullptr; h.ucount = nullptr; h.ubuf = nullptr;
     free_scratch(h);
-    h.counters = cnt; h.ucount = uc; h.ubuf = ub; h.ubuf_rows = ur; h.float_share = share;
+    h.counters = cnt; h.ucount = uc; h.ubuf = ub; h.ubuf_rows = ur;
     const KParams &P = d->base;
     for (int i = 0; i < HOST_SLOTS; ++i) {
         CUDA_TRY(cudaStreamCreateWithFlags(&h.st[i], cudaStreamNonBlocking));
@@ -961,31 +958,42 @@ bool host_ptr_pageable(const void *p) {
 }
 
 // The host-buffer pipeline.  A call is cut into chunks (a few waves of CTAs, ~32 MiB of float32 words; the first ones
-// shorter so the device starts early); chunk c uses slot c mod HOST_SLOTS (device buffers, stream, pinned staging), so up
-// to HOST_SLOTS - 1 chunks are queued on the device while the host prepares the next ones.  float32 words of a quantised
-// decoder cross PCIe in one of two forms, chosen per chunk:
+// shorter so the device starts early).  Up to HOST_SLOTS chunks are in flight, each on a slot of its own (device buffers,
+// stream, two sets of pinned result buffers).  float32 words of a quantised decoder cross PCIe in one of two forms:
 //   * as they are (DMA straight from the caller's pinned memory: no host work, 4 bytes per value), or
 //   * packed to int8 by the host threads (host_pack.cpp: 1 byte per value) -- the same decoder input bit for bit.
-// PCIe bounds the first form (the decoder is ~2x faster than 55 GB/s of float32 words), the host's cores the second, and the
-// two resources work side by side: `float_share` of the chunks goes the first way, the others the second.
-// Two host threads drive a call: a FEEDER prepares chunks ahead (decides the form, packs / stages into the slot's pinned
-// buffer as soon as the copy that last read it has completed -- an event, not the whole stream), the CALLING thread waits
-// for a slot's previous results, hands them to the caller, and issues copy + kernel + result copies for the next prepared
-// chunk.  The share follows what the calling thread waits for: the feeder -> leave more chunks to the DMA engine; the
-// device -> pack more.  Pageable input is always packed (reading it is the cost either way) unless it has no int8 form;
-// then the same threads stage it through pinned memory.
+// PCIe bounds the first form (the decoder is ~2x faster than 55 GB/s of float32 words), the host's cores and memory the
+// second, so the two work side by side on ONE list of chunks taken from both ends:
+//   * a FEEDER thread claims chunks from the front, packs each (with the pool) into the next buffer of a ring of pinned
+//     staging buffers -- free again as soon as the copy that last read it has completed: an event, not a stream -- and
+//     publishes it; between chunks it copies finished results into the caller's arrays;
+//   * the CALLING thread waits for a free slot, then issues copy + kernel + result copies for the next published chunk
+//     or, when none is ready, for a chunk claimed from the BACK of the list, sent as float32.
+// The two lanes meet wherever their speeds put them: no tuning, and whichever resource is scarce on the box (PCIe at one
+// GPU, cores and host memory when eight GPUs share them) sets the split.  Pageable input has no float32 lane worth having
+// (reading it is the cost either way): the feeder packs every chunk, or stages the ones without an int8 form through the
+// same pinned buffers.
 struct HostFeed {
-    enum : int { PENDING = 0, DIRECT_F32, DIRECT_Q8, STAGED_F32, STAGED_Q8, FAILED };
-    std::vector<std::atomic<int>> state;            // per chunk: how the calling thread finds its words
-    std::atomic<long long> issued[HOST_SLOTS];      // copies issued from slot r's staging buffer so far
-    std::atomic<double> share{0.0};
-    std::atomic<bool> abort{false};
-    std::atomic<int> chunks_q8{0}, chunks_unencodable{0};
-    double s_pack = 0.0;
-    explicit HostFeed(size_t n) : state(n) {
+    enum : int { PENDING = 0, DIRECT, STAGED_F32, STAGED_Q8, FAILED };
+    std::mutex claim_mu;
+    int front = 0, back = 0;                        // chunks [front, back) are unclaimed
+    std::vector<std::atomic<int>> state;            // per front chunk: how the calling thread finds its words
+    std::atomic<int> prepared{0};                   // front chunks published so far (chunks 0 .. prepared-1, in order)
+    std::atomic<bool> front_done{false};            // the feeder claims no more chunks
+    std::atomic<long long> issued[HOST_SLOTS];      // copies issued from staging buffer r so far
+    std::atomic<bool> abort{false}, failed{false};
+    int chunks_q8 = 0, chunks_unencodable = 0;
+    double s_pack = 0.0, s_copy_out = 0.0;
+    // results ready for the caller, in issue order: the calling thread queues them, the feeder copies them out with the pool
+    struct Results { int64_t off, n; int buf; } rq[32];
+    std::atomic<long long> rq_head{0}, rq_tail{0};
+    std::atomic<bool> rq_closed{false};
+    explicit HostFeed(size_t n) : back((int)n), state(n) {
         for (auto &x : state) x.store(PENDING, std::memory_order_relaxed);
         for (auto &x : issued) x.store(0, std::memory_order_relaxed);
     }
+    int claim_front() { std::lock_guard<std::mutex> g(claim_mu); return front < back ? front++ : -1; }
+    int claim_back() { std::lock_guard<std::mutex> g(claim_mu); return back > front ? --back : -1; }
 };
 
 int decode_host_impl(const ldpc_decoder_t *dc, const void *src_host, bool q8, float step, int64_t B, int32_t iters,
@@ -1020,7 +1028,9 @@ int decode_host_impl(const ldpc_decoder_t *dc, const void *src_host, bool q8, fl
     const int pack_mode = (q8 || app_iters) ? 0 : host_pack_mode(d, &qk, &kmax);
     const bool pageable = host_ptr_pageable(src_host);
     const size_t elem = q8 ? 1 : sizeof(float);
-    if (pack_mode || pageable) {
+    const bool front_lane = pack_mode != 0 || pageable;   // chunks that need the host's hands
+    const bool back_lane = !pageable;                     // chunks the DMA engine can fetch from the caller's memory
+    if (front_lane) {
         rc = ensure_host_staging(h, chunk * NZ * ((pageable && !q8) ? sizeof(float) : 1));
         if (rc != LDPC_OK) return rc;
     }
@@ -1034,51 +1044,83 @@ int decode_host_impl(const ldpc_decoder_t *dc, const void *src_host, bool q8, fl
     const int nchunks = (int)c_off.size();
     ldpc_host_stats_t stats{};
     HostFeed feed((size_t)nchunks);
-    feed.share.store(pageable ? 0.0 : h.float_share);
-    const bool threaded = pack_mode != 0 || pageable;
-    stats.threads = threaded ? hostpack::pool_threads() : 1;
+    stats.threads = front_lane ? hostpack::pool_threads() : 1;
 
-    // ---- feeder: chunk c -> (form, where its words are)
-    auto feeder = [&]() {
+    // results of a chunk: copied by its stream into the pinned staging buffers (slot, parity), from there into the caller's
+    // arrays once the stream has drained
+    auto copy_results = [&](int64_t off, int64_t nb, int b, bool mt) {
+        if (nb <= 0) return;
+        if (hard_host) {
+            const size_t bytes = (size_t)nb * P0.HW * 4;
+            if (mt && bytes >= (256u << 10)) hostpack::memcpy_mt(hard_host + off * P0.HW, h.h_hard[b], bytes);
+            else std::memcpy(hard_host + off * P0.HW, h.h_hard[b], bytes);
+        }
+        if (iters_host) std::memcpy(iters_host + off, h.h_iters[b], (size_t)nb * 4);
+        if (flags_host) std::memcpy(flags_host + off, h.h_flags[b], (size_t)nb);
+        if (biterr_host) std::memcpy(biterr_host + off, h.h_biterr[b], (size_t)nb * 4);
+    };
+    auto feeder_copy_out = [&]() {   // feeder thread: everything the calling thread has queued so far
+        long long t = feed.rq_tail.load(std::memory_order_relaxed);
+        while (t < feed.rq_head.load(std::memory_order_acquire)) {
+            const HostFeed::Results r = feed.rq[t % 32];
+            const double t0 = now_s();
+            copy_results(r.off, r.n, r.buf, true);
+            feed.s_copy_out += now_s() - t0;
+            feed.rq_tail.store(++t, std::memory_order_release);
+        }
+    };
+
+    // ---- feeder: front chunk c -> (form, where its words are); between chunks, results -> caller
+    auto feeder = [&](bool own_thread) {
         if (cudaSetDevice(d->device) != cudaSuccess) { cudaGetLastError(); }
-        double credit = 0.5;
         int unencodable_run = 0;
-        for (int c = 0; c < nchunks; ++c) {
+        for (;;) {
+            if (own_thread) feeder_copy_out();
+            // pinned words that keep failing the "has an int8 form" test: leave the rest to the float32 lane
+            if (!pageable && (pack_mode == 0 || unencodable_run >= 2)) break;
+            const int c = feed.claim_front();
+            if (c < 0) break;
             const int r = c % HOST_SLOTS;
             const char *src = (const char *)src_host + (size_t)c_off[c] * NZ * elem;
             const size_t nval = (size_t)c_n[c] * NZ;
-            bool want_pack = false;
+            // staging buffer r is free once the copy that last read it (front chunk c - HOST_SLOTS) has completed
+            const long long need = c / HOST_SLOTS;
+            for (int spin = 0; feed.issued[r].load(std::memory_order_acquire) < need; ++spin) {
+                if (feed.abort.load(std::memory_order_relaxed)) return;
+                if (own_thread) feeder_copy_out();
+                if (spin > 200) std::this_thread::yield();
+            }
+            if (need > 0 && cudaEventSynchronize(h.ev_h2d[r]) != cudaSuccess) {
+                cudaGetLastError();
+                feed.failed.store(true, std::memory_order_release);
+                feed.state[c].store(HostFeed::FAILED, std::memory_order_release);
+                feed.prepared.store(c + 1, std::memory_order_release);
+                return;
+            }
+            const double t0 = now_s();
+            int result = HostFeed::DIRECT;
             if (pack_mode && unencodable_run < 2) {
-                credit += 1.0 - feed.share.load(std::memory_order_relaxed);   // error diffusion over the chunks
-                if (credit >= 1.0) { credit -= 1.0; want_pack = true; }
+                const int64_t bad = hostpack::pack_q8_mt((const float *)src, (int64_t)nval, qk, kmax, pack_mode == 2,
+                                                         (int8_t *)h.h_in[r], true);
+                if (bad == 0) { result = HostFeed::STAGED_Q8; unencodable_run = 0; ++feed.chunks_q8; }
+                else { ++unencodable_run; ++feed.chunks_unencodable; }
             }
-            int result = q8 ? HostFeed::DIRECT_Q8 : HostFeed::DIRECT_F32;
-            if (want_pack || pageable) {
-                // the staging buffer of slot r is free once the copy that last read it has completed
-                const long long need = c / HOST_SLOTS;
-                for (int spin = 0; feed.issued[r].load(std::memory_order_acquire) < need; ++spin) {
-                    if (feed.abort.load(std::memory_order_relaxed)) return;
-                    if (spin > 200) std::this_thread::yield();
-                }
-                if (need > 0 && cudaEventSynchronize(h.ev_h2d[r]) != cudaSuccess) {
-                    cudaGetLastError();
-                    feed.state[c].store(HostFeed::FAILED, std::memory_order_release);
-                    return;
-                }
-                const double t0 = now_s();
-                if (want_pack) {
-                    const int64_t bad = hostpack::pack_q8_mt((const float *)src, (int64_t)nval, qk, kmax, pack_mode == 2,
-                                                             (int8_t *)h.h_in[r], true);
-                    if (bad == 0) { result = HostFeed::STAGED_Q8; unencodable_run = 0; feed.chunks_q8.fetch_add(1); }
-                    else { ++unencodable_run; feed.chunks_unencodable.fetch_add(1); want_pack = false; }
-                }
-                if (!want_pack && pageable) {
-                    hostpack::memcpy_mt(h.h_in[r], src, nval * elem);
-                    result = q8 ? HostFeed::STAGED_Q8 : HostFeed::STAGED_F32;
-                }
-                feed.s_pack += now_s() - t0;
+            if (result == HostFeed::DIRECT && pageable) {
+                hostpack::memcpy_mt(h.h_in[r], src, nval * elem);
+                result = q8 ? HostFeed::STAGED_Q8 : HostFeed::STAGED_F32;
             }
-            feed.state[c].store(result, std::memory_order_release);
+            feed.s_pack += now_s() - t0;
+            feed.state[c].store(result, std::memory_order_relaxed);
+            feed.prepared.store(c + 1, std::memory_order_release);
+        }
+        feed.front_done.store(true, std::memory_order_release);
+        if (!own_thread) return;
+        for (int spin = 0;; ++spin) {   // results, until the calling thread closes the queue
+            feeder_copy_out();
+            if (feed.rq_closed.load(std::memory_order_acquire) &&
+                feed.rq_tail.load(std::memory_order_relaxed) >= feed.rq_head.load(std::memory_order_acquire)) return;
+            if (feed.abort.load(std::memory_order_relaxed)) return;
+            if (spin > 200) std::this_thread::yield();
         }
     };
     std::thread feeder_thread;
@@ -1086,11 +1128,18 @@ int decode_host_impl(const ldpc_decoder_t *dc, const void *src_host, bool q8, fl
         std::thread &t; HostFeed &f;
         ~Joiner() { f.abort.store(true); if (t.joinable()) t.join(); }
     } joiner{feeder_thread, feed};
-    if (threaded && nchunks > 1) feeder_thread = std::thread(feeder);
-    else feeder();   // one chunk (or nothing to prepare): no second thread
+    if (front_lane && nchunks > 1) {
+        try {
+            feeder_thread = std::thread(feeder, true);
+        } catch (...) {
+            return fail(LDPC_E_ALLOC, "decode_host: cannot start the feeder thread");
+        }
+    } else if (front_lane) {
+        feeder(false);                   // one chunk: prepared right here
+    } else {
+        feed.front_done.store(true);     // nothing needs preparing: every chunk goes the direct way, in order
+    }
 
-    // results of a chunk: copied by its stream into pinned staging buffer (slot, parity), handed to the caller by hand_over()
-    // once the stream has drained -- which the slot's next chunk waits for anyway
     struct Pending { int64_t off = 0, n = 0; int buf = 0; } pend[HOST_SLOTS];
     auto wait_slot = [&](int k) -> int {
         const double t0 = now_s();
@@ -1098,45 +1147,81 @@ int decode_host_impl(const ldpc_decoder_t *dc, const void *src_host, bool q8, fl
         stats.s_wait += now_s() - t0;
         return LDPC_OK;
     };
+    const bool feeder_copies = feeder_thread.joinable();
+    long long handed = 0;   // results handed over (queued or copied) so far, in issue order
     auto hand_over = [&](const Pending &p) {
         if (p.n <= 0) return;
-        const double t1 = now_s();
-        const int64_t off = p.off, nb = p.n;
-        const int b = p.buf;
-        if (hard_host) std::memcpy(hard_host + off * P0.HW, h.h_hard[b], (size_t)nb * P0.HW * 4);
-        if (iters_host) std::memcpy(iters_host + off, h.h_iters[b], (size_t)nb * 4);
-        if (flags_host) std::memcpy(flags_host + off, h.h_flags[b], (size_t)nb);
-        if (biterr_host) std::memcpy(biterr_host + off, h.h_biterr[b], (size_t)nb * 4);
-        stats.s_copy_out += now_s() - t1;
+        if (feeder_copies) {
+            feed.rq[handed % 32] = HostFeed::Results{p.off, p.n, p.buf};
+            feed.rq_head.store(handed + 1, std::memory_order_release);
+        } else {
+            const double t1 = now_s();
+            copy_results(p.off, p.n, p.buf, false);
+            stats.s_copy_out += now_s() - t1;
+        }
+        ++handed;
     };
 
-    double share = feed.share.load();
-    double win_dev = 0.0, win_feed = 0.0, win_t0 = now_s();
-    int win_chunks = 0;
-    for (int c = 0; c < nchunks; ++c) {
-        const int k = c % HOST_SLOTS;
-        const int64_t off = c_off[c], nb = c_n[c];
-        cudaStream_t st = h.st[k];
-        const double wait_before = stats.s_wait;
+    bool slot_back[HOST_SLOTS] = {};   // the slot's chunk in flight came from the back of the list (float32 as it is)
+    int pf = 0;          // next published front chunk to issue
+    int direct_next = 0; // without a feeder: chunks in order
+    for (int i = 0;; ++i) {   // i-th chunk issued by this call
+        const int k = i % HOST_SLOTS;
         rc = wait_slot(k);
         if (rc != LDPC_OK) return rc;
-        win_dev += stats.s_wait - wait_before;
-        const Pending done = pend[k];          // complete now; handed over below, after this chunk has been issued
+        const Pending done = pend[k];          // complete now; handed over below, after the next chunk has been issued
         pend[k] = Pending();
+        // ---- which chunk: a published one, else one from the back of the list as it is, else wait for the feeder
+        int c = -1, form = HostFeed::DIRECT;
+        bool from_front = false;
         const double tf0 = now_s();
-        int form;
-        for (int spin = 0; (form = feed.state[c].load(std::memory_order_acquire)) == HostFeed::PENDING; ++spin)
+        slot_back[k] = false;
+        int back_in_flight = 0;
+        for (int j = 0; j < HOST_SLOTS; ++j) back_in_flight += slot_back[j] ? 1 : 0;
+        for (int spin = 0;; ++spin) {
+            if (!front_lane) { c = direct_next < nchunks ? direct_next++ : -1; break; }
+            const int prepared = feed.prepared.load(std::memory_order_acquire);
+            if (pf < prepared) {
+                c = pf++;
+                form = feed.state[c].load(std::memory_order_relaxed);
+                from_front = true;
+                break;
+            }
+            const bool done_front = feed.front_done.load(std::memory_order_acquire);
+            if (done_front && pf >= feed.prepared.load(std::memory_order_acquire)) {
+                if (back_lane) c = feed.claim_back();
+                break;                                   // c < 0: the list is empty
+            }
+            // two float32 chunks in flight keep the DMA engine busy; more would only queue in front of the packed ones.
+            // Nothing from the back before the feeder's first (short) chunk either: the device would start later.
+            if (back_lane && prepared > 0 && back_in_flight < 2 && (c = feed.claim_back()) >= 0) break;
+            if (back_in_flight >= 2 && (spin & 63) == 63) {   // still in flight?
+                back_in_flight = 0;
+                for (int j = 0; j < HOST_SLOTS; ++j) {
+                    if (slot_back[j] && cudaStreamQuery(h.st[j]) == cudaSuccess) slot_back[j] = false;
+                    back_in_flight += slot_back[j] ? 1 : 0;
+                }
+                cudaGetLastError();   // cudaErrorNotReady is not an error here
+            }
             if (spin > 200) std::this_thread::yield();
-        const double tf = now_s() - tf0;
-        stats.s_wait_feed += tf; win_feed += tf;
+        }
+        stats.s_wait_feed += now_s() - tf0;
+        if (c < 0) { hand_over(done); break; }
         if (form == HostFeed::FAILED) return fail(LDPC_E_CUDA, "decode_host: waiting for a staging buffer failed");
-        const bool as_q8 = form == HostFeed::DIRECT_Q8 || form == HostFeed::STAGED_Q8;
+        const int64_t off = c_off[c], nb = c_n[c];
+        cudaStream_t st = h.st[k];
         const bool staged = form == HostFeed::STAGED_F32 || form == HostFeed::STAGED_Q8;
-        const char *src = staged ? h.h_in[k] : (const char *)src_host + (size_t)off * NZ * elem;
+        const bool as_q8 = q8 || form == HostFeed::STAGED_Q8;
+        const int r = c % HOST_SLOTS;   // staging buffer of a front chunk
+        const char *src = staged ? h.h_in[r] : (const char *)src_host + (size_t)off * NZ * elem;
         const size_t bytes = (size_t)nb * NZ * (as_q8 ? 1 : sizeof(float));
         CUDA_TRY(cudaMemcpyAsync(h.llr[k], src, bytes, cudaMemcpyHostToDevice, st));
-        CUDA_TRY(cudaEventRecord(h.ev_h2d[k], st));
-        feed.issued[k].fetch_add(1, std::memory_order_release);
+        if (from_front) {   // its staging buffer (used or not) may go to front chunk c + HOST_SLOTS once this copy is through
+            CUDA_TRY(cudaEventRecord(h.ev_h2d[r], st));
+            feed.issued[r].fetch_add(1, std::memory_order_release);
+        } else {
+            slot_back[k] = front_lane;
+        }
         stats.h2d_bytes += (int64_t)bytes;
         KParams P = P0;
         P.T_run = T_run; P.early_term = early_term ? 1 : 0;
@@ -1148,7 +1233,15 @@ int decode_host_impl(const ldpc_decoder_t *dc, const void *src_host, bool q8, fl
         P.flags = flags_host ? h.flags[k] : nullptr; P.biterr = biterr_host ? h.biterr[k] : nullptr;
         rc = launch(d, P, st);
         if (rc != LDPC_OK) return rc;
-        const int rb = k + HOST_SLOTS * ((c / HOST_SLOTS) & 1);
+        const int rb = k + HOST_SLOTS * ((i / HOST_SLOTS) & 1);
+        if (feeder_copies && i >= 2 * HOST_SLOTS) {   // the (i - 8)-th chunk last used these result buffers: hand-over job i - 8
+            const double t0 = now_s();
+            for (int spin = 0; feed.rq_tail.load(std::memory_order_acquire) < (long long)(i - 2 * HOST_SLOTS + 1); ++spin) {
+                if (feed.failed.load(std::memory_order_acquire)) return fail(LDPC_E_CUDA, "decode_host: the feeder thread failed");
+                if (spin > 200) std::this_thread::yield();
+            }
+            stats.s_wait_feed += now_s() - t0;
+        }
         if (hard_host) CUDA_TRY(cudaMemcpyAsync(h.h_hard[rb], h.hard[k], (size_t)nb * P.HW * 4, cudaMemcpyDeviceToHost, st));
         if (iters_host) CUDA_TRY(cudaMemcpyAsync(h.h_iters[rb], h.iters[k], (size_t)nb * 4, cudaMemcpyDeviceToHost, st));
         if (flags_host) CUDA_TRY(cudaMemcpyAsync(h.h_flags[rb], h.flags[k], (size_t)nb, cudaMemcpyDeviceToHost, st));
@@ -1162,28 +1255,27 @@ int decode_host_impl(const ldpc_decoder_t *dc, const void *src_host, bool q8, fl
             stats.d2h_bytes += (int64_t)(row * app_iters);
         }
         hand_over(done);
-        if (pack_mode && !pageable && ++win_chunks == 6) {
-            const double now = now_s(), el = std::max(1e-9, now - win_t0);
-            if (win_feed / el > 0.10) share = std::min(1.0, share + 0.06);        // the cores are the limit
-            else if (win_dev / el > 0.15) share = std::max(0.0, share - 0.06);    // the device or PCIe is
-            feed.share.store(share, std::memory_order_relaxed);
-            win_chunks = 0; win_dev = win_feed = 0.0; win_t0 = now;
-        }
+        ++stats.chunks_total;
     }
-    for (int i = 0; i < HOST_SLOTS; ++i) {   // oldest chunk first, so the caller's arrays fill in order
-        const int k = (nchunks + i) % HOST_SLOTS;
+    for (int k = 0; k < HOST_SLOTS; ++k) {
         rc = wait_slot(k);
         if (rc != LDPC_OK) return rc;
-        hand_over(pend[k]);
-        pend[k] = Pending();
     }
+    // the chunks still in flight when the list ran out, oldest first
+    {
+        int order[HOST_SLOTS];
+        for (int k = 0; k < HOST_SLOTS; ++k) order[k] = k;
+        std::sort(order, order + HOST_SLOTS, [&](int x, int y) { return pend[x].off < pend[y].off; });
+        for (int j = 0; j < HOST_SLOTS; ++j) { hand_over(pend[order[j]]); pend[order[j]] = Pending(); }
+    }
+    feed.rq_closed.store(true, std::memory_order_release);
     if (feeder_thread.joinable()) feeder_thread.join();
-    if (pack_mode && !pageable) h.float_share = share;
-    stats.chunks_q8 = feed.chunks_q8.load(); stats.chunks_unencodable = feed.chunks_unencodable.load();
-    stats.chunks_f32 = nchunks - stats.chunks_q8 - stats.chunks_unencodable;
-    if (q8) { stats.chunks_q8 = nchunks; stats.chunks_f32 = 0; }
+    if (feeder_copies) stats.s_copy_out = feed.s_copy_out;
+    stats.chunks_q8 = q8 ? stats.chunks_total : feed.chunks_q8;
+    stats.chunks_unencodable = feed.chunks_unencodable;
+    stats.chunks_f32 = stats.chunks_total - stats.chunks_q8 - stats.chunks_unencodable;
     stats.s_pack = feed.s_pack;
-    stats.float_share = share;
+    stats.float_share = stats.chunks_total ? (double)(stats.chunks_total - stats.chunks_q8) / stats.chunks_total : 0.0;
     stats.s_total = now_s() - t_begin;
     h.stats = stats;
     return LDPC_OK;
