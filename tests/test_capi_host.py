@@ -175,3 +175,69 @@ def test_jit_prebuild_needs_no_gpu(tmp_path, monkeypatch):
     assert len(files) == 2 and all(f.endswith(".cubin") for f in files)
     t0 = time.time()
     assert _lib.jit_prebuild(proto, 8) == 2 and time.time() - t0 < 2.0
+
+
+# ---------------------------------------------------------------- host side of the int8 transport (csrc/host_pack.cpp)
+def _ref_pack(x, step, qmax, lossless):
+    """numpy restatement: Q(x) / step as the kernels compute it (nms_device.cuh qf: clamp to +-1e5, (x + M) - M, clamp to
+    +-qmax; Main_Functions.py:475-494), or the exact 'is on the grid and in range' test."""
+    qk = np.float32(1.0 / step)
+    kmax = qmax / step
+    x = x.astype(np.float32)
+    with np.errstate(all="ignore"):
+        if not lossless:
+            v = np.where(x > -1e5, x, np.float32(-1e5))          # NaN -> -bound, as fmaxf(NaN, -b)
+            v = np.where(v < 1e5, v, np.float32(1e5))
+            return np.clip(np.rint(v * qk), -kmax, kmax).astype(np.int8), 0
+        y = x * qk
+        inr = np.abs(y) <= kmax
+        k = np.where(inr, np.rint(np.where(inr, y, 0)), 0)
+        return k.astype(np.int8), int((~(inr & (k == y))).sum())
+
+
+@pytest.mark.parametrize("step, qmax", [(0.5, 7.5), (1.0, 15.0), (1.0, 7.0), (2.0, 6.0)])
+def test_pack_q8_values_matches_the_quantiser(step, qmax):
+    """ldpc_pack_q8_values == Q() of the reference (every q_bit that has an int8 form), quirk values included; the lossless
+    verdict counts exactly the values that are off the grid or out of range; odd lengths, several pool blocks."""
+    from ldpc_error_floor_b200 import _lib
+    rng = np.random.default_rng(int(step * 10 + qmax))
+    quirks = np.array([0.0, -0.0, np.nan, np.inf, -np.inf, 1e-4, -1e-4, 0.25, 0.75, -0.25, 1e30, -1e30, 7.5, -7.5, 7.75,
+                       8.0, 15.0, 15.5, -15.5, 6.0, 1e5, -1e5, 2e5, 0.24999999, 2.5, 3.5, -2.5, -3.5], dtype=np.float32)
+    for n in (0, 1, 31, 32, 33, 1000, 65536 * 3 + 17, 1_000_003):
+        x = (rng.standard_normal(n) * 6).astype(np.float32)
+        if n >= quirks.size:
+            x[:quirks.size] = quirks
+        q, bad = _lib.pack_q8_values(x, step, qmax, False)
+        r, _ = _ref_pack(x, step, qmax, False)
+        assert bad == 0 and np.array_equal(q, r)
+        q, bad = _lib.pack_q8_values(x, step, qmax, True)
+        _, rb = _ref_pack(x, step, qmax, True)
+        assert bad == rb
+        xg = (np.clip(np.rint(np.nan_to_num(x, posinf=0, neginf=0) / step), -qmax / step, qmax / step) * step).astype(np.float32)
+        q, bad = _lib.pack_q8_values(xg, step, qmax, True)
+        assert bad == 0 and np.array_equal(q.astype(np.float32) * np.float32(step), xg)
+
+
+def test_pack_q8_values_scalar_and_vector_bodies_agree(monkeypatch):
+    """The AVX2 body and the portable one give the same bytes (LDPC_B200_NO_AVX2 is read once per process: run the portable
+    body in a child)."""
+    import subprocess
+    import sys
+    code = ("import numpy as np, sys; sys.path.insert(0, %r); from ldpc_error_floor_b200 import _lib; "
+            "x = (np.random.default_rng(5).standard_normal(200003) * 6).astype(np.float32); x[:4] = [np.nan, -0.0, 1e30, 0.25]; "
+            "q, b = _lib.pack_q8_values(x, 0.5, 7.5, False); q2, b2 = _lib.pack_q8_values(x, 0.5, 7.5, True); "
+            "ok = np.abs(x * 2) <= 15; ok &= np.rint(np.where(ok, x * 2, 0)) == x * 2; "      # bytes of unencodable values are unspecified
+            "import hashlib; print(hashlib.sha1(q.tobytes() + q2[ok].tobytes()).hexdigest(), b, b2)" % ROOT)
+    outs = []
+    for env in ({}, {"LDPC_B200_NO_AVX2": "1"}, {"LDPC_B200_HOST_THREADS": "1"}):
+        e = dict(os.environ); e.update(env)
+        outs.append(subprocess.run([sys.executable, "-c", code], capture_output=True, text=True, env=e, check=True).stdout.strip())
+    assert outs[0] == outs[1] == outs[2], outs
+
+
+def test_pack_q8_values_rejects_bad_arguments():
+    from ldpc_error_floor_b200 import _lib
+    x = np.zeros(8, dtype=np.float32)
+    for step, qmax in ((0.0, 7.5), (0.5, 0.0), (0.01, 7.5)):       # qmax / step must fit int8
+        with pytest.raises(_lib.LdpcError):
+            _lib.pack_q8_values(x, step, qmax, False)
