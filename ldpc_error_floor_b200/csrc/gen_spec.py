@@ -41,7 +41,7 @@ GEOMETRIES = {
 GEOMETRIES_NOET = {"wimax": (8, 2)}
 # float32 kernels (one frame per lane): same lanes as the packed choice
 GEOMETRIES_F32 = {
-    "wimax": [(4, 2)], "wifi": [(7, 2)], "5g_r073_z72": [(4, 2)], "5g_r050_z64": [(2, 2)], "5g_r050_z32": [(4, 2)],
+    "wimax": [(4, 2)],   # round-2 re-sweep (profiles/r02_f32_geometry_sweep.txt): (8,2) 19.1, (4,2) 18.8, (16,2) 18.8, (8,3) 17.1, (4,3) 16.8, (2,2) 12.6 "wifi": [(7, 2)], "5g_r073_z72": [(4, 2)], "5g_r050_z64": [(2, 2)], "5g_r050_z32": [(4, 2)],
     "5g_r033_z32": [(4, 2)], "5g_r073_z32": [(4, 2)], "mackay": [(32, 8)], "bch": [(32, 4)],
 }
 # persistent-slot Monte-Carlo kernels (nms_mcp.cuh: no float channel array, no ballots -> smaller CTAs, more of them per SM).
