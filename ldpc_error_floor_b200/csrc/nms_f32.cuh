@@ -173,10 +173,19 @@ __device__ __forceinline__ void f32_min12t(const uint32_t (&raw)[DC], float &m1,
 template <int DC>
 __device__ __forceinline__ void f32_min12(const uint32_t (&raw)[DC], float &m1, float &m2) { f32_min12t<DC, 0, DC>(raw, m1, m2); }
 
+__device__ __forceinline__ uint32_t opaque_xor(uint32_t a, uint32_t b) {
+    uint32_t r;
+    asm("xor.b32 %0, %1, %2;" : "=r"(r) : "r"(a), "r"(b));
+    return r;
+}
+
 // one check row held in registers, one weight per row.  a0: byte address of msg[e0][q]; stride4 = LP*4
 // par: this lane's syndrome bit of the previous hard decision (f32_row_syndrome)
+// Returns false -- nothing written -- when the row holds a zero V->C on the float path of a graph-specialised kernel
+// (QM == 0): the caller then runs the two-pass row code, which is a call, so the rare case costs the common one no
+// register moves (patching the register array in line made ptxas keep two copies of it: 56 MOVs per 3 rows).
 template <int DC, int QM>
-__device__ __forceinline__ void cn_row_f32(const KParams &P, uint32_t a0, uint32_t stride4, float w0, float w1,
+__device__ __forceinline__ bool cn_row_f32(const KParams &P, uint32_t a0, uint32_t stride4, float w0, float w1,
                                            uint32_t par) {
     uint32_t raw[DC];
 #pragma unroll
@@ -186,7 +195,10 @@ __device__ __forceinline__ void cn_row_f32(const KParams &P, uint32_t a0, uint32
     for (int p = 0; p < DC; ++p) sx ^= raw[p];
     float m1, m2;
     f32_min12<DC>(raw, m1, m2);
-    if (QM != 1 && m1 == 0.0f) {   // a zero V->C counts as +1e-4 (:230): rare on the float path, so patch the zeros and redo the minima
+    if constexpr (QM == 0) {
+        if (m1 == 0.0f) return false;   // a zero V->C counts as +1e-4 (:230): rare on the float path
+    }
+    if (QM == 2 && m1 == 0.0f) {   // run-time mode (generic kernels): patch the zeros and redo the minima
 #pragma unroll
         for (int p = 0; p < DC; ++p) raw[p] = __uint_as_float(raw[p]) == 0.0f ? __float_as_uint(0.0001f) : raw[p];
         f32_min12<DC>(raw, m1, m2);
@@ -195,13 +207,17 @@ __device__ __forceinline__ void cn_row_f32(const KParams &P, uint32_t a0, uint32
     // C->V of edge p is negative iff the number of positive OTHER inputs is even (:251-254; an input is never 0, :230):
     // sign bit = sign(adjusted min) ^ (dc & 1) ^ parity(negative inputs) ^ own sign
     const uint32_t Pbit = (sx ^ ((DC & 1) ? SIGN1 : 0u)) & SIGN1;
-    const uint32_t A = f32_row_mag<QM, true>(P, __float_as_uint(m1), w) ^ Pbit,
-                   B = f32_row_mag<QM, (DC >= 2)>(P, __float_as_uint(m2), w) ^ Pbit;   // degree 1: min2 is the 10000 of :248
+    // The row's sign parity is folded into A and B ONCE, through an opaque XOR: left to itself the compiler pulls it back out
+    // of the select (select(c, a ^ p, b ^ p) -> select(c, a, b) ^ p), and sel ^ p ^ (raw & SIGN) then has four inputs -- two
+    // LOP3 per edge instead of one on the busiest pipe of this kernel.
+    const uint32_t A = opaque_xor(f32_row_mag<QM, true>(P, __float_as_uint(m1), w), Pbit),
+                   B = opaque_xor(f32_row_mag<QM, (DC >= 2)>(P, __float_as_uint(m2), w), Pbit);   // degree 1: min2 is the 10000 of :248
 #pragma unroll
     for (int p = 0; p < DC; ++p) {
         const uint32_t v = fabsf(__uint_as_float(raw[p])) > m1 ? A : B;   // others' minimum: min1 unless this edge is it
         sts32(a0 + p * stride4, v ^ (raw[p] & SIGN1));
     }
+    return true;
 }
 
 // magnitude of a V->C word as the check sees it: a zero counts as +1e-4 (:230)

@@ -72,7 +72,7 @@ struct F32SpecPolicy {
     // degree, G::cn_cls_cnt[slot][class] of them), the row list read one entry ahead, weights that do not vary per row loaded
     // once per phase (WROW = false) -- the structure of spec_cn_rows in nms_h2_spec.cuh
     template <bool WROW>
-    static __device__ __forceinline__ void cn_rows(const KParams &P, const Ctx &c, uint32_t a00, uint32_t hb4, uint32_t et2c,
+    static __device__ __forceinline__ void cn_rows(const KParams &P, const Ctx &c, int t, uint32_t a00, uint32_t hb4, uint32_t et2c,
                                                    uint32_t w0row, int m0, uint32_t w1row, int m1, uint32_t &bad) {
         constexpr int NT = (G::M + G::R - 1) / G::R;
         float w0 = 1.0f, w1 = 1.0f;
@@ -98,7 +98,8 @@ struct F32SpecPolicy {
                     w0 = ldsf(w0row + (uint32_t)((i & m0) * 4));
                     w1 = ldsf(w1row + (uint32_t)((i & m1) * 4));
                 }
-                cn_row_f32<DC, QM>(P, a00 + cur.x, LP4, w0, w1, par);
+                if (!cn_row_f32<DC, QM>(P, a00 + cur.x, LP4, w0, w1, par))
+                    cn_row_f32_generic<QM>(P, a00 + cur.x, LP4, DC, t, (int)(cur.y >> 16), (int)(cur.x / LP4), par);
             }
         });
     }
@@ -116,8 +117,8 @@ struct F32SpecPolicy {
         const uint32_t w1row = P.sharing1 != 0 ? h.sb + (uint32_t)(P.off_w + P.w_off_ucn + t * P.wu) * 4u : w0row;
         const int m1 = P.sharing1 != 0 ? (P.wu > 1 ? -1 : 0) : m0;
         if (!(QM == 0 && P.sp) && P.sharing0 != 1) {   // uniform
-            if ((m0 | m1) != 0) cn_rows<true>(P, c, a00, hb4, et2c, w0row, m0, w1row, m1, bad);
-            else cn_rows<false>(P, c, a00, hb4, et2c, w0row, m0, w1row, m1, bad);
+            if ((m0 | m1) != 0) cn_rows<true>(P, c, t, a00, hb4, et2c, w0row, m0, w1row, m1, bad);
+            else cn_rows<false>(P, c, t, a00, hb4, et2c, w0row, m0, w1row, m1, bad);
             return;
         }
         constexpr int NT = (G::M + G::R - 1) / G::R;
