@@ -47,6 +47,16 @@ __device__ __forceinline__ float qround(float x, float magic) { return __fsub_rn
 __device__ __forceinline__ float2 qround2(float2 x, float magic) {
     return __fadd2_rn(__fadd2_rn(x, make_float2(magic, magic)), make_float2(-magic, -magic));
 }
+// x * w for two values, each product rounded to float32 on its own.  NOT __fmul2_rn: ptxas (12.9) contracts
+// mul.rn.f32x2 + add.rn.f32x2 into one FFMA2 -- it keeps the scalar forms apart, and neither -fmad=false nor an asm barrier
+// stops it -- and Q(x * w) = rint(float32(x * w) * qk) / qk is a DOUBLE rounding: fused, 2.5 * 0.9f = 2.25000009 rounds to 2.5
+// where the reference (float32 product 2.25, tie to even) gives 2.0.  One in 5e6 (level, weight) pairs differs, among them
+// weights as plain as 0.9f, 0.85f and 0.95f (tests/test_gpu_parity.py: DOUBLE_ROUNDING_WEIGHTS).  An explicit fused
+// multiply-add with a zero addend IS the rounded product (a -0 product becomes +0, which the quantiser's add erases
+// anyway), still one instruction for both values, and nothing may fold a further add into it.
+__device__ __forceinline__ float2 mul2_rn_unfused(float2 x, float2 w) {
+    return __ffma2_rn(x, w, make_float2(0.0f, 0.0f));
+}
 __device__ __forceinline__ float qf(const KParams &P, float x) {   // full float quantiser
     return fminf(fmaxf(qround(x, P.qmagic), -P.qmax), P.qmax);
 }

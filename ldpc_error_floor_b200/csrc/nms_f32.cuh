@@ -181,12 +181,16 @@ __device__ __forceinline__ uint32_t opaque_xor(uint32_t a, uint32_t b) {
 
 // one check row held in registers, one weight per row.  a0: byte address of msg[e0][q]; stride4 = LP*4
 // par: this lane's syndrome bit of the previous hard decision (f32_row_syndrome)
-// Returns false -- nothing written -- when the row holds a zero V->C on the float path of a graph-specialised kernel
-// (QM == 0): the caller then runs the two-pass row code, which is a call, so the rare case costs the common one no
-// register moves (patching the register array in line made ptxas keep two copies of it: 56 MOVs per 3 rows).
-template <int DC, int QM>
-__device__ __forceinline__ bool cn_row_f32(const KParams &P, uint32_t a0, uint32_t stride4, float w0, float w1,
-                                           uint32_t par) {
+// ZERO: what to do about a zero V->C, which counts as +1e-4 (:230) --
+//   ZERO_PATCH  patch the register array and redo the minima in line (generic kernels, run-time mode);
+//   ZERO_BAIL   return false with nothing written (float path of the graph-specialised kernels): the caller then CALLS the
+//               patched form, so the rare case costs the common one no register moves -- patching in line made ptxas keep
+//               two copies of the array, 56 MOVs per 3 rows.  Rare means: float messages are zero when a channel value
+//               is (words on a quantiser grid fed to the float decoder: iteration 0 only).
+enum { ZERO_NONE = 0, ZERO_PATCH = 1, ZERO_BAIL = 2 };
+template <int DC, int QM, int ZERO>
+__device__ __forceinline__ bool cn_row_f32_body(const KParams &P, uint32_t a0, uint32_t stride4, float w0, float w1,
+                                                uint32_t par) {
     uint32_t raw[DC];
 #pragma unroll
     for (int p = 0; p < DC; ++p) raw[p] = lds32(a0 + p * stride4);
@@ -195,10 +199,10 @@ __device__ __forceinline__ bool cn_row_f32(const KParams &P, uint32_t a0, uint32
     for (int p = 0; p < DC; ++p) sx ^= raw[p];
     float m1, m2;
     f32_min12<DC>(raw, m1, m2);
-    if constexpr (QM == 0) {
-        if (m1 == 0.0f) return false;   // a zero V->C counts as +1e-4 (:230): rare on the float path
+    if constexpr (ZERO == ZERO_BAIL) {
+        if (m1 == 0.0f) return false;
     }
-    if (QM == 2 && m1 == 0.0f) {   // run-time mode (generic kernels): patch the zeros and redo the minima
+    if (ZERO == ZERO_PATCH && m1 == 0.0f) {
 #pragma unroll
         for (int p = 0; p < DC; ++p) raw[p] = __uint_as_float(raw[p]) == 0.0f ? __float_as_uint(0.0001f) : raw[p];
         f32_min12<DC>(raw, m1, m2);
@@ -218,6 +222,21 @@ __device__ __forceinline__ bool cn_row_f32(const KParams &P, uint32_t a0, uint32
         sts32(a0 + p * stride4, v ^ (raw[p] & SIGN1));
     }
     return true;
+}
+template <int DC, int QM>
+static __device__ __noinline__ void cn_row_f32_zero(const KParams &P, uint32_t a0, uint32_t stride4, float w0, float w1,
+                                                    uint32_t par) {
+    cn_row_f32_body<DC, QM, ZERO_PATCH>(P, a0, stride4, w0, w1, par);
+}
+template <int DC, int QM>
+__device__ __forceinline__ void cn_row_f32(const KParams &P, uint32_t a0, uint32_t stride4, float w0, float w1, uint32_t par) {
+    if constexpr (QM == 0) {          // float path, specialised kernels
+        if (!cn_row_f32_body<DC, 0, ZERO_BAIL>(P, a0, stride4, w0, w1, par)) cn_row_f32_zero<DC, 0>(P, a0, stride4, w0, w1, par);
+    } else if constexpr (QM == 1) {   // quantised twin: a zero stays the row's minimum and needs no patching (f32_row_mag)
+        cn_row_f32_body<DC, 1, ZERO_NONE>(P, a0, stride4, w0, w1, par);
+    } else {
+        cn_row_f32_body<DC, 2, ZERO_PATCH>(P, a0, stride4, w0, w1, par);
+    }
 }
 
 // magnitude of a V->C word as the check sees it: a zero counts as +1e-4 (:230)

@@ -98,8 +98,7 @@ struct F32SpecPolicy {
                     w0 = ldsf(w0row + (uint32_t)((i & m0) * 4));
                     w1 = ldsf(w1row + (uint32_t)((i & m1) * 4));
                 }
-                if (!cn_row_f32<DC, QM>(P, a00 + cur.x, LP4, w0, w1, par))
-                    cn_row_f32_generic<QM>(P, a00 + cur.x, LP4, DC, t, (int)(cur.y >> 16), (int)(cur.x / LP4), par);
+                cn_row_f32<DC, QM>(P, a00 + cur.x, LP4, w0, w1, par);
             }
         });
     }

@@ -110,8 +110,8 @@ __device__ __forceinline__ void h2_row_mags(const KParams &P, float w0lo, float 
     const float whi = (par & 0x10000u) ? w1hi : w0hi;
     // Q(relu(min * w)) (:308-311)
     const float2 w2 = make_float2(wlo, whi);
-    const float2 qa = qround2(__fmul2_rn(__half22float2(m1c), w2), P.qmagic);
-    const float2 qb = qround2(__fmul2_rn(__half22float2(m2c), w2), P.qmagic);
+    const float2 qa = qround2(mul2_rn_unfused(__half22float2(m1c), w2), P.qmagic);
+    const float2 qb = qround2(mul2_rn_unfused(__half22float2(m2c), w2), P.qmagic);
     __half2 magA = __floats2half2_rn(qa.x, qa.y);
     __half2 magB = __floats2half2_rn(qb.x, qb.y);
     magA = __hmax2(__hmin2(magA, qm), zero);

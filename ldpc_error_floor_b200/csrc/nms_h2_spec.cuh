@@ -153,7 +153,7 @@ struct H2SpecPolicy {
         __half2 xin = xqh;
         if constexpr (VNW) {
             const float w = P.h2_mv != 0 ? h2_w(wvrow, J, -1) : wvs;       // uniform branch
-            const float2 xw = __fmul2_rn(x, make_float2(w, w));
+            const float2 xw = mul2_rn_unfused(x, make_float2(w, w));
             xin = q2(P, xw.x, xw.y);                             // Q(xa * w), :168-177
         }
         // hard bit = (value >= 0): of xin_0 before iteration 0 (:181-182), of the APP afterwards (a zero is +0)

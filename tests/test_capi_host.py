@@ -241,3 +241,25 @@ def test_pack_q8_values_rejects_bad_arguments():
     for step, qmax in ((0.0, 7.5), (0.5, 0.0), (0.01, 7.5)):       # qmax / step must fit int8
         with pytest.raises(_lib.LdpcError):
             _lib.pack_q8_values(x, step, qmax, False)
+
+
+def test_no_fused_packed_multiply_add_in_the_decode_kernels():
+    """The quantiser rounds twice (float32 product, then rint to the grid); ptxas 12.9 fuses mul.rn.f32x2 + add.rn.f32x2 into
+    one FFMA2 behind the programmer's back, which rounds once and differs for weights like 0.9f (nms_device.cuh
+    mul2_rn_unfused).  Static guard on the built objects: every FFMA2 in the packed decode kernels has a zero addend."""
+    import shutil
+    import subprocess
+    build = os.path.join(ROOT, "ldpc_error_floor_b200", "csrc", "build")
+    objs = [os.path.join(build, n) for n in ("spec_wimax_fp8_r2.o", "spec_wimax_fp4_r2.o", "spec_mcp_5g_r073_z72_fp4_r2.o",
+                                             "spec_mcp_wimax_fp4_r2.o", "nms_h2_16_8.o", "nms_h2_0_0.o")]
+    objs = [o for o in objs if os.path.exists(o)]
+    if not objs or shutil.which("cuobjdump") is None:
+        pytest.skip("no built objects / cuobjdump here")
+    seen = 0
+    for o in objs:
+        sass = subprocess.run(["cuobjdump", "-sass", o], capture_output=True, text=True, check=True).stdout
+        for line in sass.splitlines():
+            if "FFMA2" in line:
+                seen += 1
+                assert "RZ.F32" in line.split(";")[0], f"{os.path.basename(o)}: fused packed multiply-add: {line.strip()}"
+    assert seen > 0

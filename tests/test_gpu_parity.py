@@ -597,3 +597,65 @@ def test_custom_op_handle_is_stable():
     assert torch.equal(dec.decode(xa).hard_packed, a[0])
     with pytest.raises(RuntimeError):
         torch.ops.ldpc_b200.nms_decode(xa, 10 ** 9, 0, False, 0)
+
+
+# weights for which float32(k * 0.5 * w) lands exactly on a half step although the exact product does not: the reference
+# rounds TWICE (float32 product, then rint to the grid, Main_Functions.py:267-311, 475-494), so a kernel that fuses the
+# multiply into the quantiser's add differs by one step -- ptxas 12.9 does that to mul.rn.f32x2 + add.rn.f32x2 on its own
+# (nms_device.cuh mul2_rn_unfused).  0.9f, 0.85f and 0.95f are among them.
+DOUBLE_ROUNDING_WEIGHTS = [0.9, 0.85, 0.95, 0.8333333730697632, 0.9166666269302368, 1.0714285373687744]
+
+
+def test_double_rounding_weights_exist():
+    """CPU-side sanity of the constants above (float64 holds the exact product of two float32)."""
+    k = np.arange(1, 16, dtype=np.float32) * np.float32(0.5)
+    for w in DOUBLE_ROUNDING_WEIGHTS:
+        p = k.astype(np.float64) * np.float64(np.float32(w))
+        fused = np.rint(p * 2) / 2
+        twice = np.rint(np.float32(p).astype(np.float64) * 2) / 2
+        assert (fused != twice).any(), w
+
+
+@pytest.mark.parametrize("graph", ["wimax_qms_333_t20", "5g_r073_z72_qms_300_t20_sys", "mackay_qms_300_t20"])
+@pytest.mark.parametrize("raw", [False, True])
+def test_weights_that_expose_a_fused_multiply_add(graph, raw):
+    """Decoders whose CN / UCN / VN weights are the double-rounding constants, against the C oracle: fast path (no APP
+    output, unrolled kernels), APP path, persistent-slot Monte-Carlo kernel; on-grid words and raw float32 LLRs."""
+    import torch
+    import ldpc_error_floor_b200 as L
+    from oracle import c_oracle
+    case = load_case(graph)
+    g = L.BaseGraph(case["proto"], case["z"], case["punct"], case["short"])
+    T = 12
+    wc = np.array([DOUBLE_ROUNDING_WEIGHTS[t % 6] for t in range(T)], dtype=np.float32).reshape(T, 1)
+    wu = np.array([DOUBLE_ROUNDING_WEIGHTS[(t + 2) % 6] for t in range(T)], dtype=np.float32).reshape(T, 1)
+    wv = np.array([DOUBLE_ROUNDING_WEIGHTS[(t + 4) % 6] for t in range(T)], dtype=np.float32).reshape(T, 1)
+    sharing, blocks = [3, 3, 3], {0: wc, 1: wu, 2: wv}
+    dec = L.NMSDecoder(g, L.WeightSet(sharing, blocks), iters=T, decoding_type=2, q_bit=5, clip_llr=20.0)
+    assert dec.packed
+    B = 2500
+    sigma = float(g.sigma([3.0])[0])
+    if raw:
+        rng = np.random.RandomState(77)
+        xa = (2.0 * (rng.normal(size=(B, g.NZ)) * sigma - 1.0) / sigma ** 2).astype(np.float32)
+    else:
+        xa = dec.generate(sigma, B, seed=5).reshape(B, -1).cpu().numpy()
+    ref = c_oracle.decode(case["proto"], case["z"], xa.reshape(B, g.N, g.z), sharing, blocks, T, 2, 5, 20.0, want_all=True)
+    hard_ref = ref["app"] >= 0                                   # [T, B, NZ]
+    synd_ok = ~ref["synd"]
+    iters = np.where(synd_ok.any(axis=0), synd_ok.argmax(axis=0) + 1, T)
+    xd = torch.from_numpy(xa).cuda()
+    fast = dec.decode(xd, unpack=True)                           # unrolled kernels
+    assert np.array_equal(fast.hard.cpu().numpy().astype(bool), hard_ref[T - 1])
+    assert np.array_equal(fast.iters.cpu().numpy(), iters)
+    slow = dec.decode(xd, app="all")                             # table-driven VN phase
+    assert np.array_equal(slow.app.reshape(T, B, -1).cpu().numpy(), ref["app"])
+    et = dec.decode(xd, early_term=True, unpack=True)
+    stop = np.where(synd_ok.any(axis=0), synd_ok.argmax(axis=0), T - 1)
+    assert np.array_equal(et.hard.cpu().numpy().astype(bool), hard_ref[stop, np.arange(B)])
+    if not raw:                                                  # the fused Monte-Carlo launch draws these very words
+        cnt, _ = dec.mc_run_host(sigma, B, seed=5, early_term=True)
+        ones = hard_ref.sum(axis=2)
+        assert cnt["iters"] == int(iters.sum())
+        assert cnt["frame_err_last"] == int((ones[stop, np.arange(B)] > 0).sum())
+        assert cnt["bit_err_last"] == int(ones[stop, np.arange(B)].sum())
