@@ -86,6 +86,8 @@ struct Ctx {
     int a_lane;   // circulant lane of q
     long long frame0;
     int nvalid;
+    int og;       // 1: every channel value of this warp's lanes is on the quantiser grid and inside +-qmax (batch in flight;
+                  // only policies with TRACKS_GRID look at it)
 };
 
 // is frame f frozen as far as the VN phase of iteration t can tell?  (only used for the optional APP output)
@@ -325,17 +327,15 @@ __device__ __forceinline__ void nms_decode_body(const KParams &P) {
         }
 
         // ---------------- init pass: xq, first V->C messages, hard bits of xin_0
+        c.og = 0;
+        uint32_t offgrid = 0;   // policies with TRACKS_GRID: OR of "this value has no exact grid form" over the thread's columns
         if constexpr (Policy::FUSED_LOAD) {
-            if (fused) {
-                Policy::load_init(P, c);
-            } else {
-                uint32_t dummy = 0;
-                Policy::template vn_phase<true>(P, c, -1, true, dummy);
-            }
+            if (fused) Policy::load_init(P, c, offgrid);
+            else Policy::template vn_phase<true>(P, c, -1, true, offgrid);
         } else {
-            uint32_t dummy = 0;
-            Policy::template vn_phase<true>(P, c, -1, true, dummy);
+            Policy::template vn_phase<true>(P, c, -1, true, offgrid);
         }
+        if constexpr (Policy::TRACKS_GRID) c.og = __all_sync(0xffffffffu, offgrid == 0u) ? 1 : 0;
         __syncthreads();
 
         bool alldone = false;

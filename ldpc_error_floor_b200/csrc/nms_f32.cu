@@ -19,6 +19,7 @@ template <int DCB, int DVB>
 struct F32Policy {
     static constexpr bool H2 = false;
     static constexpr bool FUSED_LOAD = false;
+    static constexpr bool TRACKS_GRID = false;
     static __device__ __forceinline__ void setup(const KParams &, int) {}
 
     static __device__ __forceinline__ void cn_phase(const KParams &P, const Ctx &c, int t, uint32_t &bad) {

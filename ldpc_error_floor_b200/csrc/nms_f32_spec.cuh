@@ -29,6 +29,7 @@ template <class G, int QM>
 struct F32SpecPolicy {
     static constexpr bool H2 = false;
     static constexpr bool FUSED_LOAD = true;
+    static constexpr bool TRACKS_GRID = false;
     static constexpr uint32_t LP4 = G::LP * 4u;
     static constexpr bool PAD = G::L != G::LP;
     enum { F_ITER = 0, F_INIT_GLOBAL = 2 };   // VN column code: iteration t / pass before iteration 0 fed from global memory
@@ -261,7 +262,7 @@ struct F32SpecPolicy {
     }
 
     // channel LLRs straight from global memory into the first V->C messages (replaces load + init pass)
-    static __device__ __forceinline__ void load_init(const KParams &P, const Ctx &c) {
+    static __device__ __forceinline__ void load_init(const KParams &P, const Ctx &c, uint32_t &) {
         const F32Ctx h = f32_ctx(P, c);
         uint32_t dummy = 0;
         vn_dispatch<F_INIT_GLOBAL>(P, c, h, 0, 1, dummy);   // hard bits of xin_0 -> ballot buffer 1

@@ -16,6 +16,7 @@ template <int DCB, int DVB>
 struct H2Policy {
     static constexpr bool H2 = true;
     static constexpr bool FUSED_LOAD = false;
+    static constexpr bool TRACKS_GRID = false;
     static __device__ __forceinline__ void setup(const KParams &, int) {}
 
     template <int DC>

@@ -95,6 +95,7 @@ template <class G>
 struct H2SpecPolicy {
     static constexpr bool H2 = true;
     static constexpr bool FUSED_LOAD = true;
+    static constexpr bool TRACKS_GRID = true;   // the init pass reports off-grid channel values (Ctx::og)
     static constexpr uint32_t LP4 = G::LP * 4u;
     static constexpr bool PAD = G::L != G::LP;
     static __device__ __forceinline__ void setup(const KParams &, int) {}
@@ -114,7 +115,11 @@ struct H2SpecPolicy {
     //   VNW: VN weights present.  HB: publish the hard decisions as ballots (a copy-out may follow).
     // wvs: the VN weight when it does not vary per column (sharing code 3: loaded once per phase), NaN-free sentinel < 0
     // otherwise (sharing code 2: fetched per column from wvrow)
-    template <int J, int MODE, bool VNW, bool HB>
+    //   MV:  VN weights vary per column (sharing code 2: fetched per column from wvrow) -- else `wvs` is THE weight of the
+    //        iteration (code 3: loaded once per phase)
+    //   OG:  this warp's channel values are on the quantiser grid and inside +-qmax (found by the init pass, which reports
+    //        off-grid values through `ones`): Q(xa) is then xa itself, one pack instead of round + pack + clamp
+    template <int J, int MODE, bool VNW, bool HB, bool MV, bool OG>
     static __device__ __forceinline__ void vn_col(const KParams &P, const H2Ctx &h, uint32_t wvrow, float wvs, uint32_t hbrow,
                                                   float2 xg, uint32_t &ones) {
         constexpr int C0 = G::col_ptr[J], DV = G::col_ptr[J + 1] - C0;
@@ -144,15 +149,21 @@ struct H2SpecPolicy {
         if constexpr (MODE == VN_INIT_SMEM || (MODE == VN_ITER && VNW)) x = lds64f(h.xa8 + XA8);
         // With VN weights xa is loaded anyway, so Q(xa) is recomputed (6 instructions) instead of kept in an array of its
         // own: 9 KB less shared memory per CTA on WiMAX, i.e. a fourth resident CTA (KParams::no_xq, set by the host).
-        if constexpr (INIT || VNW) {
+        if constexpr (!INIT && VNW && OG) {
+            xqh = __floats2half2_rn(x.x, x.y);           // Q(xa) = xa: exact
+        } else if constexpr (INIT || VNW) {
             xqh = q2(P, x.x, x.y);                       // Q(xa), :321-322
             if constexpr (!VNW) sts32(h.xq4 + XQ4, h2u(xqh));
+            if constexpr (INIT && VNW) {                 // any value off the grid or outside +-qmax?  (NaN: yes)
+                const float2 back = __half22float2(xqh);   // compared as bits: -0.0 (Q gives +0.0) counts as off the grid
+                ones |= (__float_as_uint(back.x) ^ __float_as_uint(x.x)) | (__float_as_uint(back.y) ^ __float_as_uint(x.y));
+            }
         } else {
             xqh = u2h(lds32(h.xq4 + XQ4));
         }
         __half2 xin = xqh;
         if constexpr (VNW) {
-            const float w = P.h2_mv != 0 ? h2_w(wvrow, J, -1) : wvs;       // uniform branch
+            const float w = MV ? h2_w(wvrow, J, -1) : wvs;
             const float2 xw = mul2_rn_unfused(x, make_float2(w, w));
             xin = q2(P, xw.x, xw.y);                             // Q(xa * w), :168-177
         }
@@ -179,7 +190,7 @@ struct H2SpecPolicy {
         }
     }
 
-    template <int SLOT, int MODE, bool VNW, bool HB>
+    template <int SLOT, int MODE, bool VNW, bool HB, bool MV, bool OG>
     static __device__ __forceinline__ void vn_slot(const KParams &P, const Ctx &c, const H2Ctx &h, uint32_t wvrow, float wvs,
                                                    uint32_t hbrow, uint32_t &ones) {
         constexpr int NT = (G::N - SLOT + G::R - 1) / G::R;
@@ -206,12 +217,12 @@ struct H2SpecPolicy {
             }
             static_for<0, NT>([&](auto n) {
                 constexpr int J = G::vn_order[SLOT + decltype(n)::v * G::R];
-                vn_col<J, MODE, VNW, HB>(P, h, wvrow, wvs, hbrow, x[decltype(n)::v], ones);
+                vn_col<J, MODE, VNW, HB, MV, OG>(P, h, wvrow, wvs, hbrow, x[decltype(n)::v], ones);
             });
         } else {
             static_for<0, NT>([&](auto n) {
                 constexpr int J = G::vn_order[SLOT + decltype(n)::v * G::R];
-                vn_col<J, MODE, VNW, HB>(P, h, wvrow, wvs, hbrow, make_float2(0.0f, 0.0f), ones);
+                vn_col<J, MODE, VNW, HB, MV, OG>(P, h, wvrow, wvs, hbrow, make_float2(0.0f, 0.0f), ones);
             });
         }
     }
@@ -224,12 +235,21 @@ struct H2SpecPolicy {
         const uint32_t hbrow = h.sb + (uint32_t)(P.off_hb + tbuf * 2 * G::N * G::C + c.chunk) * 4u;
         if (P.sharing2 != 0) {
             const float wvs = ldsf(wvrow);                       // element 0 of the row: THE weight when sharing code is 3
+            const bool og = MODE == VN_ITER && c.og != 0;        // uniform per warp
             static_for<0, G::R>([&](auto s) {
-                if (c.slot == decltype(s)::v) vn_slot<decltype(s)::v, MODE, true, HB>(P, c, h, wvrow, wvs, hbrow, ones);
+                constexpr int S = decltype(s)::v;
+                if (c.slot != S) return;
+                if (P.h2_mv != 0) {                              // uniform
+                    if (og) vn_slot<S, MODE, true, HB, true, MODE == VN_ITER>(P, c, h, wvrow, wvs, hbrow, ones);
+                    else vn_slot<S, MODE, true, HB, true, false>(P, c, h, wvrow, wvs, hbrow, ones);
+                } else {
+                    if (og) vn_slot<S, MODE, true, HB, false, MODE == VN_ITER>(P, c, h, wvrow, wvs, hbrow, ones);
+                    else vn_slot<S, MODE, true, HB, false, false>(P, c, h, wvrow, wvs, hbrow, ones);
+                }
             });
         } else {
             static_for<0, G::R>([&](auto s) {
-                if (c.slot == decltype(s)::v) vn_slot<decltype(s)::v, MODE, false, HB>(P, c, h, wvrow, 1.0f, hbrow, ones);
+                if (c.slot == decltype(s)::v) vn_slot<decltype(s)::v, MODE, false, HB, false, false>(P, c, h, wvrow, 1.0f, hbrow, ones);
             });
         }
     }
@@ -253,10 +273,9 @@ struct H2SpecPolicy {
     }
 
     // channel LLRs straight from global memory into the first V->C messages (replaces load + init pass)
-    static __device__ __forceinline__ void load_init(const KParams &P, const Ctx &c) {
+    static __device__ __forceinline__ void load_init(const KParams &P, const Ctx &c, uint32_t &offgrid) {
         const H2Ctx h = h2_ctx(P, c);
-        uint32_t dummy = 0;
-        vn_dispatch<VN_INIT_GLOBAL, false>(P, c, h, 0, 0, dummy);
+        vn_dispatch<VN_INIT_GLOBAL, false>(P, c, h, 0, 0, offgrid);
     }
 
     // ------------------------------------------------------------------ final syndrome pass
