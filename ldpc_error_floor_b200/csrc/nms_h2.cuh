@@ -155,6 +155,18 @@ __device__ __forceinline__ void h2_min12(const uint32_t (&raw)[DC], __half2 &m1,
     }
 }
 
+// sum of the packed words cv[LO..HI) as a balanced tree: log2(n) dependent additions instead of n - 1 (the VN phase waits on
+// fixed-latency dependencies more than on anything else).  Exact in any order: on-grid values, |partial sums| < 512 steps.
+template <int DV, int LO, int HI>
+__device__ __forceinline__ __half2 h2_tree_sum(const uint32_t (&cv)[DV]) {
+    if constexpr (HI - LO == 1) {
+        return u2h(cv[LO]);
+    } else {
+        constexpr int MID = LO + (HI - LO + 1) / 2;
+        return __hadd2(h2_tree_sum<DV, LO, MID>(cv), h2_tree_sum<DV, MID, HI>(cv));
+    }
+}
+
 // one check row held in registers.  a0: byte address of msg[e0][q]; stride4: bytes between edges (LP*4)
 template <int DC>
 __device__ __forceinline__ void cn_row_h2(const KParams &P, uint32_t a0, uint32_t stride4, float w0lo, float w0hi,

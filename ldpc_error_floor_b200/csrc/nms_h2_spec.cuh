@@ -133,11 +133,7 @@ struct H2SpecPolicy {
             if constexpr (!INIT) cv[U] = lds32(addr[U]);
         });
         __half2 S = __float2half2_rn(0.0f);
-        if constexpr (!INIT) {
-            S = u2h(cv[0]);
-#pragma unroll
-            for (int u = 1; u < DV; ++u) S = __hadd2(S, u2h(cv[u]));
-        }
+        if constexpr (!INIT) S = h2_tree_sum<DV, 0, DV>(cv);
         constexpr uint32_t XA8 = (uint32_t)(J * G::LP) * 8u, XQ4 = (uint32_t)(J * G::LP) * 4u;
         float2 x = xg;
         __half2 xqh;

@@ -221,9 +221,8 @@ struct McpKernel {
             addr[U] = h.sb + spec_rot<G, ROT>(h) + X4;
             cv[U] = lds32(addr[U]);
         });
-        __half2 S = __hmul2(u2h(cv[0]), u2h(keep));
-#pragma unroll
-        for (int u = 1; u < DV; ++u) S = __hfma2(u2h(cv[u]), u2h(keep), S);   // exact: cv * 1 + S, or 0 + S
+        // stale words of a refilled half are finite on-grid values, so their sum times 0 is 0: one multiply after the tree
+        const __half2 S = __hmul2(h2_tree_sum<DV, 0, DV>(cv), u2h(keep));
         const __half2 xqh = u2h(lds32(h.xq4 + (uint32_t)(J * G::LP) * 4u));
         __half2 xin = xqh;
         uint32_t hs = h2u(__hadd2(xqh, S));                                   // unclipped APP (a refilled half: xq itself)
