@@ -142,8 +142,9 @@ struct F32SpecPolicy {
     // VNW: VN weights present (wvrow = the next iteration's row).  The hard decisions of the column go out as one
     // ballot word per chunk (hbrow) and are OR-ed into `onesw` (bit l = lane l's decision has a one so far).
     // TALL: every column counts in the error metrics (target_node = N), so the "has a one" word needs no column test.
-    template <int J, int MODE, bool VNW, bool TALL>
-    static __device__ __forceinline__ void vn_col(const KParams &P, const F32Ctx &h, uint32_t wvrow, int wvmask, uint32_t hbrow,
+    // MV: the VN weight varies per column (sharing code 2) -- else element 0 of the row is THE weight (code 3)
+    template <int J, int MODE, bool VNW, bool TALL, bool MV>
+    static __device__ __forceinline__ void vn_col(const KParams &P, const F32Ctx &h, uint32_t wvrow, float wvs, uint32_t hbrow,
                                                   float xg, uint32_t &onesw) {
         constexpr int C0 = G::col_ptr[J], DV = G::col_ptr[J + 1] - C0;
         constexpr bool INIT = MODE != F_ITER;
@@ -180,7 +181,7 @@ struct F32SpecPolicy {
         }
         float xin = QM == 1 ? xqv : xa;
         if constexpr (VNW) {
-            xin = __fmul_rn(xa, ldsf(wvrow + (uint32_t)((J & wvmask) * 4)));   // :168-169
+            xin = __fmul_rn(xa, MV ? ldsf(wvrow + (uint32_t)(J * 4)) : wvs);   // :168-169
             xin = QM == 1 ? qf(P, xin) : f32_pos_zero(xin);                    // :176-177
         }
         const float hsrc = INIT ? xin : __fadd_rn(xqv, S);          // :181-182 / :324 (clip_LLR never changes the sign)
@@ -194,8 +195,8 @@ struct F32SpecPolicy {
         for (int u = 0; u < DV; ++u) sts32(addr[u], f32_v2c<QM>(P, xin, INIT ? 0.0f : ext[u]));
     }
 
-    template <int SLOT, int MODE, bool VNW, bool TALL>
-    static __device__ __forceinline__ void vn_slot(const KParams &P, const Ctx &c, const F32Ctx &h, uint32_t wvrow, int wvmask,
+    template <int SLOT, int MODE, bool VNW, bool TALL, bool MV>
+    static __device__ __forceinline__ void vn_slot(const KParams &P, const Ctx &c, const F32Ctx &h, uint32_t wvrow, float wvs,
                                                    uint32_t hbrow, uint32_t &onesw) {
         constexpr int NT = (G::N - SLOT + G::R - 1) / G::R;
         if constexpr (MODE == F_INIT_GLOBAL) {
@@ -216,11 +217,11 @@ struct F32SpecPolicy {
                 });
             }
             static_for<0, NT>([&](auto n) {
-                vn_col<G::vn_order[SLOT + decltype(n)::v * G::R], MODE, VNW, TALL>(P, h, wvrow, wvmask, hbrow, x[decltype(n)::v], onesw);
+                vn_col<G::vn_order[SLOT + decltype(n)::v * G::R], MODE, VNW, TALL, MV>(P, h, wvrow, wvs, hbrow, x[decltype(n)::v], onesw);
             });
         } else {
             static_for<0, NT>([&](auto n) {
-                vn_col<G::vn_order[SLOT + decltype(n)::v * G::R], MODE, VNW, TALL>(P, h, wvrow, wvmask, hbrow, 0.0f, onesw);
+                vn_col<G::vn_order[SLOT + decltype(n)::v * G::R], MODE, VNW, TALL, MV>(P, h, wvrow, wvs, hbrow, 0.0f, onesw);
             });
         }
     }
@@ -231,17 +232,23 @@ struct F32SpecPolicy {
         const uint32_t hbrow = h.sb + (uint32_t)(P.off_hb + tbuf * G::N * G::C + c.chunk) * 4u;   // hb[buf][j][chunk]
         uint32_t onesw = 0;
         const uint32_t wvrow = h.sb + (uint32_t)(P.off_w + P.w_off_vn + trow * P.wv) * 4u;
-        const int wvmask = P.wv > 1 ? -1 : 0;
+        const bool mv = P.wv > 1;
+        const float wvs = P.sharing2 != 0 ? ldsf(wvrow) : 1.0f;   // THE weight of the iteration when it does not vary per column
         const bool tall = MODE != F_ITER || P.target_n >= G::N;
         static_for<0, G::R>([&](auto s) {
             constexpr int S = decltype(s)::v;
             if (c.slot == S) {
                 if (P.sharing2 != 0) {
-                    if (tall) vn_slot<S, MODE, true, true>(P, c, h, wvrow, wvmask, hbrow, onesw);
-                    else vn_slot<S, MODE, true, false>(P, c, h, wvrow, wvmask, hbrow, onesw);
+                    if (mv) {
+                        if (tall) vn_slot<S, MODE, true, true, true>(P, c, h, wvrow, wvs, hbrow, onesw);
+                        else vn_slot<S, MODE, true, false, true>(P, c, h, wvrow, wvs, hbrow, onesw);
+                    } else {
+                        if (tall) vn_slot<S, MODE, true, true, false>(P, c, h, wvrow, wvs, hbrow, onesw);
+                        else vn_slot<S, MODE, true, false, false>(P, c, h, wvrow, wvs, hbrow, onesw);
+                    }
                 } else {
-                    if (tall) vn_slot<S, MODE, false, true>(P, c, h, 0u, 0, hbrow, onesw);
-                    else vn_slot<S, MODE, false, false>(P, c, h, 0u, 0, hbrow, onesw);
+                    if (tall) vn_slot<S, MODE, false, true, false>(P, c, h, 0u, 1.0f, hbrow, onesw);
+                    else vn_slot<S, MODE, false, false, false>(P, c, h, 0u, 1.0f, hbrow, onesw);
                 }
             }
         });

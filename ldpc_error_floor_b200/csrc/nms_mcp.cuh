@@ -208,7 +208,8 @@ struct McpKernel {
     // freshsel: 0xffff per refilled half.  wv_lo / wv_hi: byte address of the VN weight row of the iteration each half enters.
     // sh_lo / sh_hi: this lane's bit j*z + a is shortened iff sh_lo <= j*z <= sh_hi (VN weights see the SAMPLE there, -clip_LLR,
     // not Q(-clip_LLR) = -qmax: Print_Functions.py:59-60 vs Main_Functions.py:168-177)
-    template <int J, bool VNW>
+    // MV: VN weights vary per column (sharing code 2); else wsl / wsh are THE weights of the two halves' iterations
+    template <int J, bool VNW, bool MV>
     static __device__ __forceinline__ void vn_col(const KParams &P, const H2Ctx &h, uint32_t keep, uint32_t negkeep,
                                                   uint32_t freshsel, uint32_t wv_lo, uint32_t wv_hi, float wsl, float wsh,
                                                   int sh_lo, int sh_hi, uint32_t &cnt) {
@@ -228,7 +229,7 @@ struct McpKernel {
         uint32_t hs = h2u(__hadd2(xqh, S));                                   // unclipped APP (a refilled half: xq itself)
         if constexpr (VNW) {
             // per-column rows (sharing code 2) are fetched here, a per-iteration scalar (code 3) came in with the phase
-            const float wl = P.h2_mv != 0 ? h2_w(wv_lo, J, -1) : wsl, wh = P.h2_mv != 0 ? h2_w(wv_hi, J, -1) : wsh;
+            const float wl = MV ? h2_w(wv_lo, J, -1) : wsl, wh = MV ? h2_w(wv_hi, J, -1) : wsh;
             const bool shortened = J * G::z >= sh_lo && J * G::z <= sh_hi;
             const float xl = shortened ? -P.clip : __low2float(xqh), xh = shortened ? -P.clip : __high2float(xqh);
             xin = q2(P, __fmul_rn(xl, wl), __fmul_rn(xh, wh));               // Q(xa * w), :168-177
@@ -241,14 +242,14 @@ struct McpKernel {
         for (int u = 0; u < DV; ++u) sts32(addr[u], h2u(__hfma2(u2h(cv[u]), u2h(negkeep), SX)) | hbw);   // total - self
     }
 
-    template <int SLOT, bool VNW>
+    template <int SLOT, bool VNW, bool MV>
     static __device__ __forceinline__ void vn_slot(const KParams &P, const H2Ctx &h, uint32_t keep, uint32_t negkeep,
                                                    uint32_t freshsel, uint32_t wv_lo, uint32_t wv_hi, float wsl, float wsh,
                                                    int sh_lo, int sh_hi, uint32_t &cnt) {
         constexpr int NT = (G::N - SLOT + G::R - 1) / G::R;
         static_for<0, NT>([&](auto n) {
             constexpr int J = G::vn_order[SLOT + decltype(n)::v * G::R];
-            vn_col<J, VNW>(P, h, keep, negkeep, freshsel, wv_lo, wv_hi, wsl, wsh, sh_lo, sh_hi, cnt);
+            vn_col<J, VNW, MV>(P, h, keep, negkeep, freshsel, wv_lo, wv_hi, wsl, wsh, sh_lo, sh_hi, cnt);
         });
     }
 
@@ -338,12 +339,13 @@ struct McpKernel {
                     const int sh_lo = P.short_s > 0 ? P.short_s - 1 - a_lane : 0x7fffffff, sh_hi = P.short_e - 1 - a_lane;
                     const float wsl = ldsf(wv_lo), wsh = ldsf(wv_hi);
                     static_for<0, G::R>([&](auto sl_) {
-                        if (slot == decltype(sl_)::v)
-                            vn_slot<decltype(sl_)::v, true>(P, h, keep, keep ^ SIGN2, freshsel, wv_lo, wv_hi, wsl, wsh, sh_lo, sh_hi, cnt);
+                        if (slot != decltype(sl_)::v) return;
+                        if (P.h2_mv != 0) vn_slot<decltype(sl_)::v, true, true>(P, h, keep, keep ^ SIGN2, freshsel, wv_lo, wv_hi, wsl, wsh, sh_lo, sh_hi, cnt);
+                        else vn_slot<decltype(sl_)::v, true, false>(P, h, keep, keep ^ SIGN2, freshsel, wv_lo, wv_hi, wsl, wsh, sh_lo, sh_hi, cnt);
                     });
                 } else {
                     static_for<0, G::R>([&](auto sl_) {
-                        if (slot == decltype(sl_)::v) vn_slot<decltype(sl_)::v, false>(P, h, keep, keep ^ SIGN2, freshsel, 0u, 0u, 1.0f, 1.0f, 0, 0, cnt);
+                        if (slot == decltype(sl_)::v) vn_slot<decltype(sl_)::v, false, false>(P, h, keep, keep ^ SIGN2, freshsel, 0u, 0u, 1.0f, 1.0f, 0, 0, cnt);
                     });
                 }
                 // ones of this hard decision, per slot pair (skipped by warps that saw none: the common case once
