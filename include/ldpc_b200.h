@@ -169,7 +169,8 @@ int ldpc_decode(const ldpc_decoder_t *d, const float *llr_dev, int64_t B, int32_
  * same decoder input bit for bit -- a quantised decoder sees a channel value only through Q(x)
  * (Main_Functions.py:321-322) and, with VN weights, Q(x * w) (:168-177), so words are packed always
  * without VN weights and, with them, whenever every value of the chunk is on the quantiser grid
- * (always, in the reference's flows).  LDPC_B200_NO_HOST_PACK=1 keeps float32 for every chunk,
+ * (always, in the reference's flows).  With fewer than three host threads pinned float32 input is not
+ * packed at all (the DMA engine alone is faster).  LDPC_B200_NO_HOST_PACK=1 keeps float32 for every chunk,
  * LDPC_B200_HOST_THREADS sets the pool size (default: hardware threads / LOCAL_WORLD_SIZE, <= 16). */
 int ldpc_decode_host(const ldpc_decoder_t *d, const float *llr_host, int64_t B, int32_t iters,
                      int32_t early_term, float *app_host, int32_t app_all_iters,

@@ -54,7 +54,7 @@ def test_on_grid_words_cross_as_int8_with_identical_results(name, B):
         short = g.short[1] > g.short[0]   # shortened bits carry -clip_LLR: outside the int8 range when VN weights are present
         if not short:
             assert st["chunks_unencodable"] == 0, st
-            assert st["chunks_q8"] >= 1, st
+            assert st["chunks_q8"] >= 1 or st["threads"] < 3, st   # fewer than three host threads: pinned words stay float32
         assert st["chunks_q8"] + st["chunks_f32"] + st["chunks_unencodable"] >= 1
         h2 = dec.decode_host(xh.numpy(), early_term=et)          # pageable: every chunk packed
         st2 = dec.host_stats()
@@ -101,7 +101,7 @@ def test_off_grid_words_with_vn_weights_stay_float32():
         h = dec.decode_host(src)
         st = dec.host_stats()
         same(h, r)
-        assert st["chunks_q8"] == 0 and st["chunks_unencodable"] >= 1, st
+        assert st["chunks_q8"] == 0 and (st["chunks_unencodable"] >= 1 or st["threads"] < 3), st   # < 3 host threads: pinned words are not even tried
     # a word set that is on the grid except for one value in the last chunk
     y = dec.generate(float(g.sigma([2.5])[0]), B, seed=9).reshape(B, -1).cpu().numpy().copy()
     y[B - 3, 17] = 0.3
