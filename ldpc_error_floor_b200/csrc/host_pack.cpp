@@ -18,6 +18,8 @@
 #include <thread>
 #include <vector>
 
+#include <unistd.h>
+
 #if defined(__x86_64__)
 #include <immintrin.h>
 #define HOSTPACK_X86 1
@@ -205,7 +207,16 @@ class Pool {
 };
 
 Pool &pool() {
-    static Pool *p = new Pool();   // never destroyed: worker threads must not be joined from a static destructor at exit
+    // never destroyed: worker threads must not be joined from a static destructor at exit.  A forked child (a Python
+    // multiprocessing worker) inherits the pointer but none of the threads: it gets a pool of its own.
+    static std::mutex mu;
+    static Pool *p = nullptr;
+    static pid_t owner = 0;
+    std::lock_guard<std::mutex> lk(mu);
+    if (p == nullptr || owner != getpid()) {
+        p = new Pool();
+        owner = getpid();
+    }
     return *p;
 }
 

@@ -263,3 +263,17 @@ def test_no_fused_packed_multiply_add_in_the_decode_kernels():
                 seen += 1
                 assert "RZ.F32" in line.split(";")[0], f"{os.path.basename(o)}: fused packed multiply-add: {line.strip()}"
     assert seen > 0
+
+
+def test_host_pool_survives_a_fork():
+    """A forked child (Python multiprocessing) inherits the pool object but none of its threads; it must get its own."""
+    import subprocess
+    import sys
+    code = ("import os, sys, numpy as np; sys.path.insert(0, %r); from ldpc_error_floor_b200 import _lib; "
+            "x = (np.random.default_rng(0).standard_normal(3000000) * 5).astype(np.float32); "
+            "q, b = _lib.pack_q8_values(x, 0.5, 7.5, False); pid = os.fork(); "
+            "ok = pid != 0 or np.array_equal(q, _lib.pack_q8_values(x, 0.5, 7.5, False)[0]); "
+            "pid == 0 and os._exit(0 if ok else 3); "
+            "print(os.WEXITSTATUS(os.waitpid(pid, 0)[1]))" % ROOT)
+    out = subprocess.run([sys.executable, "-W", "ignore", "-c", code], capture_output=True, text=True, timeout=120)
+    assert out.stdout.strip() == "0", (out.stdout, out.stderr)
