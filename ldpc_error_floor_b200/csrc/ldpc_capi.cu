@@ -1274,6 +1274,7 @@ int decode_host_impl(const ldpc_decoder_t *dc, const void *src_host, bool q8, fl
     }
     feed.rq_closed.store(true, std::memory_order_release);
     if (feeder_thread.joinable()) feeder_thread.join();
+    if (feed.failed.load()) return fail(LDPC_E_CUDA, "decode_host: the feeder thread failed");
     if (feeder_copies) stats.s_copy_out = feed.s_copy_out;
     stats.chunks_q8 = q8 ? stats.chunks_total : feed.chunks_q8;
     stats.chunks_unencodable = feed.chunks_unencodable;
