@@ -1195,11 +1195,11 @@ int decode_host_impl(const ldpc_decoder_t *dc, const void *src_host, bool q8, fl
                 if (back_lane) c = feed.claim_back();
                 break;                                   // c < 0: the list is empty
             }
-            // all slots but one may carry float32 chunks (with fewer in flight a slow feeder -- few host threads -- left gaps
-            // on PCIe: 21.5 M frames/s with one thread against 23.0 without packing); the last one waits for a packed chunk.
-            // Nothing from the back before the feeder's first (short) chunk either: the device would start later.
-            if (back_lane && prepared > 0 && back_in_flight < HOST_SLOTS - 1 && (c = feed.claim_back()) >= 0) break;
-            if (back_in_flight >= HOST_SLOTS - 1 && (spin & 63) == 63) {   // still in flight?
+            // two float32 chunks in flight keep the DMA engine busy (one copying, one queued); more would only queue in
+            // front of the packed ones (three in flight: 55.9 instead of 60.7 M frames/s on two GPUs).  Nothing from the
+            // back before the feeder's first (short) chunk either: the device would start later.
+            if (back_lane && prepared > 0 && back_in_flight < 2 && (c = feed.claim_back()) >= 0) break;
+            if (back_in_flight >= 2 && (spin & 63) == 63) {   // still in flight?
                 back_in_flight = 0;
                 for (int j = 0; j < HOST_SLOTS; ++j) {
                     if (slot_back[j] && cudaStreamQuery(h.st[j]) == cudaSuccess) slot_back[j] = false;
