@@ -277,3 +277,21 @@ def test_host_pool_survives_a_fork():
             "print(os.WEXITSTATUS(os.waitpid(pid, 0)[1]))" % ROOT)
     out = subprocess.run([sys.executable, "-W", "ignore", "-c", code], capture_output=True, text=True, timeout=120)
     assert out.stdout.strip() == "0", (out.stdout, out.stderr)
+
+
+def test_host_stats_struct_layout_matches_the_header(tmp_path):
+    """ldpc_host_stats_t as the C compiler lays it out == the ctypes mirror in _lib.HostStats (field by field)."""
+    import shutil
+    import subprocess
+    if shutil.which("gcc") is None:
+        pytest.skip("no gcc here")
+    fields = [name for name, _ in _lib.HostStats._fields_]
+    src = tmp_path / "layout.c"
+    src.write_text('#include <stdio.h>\n#include <stddef.h>\n#include "ldpc_b200.h"\nint main(void) {\n'
+                   + "".join(f'  printf("%zu\\n", offsetof(ldpc_host_stats_t, {f}));\n' for f in fields)
+                   + '  printf("%zu\\n", sizeof(ldpc_host_stats_t));\n  return 0;\n}\n')
+    exe = tmp_path / "layout"
+    subprocess.run(["gcc", "-I", os.path.join(ROOT, "include"), str(src), "-o", str(exe)], check=True)
+    got = [int(v) for v in subprocess.run([str(exe)], capture_output=True, text=True, check=True).stdout.split()]
+    want = [getattr(_lib.HostStats, f).offset for f in fields] + [ctypes.sizeof(_lib.HostStats)]
+    assert got == want
