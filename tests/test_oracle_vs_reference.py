@@ -78,3 +78,31 @@ def test_mc_fixture_reproduces(codes):
     with tempfile.TemporaryDirectory() as tmp:
         ref, _ = rd.compute_results(40, 2044, 1076, 20, sampling_type=2, cwd=tmp)
     assert np.array_equal(res[:3], ref[:3])
+
+
+def test_reference_rounds_twice_for_weights_like_0p9(codes):
+    """The constants of tests/test_gpu_parity.py (DOUBLE_ROUNDING_WEIGHTS): with these weights a product rounded ONCE into
+    the quantiser differs from the float32 product quantised afterwards.  The reference (numpy shim: float32 multiply, then
+    round(x * qk) / qk, Main_Functions.py:267-311, 475-494) does the latter, and so do both oracle restatements -- which is
+    what the CUDA kernels are held to (nms_device.cuh mul2_rn_unfused)."""
+    from oracle import c_oracle, nms_oracle as ob
+    proto = codes["graph/wimax/proto"].astype(int)
+    z, ps, pe, ss, se, _ = (int(v) for v in codes["graph/wimax/meta"])
+    T = 12
+    ws = [0.9, 0.85, 0.95, 0.8333333730697632, 0.9166666269302368, 1.0714285373687744]
+    w = {0: np.array([ws[t % 6] for t in range(T)], np.float32).reshape(T, 1),
+         1: np.array([ws[(t + 2) % 6] for t in range(T)], np.float32).reshape(T, 1),
+         2: np.array([ws[(t + 4) % 6] for t in range(T)], np.float32).reshape(T, 1)}
+    sharing = [3, 3, 3]
+    rd = ref_runner.ReferenceDecoder(proto, z, sharing, w, T, 2, 5, 20.0, (ps, pe), (ss, se), [3.0])
+    g = ob.OracleGraph(proto, z, (ps, pe), (ss, se))
+    X, _ = ob.create_mix_epoch(rd.snr_sigma, np.random.RandomState(15), np.random.RandomState(16), 40, g.N, z, 2,
+                               (ps, pe), (ss, se), 5, 20.0)
+    ref = rd.decode(X)["app"]
+    a = ob.decode(g, X, sharing, w, T, 2, 5, 20.0)["app"]
+    b = c_oracle.decode(proto, z, X, sharing, w, T, 2, 5, 20.0)["app"]
+    assert np.array_equal(a, ref) and np.array_equal(b, ref)
+    # and the fused form would NOT have matched: count the products where it differs (a float64 product of two float32 is exact)
+    k = np.arange(1, 16, dtype=np.float32) * np.float32(0.5)
+    p = k[:, None].astype(np.float64) * np.array(ws, np.float32)[None, :].astype(np.float64)
+    assert (np.rint(p * 2) != np.rint(np.float32(p).astype(np.float64) * 2)).sum() >= 6
